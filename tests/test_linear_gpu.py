@@ -1,0 +1,106 @@
+"""GPU parity of the tcgen05 GEMM + fused epilogues against a plain fp32 torch reference
+(inputs rounded to bf16 so both sides see identical operands; fp32 accumulate on both)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(m, n, k, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a = (torch.randn(m, k, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    w = (torch.randn(n, k, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    b = (torch.randn(n, generator=g) * 0.1).cuda()
+    return a, w, b
+
+
+def _ref(a, w, b):
+    return a.float() @ w.float().t() + b
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize(
+    "m,n,k",
+    [(128, 256, 64), (128, 256, 768), (6336, 768, 768), (6336, 2304, 768), (200, 3072, 784), (77, 512, 3072)],
+)
+def test_linear_bias_bf16(m, n, k, block_n):
+    from vitad import _lib, ops
+
+    a, w, b = _mk(m, n, k)
+    out = ops.linear(a, w, b, _lib.EPI_BIAS_BF16, block_n=block_n)
+    torch.cuda.synchronize()
+    ref = _ref(a, w, b)
+    err = (out.float() - ref).abs().max().item()
+    tol = 1e-2 * ref.abs().max().item()  # bf16 output rounding (2^-9 relative)
+    assert err <= tol, f"max abs err {err} > {tol}"
+
+
+def test_linear_f32_exactness():
+    """fp32 output: only accumulation-order differences remain (<= 1e-4 relative to row scale)."""
+    from vitad import _lib, ops
+
+    a, w, b = _mk(6272, 128, 768, seed=1)
+    out = ops.linear(a, w, b, _lib.EPI_F32)
+    torch.cuda.synchronize()
+    ref = _ref(a, w, b)
+    assert (out - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+def test_linear_gelu_and_residual():
+    from vitad import _lib, ops
+
+    a, w, b = _mk(6336, 3072, 768, seed=2)
+    out = ops.linear(a, w, b, _lib.EPI_BIAS_GELU_BF16)
+    ref = torch.nn.functional.gelu(_ref(a, w, b))
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+
+    a, w, b = _mk(6336, 768, 3072, seed=3)
+    resid = torch.randn(6336, 768, device="cuda")
+    ref = resid + _ref(a, w, b)
+    out = ops.linear(a, w, b, _lib.EPI_RESIDUAL_F32, out=resid, resid=resid)
+    torch.cuda.synchronize()
+    assert out.data_ptr() == resid.data_ptr()
+    assert (out - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+def test_linear_qkv_layout():
+    from vitad import ops
+
+    B, T, H, Tpad = 3, 198, 12, 256
+    a, w, b = _mk(B * T, 3 * H * 64, 768, seed=4)
+    q = torch.zeros(B, H, T, 64, device="cuda", dtype=torch.bfloat16)
+    k = torch.zeros_like(q)
+    vt = torch.zeros(B, H, 64, Tpad, device="cuda", dtype=torch.bfloat16)
+    ops.linear_qkv(a, w, b, B, T, H, Tpad, q, k, vt, 0.125)
+    torch.cuda.synchronize()
+    ref = _ref(a, w, b).reshape(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)  # [3,B,H,T,64]
+    tol = 1e-2 * ref.abs().max().item()
+    assert (q.float() - ref[0] * 0.125).abs().max().item() <= tol
+    assert (k.float() - ref[1]).abs().max().item() <= tol
+    assert (vt[..., :T].float() - ref[2].transpose(-1, -2)).abs().max().item() <= tol
+    assert vt[..., T:].abs().max().item() == 0
+
+
+def test_linear_patch_embed():
+    from vitad import ops
+
+    B, P, prefix, Cdim = 4, 196, 2, 768
+    a, w, b = _mk(B * P, Cdim, 768, seed=5)
+    pos = torch.randn(prefix + P, Cdim, device="cuda")
+    out = torch.zeros(B, prefix + P, Cdim, device="cuda")
+    ops.linear_patch_embed(a, w, b, pos, out, P, prefix)
+    torch.cuda.synchronize()
+    ref = _ref(a, w, b).reshape(B, P, Cdim) + pos[prefix:]
+    assert (out[:, prefix:] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    assert out[:, :prefix].abs().max().item() == 0
+
+
+def test_linear_rejects_bad_arguments():
+    from vitad import _lib, ops
+
+    a, w, b = _mk(128, 256, 64)
+    with pytest.raises(_lib.VitadError):
+        ops.linear(a[:, :40], w[:, :40], b, _lib.EPI_BIAS_BF16)  # K not a multiple of 16
+    with pytest.raises(RuntimeError):
+        ops.linear(a.cpu(), w.cpu(), b.cpu())  # no CPU path

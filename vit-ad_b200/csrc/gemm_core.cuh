@@ -1,0 +1,205 @@
+// Persistent, warp-specialised bf16 GEMM main loop for sm_100a:
+//   D[m][n] = sum_k A[m][k] * B[n][k]       (A: [M,K] row-major, B: [N,K] row-major = nn.Linear weight)
+// One CTA per SM, 192 threads:
+//   warp 0      TMA producer   (one lane issues cp.async.bulk.tensor for A and B k-blocks)
+//   warp 1      TMEM allocator + MMA issuer (one lane issues tcgen05.mma, commits to mbarriers)
+//   warps 2..5  epilogue       (tcgen05.ld accumulator -> registers -> Epi functor)
+// Pipelines: smem ring full/empty (TMA <-> MMA), two TMEM accumulator stages full/empty
+// (MMA <-> epilogue), static persistent tile schedule (tile += gridDim.x).
+//
+// A tile = 128 rows x (SUBTILES sub-blocks of BLOCK_N accumulator columns).  Sub-blocks of one
+// tile are processed back to back by the same CTA so an epilogue can carry per-row state across
+// them (the MDN head's online logsumexp over mixture chunks).
+#pragma once
+#include "ptx.cuh"
+
+namespace vitad {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kGemmThreads = 192;
+constexpr int kSmemBudget = 227 * 1024;
+
+template <int BLOCK_N>
+struct GemmSmem {
+    static constexpr int kABytes = kBlockM * kBlockK * 2;
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarrierBytes = 512;
+    static constexpr int kStages = (kSmemBudget - 1024 - kBarrierBytes) / kStageBytes > 8
+                                       ? 8
+                                       : (kSmemBudget - 1024 - kBarrierBytes) / kStageBytes;
+    static constexpr int kTotalBytes = kStages * kStageBytes + kBarrierBytes + 1024;
+    static_assert(kStages >= 2, "tile too large for shared memory");
+    static_assert(kBBytes % 1024 == 0, "B stage must keep 1024-byte alignment (BLOCK_N % 8 == 0)");
+};
+
+__host__ __device__ constexpr uint32_t tmem_cols_pow2(int n) {
+    return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u;
+}
+
+// Epi interface (all __device__):
+//   void tile_begin(int m_blk, int n_tile, int row)                      once per tile per thread
+//   void sub(int sub, int m_blk, int n_tile, int row, uint32_t taddr)    per sub-block; must issue all
+//        tcgen05.ld for this accumulator stage before returning (taddr has the lane base folded in)
+//   void tile_end(int m_blk, int n_tile, int row)
+template <int BLOCK_N, int SUBTILES, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
+               int num_n_tiles, int K, Epi epi) {
+    using S = GemmSmem<BLOCK_N>;
+    constexpr int kStages = S::kStages;
+    static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
+    static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
+    constexpr uint32_t kTmemCols = tmem_cols_pow2(2 * BLOCK_N);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * S::kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_m_blks = (M + kBlockM - 1) / kBlockM;
+    const int num_tiles = num_m_blks * num_n_tiles;
+    const int num_k16 = K / 16;
+    const int num_kb = (num_k16 + 3) / 4;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile % num_m_blks;
+                const int n_tile = tile / num_m_blks;
+                for (int sub = 0; sub < SUBTILES; ++sub) {
+                    const int n_row0 = (n_tile * SUBTILES + sub) * BLOCK_N;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+                        tma_load_2d(smem_a + stage * S::kABytes, &tma_a, &full_bar[stage], kb * kBlockK,
+                                    m_blk * kBlockM);
+                        tma_load_2d(smem_b + stage * S::kBBytes, &tma_b, &full_bar[stage], kb * kBlockK, n_row0);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int sub = 0; sub < SUBTILES; ++sub) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
+                        const uint32_t b_addr = smem_u32(smem_b + stage * S::kBBytes);
+                        const int nk = min(4, num_k16 - kb * 4);
+                        for (int k = 0; k < nk; ++k) {
+                            umma_bf16_ss(d_tmem, make_smem_desc_sw128(a_addr + k * 32),
+                                         make_smem_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else {
+        // Epilogue warps: TMEM lane quarter is fixed by warp id % 4.
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile % num_m_blks;
+            const int n_tile = tile / num_m_blks;
+            const int row = m_blk * kBlockM + row_in_tile;
+            epi.tile_begin(m_blk, n_tile, row);
+            for (int sub = 0; sub < SUBTILES; ++sub) {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+                epi.sub(sub, m_blk, n_tile, row, taddr);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+            epi.tile_end(m_blk, n_tile, row);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// Helper for plain epilogues: walk the BLOCK_N accumulator columns in chunks of 32 and hand each
+// chunk (as floats) to `f(col_in_block, v[32])`.  All lanes execute the tcgen05.ld.
+template <int BLOCK_N, class F>
+__device__ __forceinline__ void for_each_chunk32(uint32_t taddr, F&& f) {
+    static_assert(BLOCK_N % 32 == 0, "plain epilogues use 32-column chunks");
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + c, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        f(c, v);
+    }
+}
+
+}  // namespace vitad

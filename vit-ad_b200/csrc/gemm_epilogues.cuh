@@ -1,0 +1,199 @@
+// Epilogue functors for gemm_tc_kernel: each thread owns one accumulator row (one token) and
+// receives 32 consecutive fp32 columns at a time.
+#pragma once
+#include "gemm_core.cuh"
+
+namespace vitad {
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ void load_bias32(const float* __restrict__ bias, int col, float (&b)[32]) {
+    const float4* p = reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 t = __ldg(p + j);
+        b[4 * j + 0] = t.x;
+        b[4 * j + 1] = t.y;
+        b[4 * j + 2] = t.z;
+        b[4 * j + 3] = t.w;
+    }
+}
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
+    uint4* p = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        p[j] = u;
+    }
+}
+
+// out_bf16[row][col] = act(acc + bias[col]);  act = identity or exact-erf GELU (timm Mlp: nn.GELU()).
+template <int BLOCK_N, bool GELU>
+struct EpiBiasBf16 {
+    const float* bias;
+    __nv_bfloat16* out;
+    int ldo, M, N;
+    __device__ __forceinline__ void tile_begin(int, int, int) const {}
+    __device__ __forceinline__ void tile_end(int, int, int) const {}
+    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr) const {
+        const int n0 = n_tile * BLOCK_N;
+        for_each_chunk32<BLOCK_N>(taddr, [&](int c, float (&v)[32]) {
+            const int col = n0 + c;
+            if (row < M && col < N) {
+                float b[32];
+                load_bias32(bias, col, b);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = v[j] + b[j];
+                    v[j] = GELU ? gelu_erf(x) : x;
+                }
+                store_bf16x32(out + static_cast<size_t>(row) * ldo + col, v);
+            }
+        });
+    }
+};
+
+// out_f32[row][col] = resid_f32[row][col] + acc + bias[col]   (residual stream stays fp32; out may alias resid)
+template <int BLOCK_N>
+struct EpiResidualF32 {
+    const float* bias;
+    const float* resid;
+    float* out;
+    int ld, M, N;
+    __device__ __forceinline__ void tile_begin(int, int, int) const {}
+    __device__ __forceinline__ void tile_end(int, int, int) const {}
+    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr) const {
+        const int n0 = n_tile * BLOCK_N;
+        for_each_chunk32<BLOCK_N>(taddr, [&](int c, float (&v)[32]) {
+            const int col = n0 + c;
+            if (row < M && col < N) {
+                float b[32];
+                load_bias32(bias, col, b);
+                const float4* r = reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * ld + col);
+                float4* o = reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ld + col);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 t = r[j];
+                    t.x += v[4 * j + 0] + b[4 * j + 0];
+                    t.y += v[4 * j + 1] + b[4 * j + 1];
+                    t.z += v[4 * j + 2] + b[4 * j + 2];
+                    t.w += v[4 * j + 3] + b[4 * j + 3];
+                    o[j] = t;
+                }
+            }
+        });
+    }
+};
+
+// Fused QKV projection epilogue (timm Attention.qkv + reshape/permute):
+//   row = b*T + t, col = which*C + h*64 + e
+//   q[b][h][t][e] = (acc+bias) * scale   (scale = hd^-0.5 folded in; exact power of two for hd=64)
+//   k[b][h][t][e] =  acc+bias
+//   vt[b][h][e][t] = acc+bias            (V stored transposed, token index contiguous, padded to Tpad,
+//                                         so P@V reads a K-major B operand)
+template <int BLOCK_N>
+struct EpiQkv {
+    const float* bias;
+    __nv_bfloat16* q;
+    __nv_bfloat16* k;
+    __nv_bfloat16* vt;
+    int M, T, Tpad, H;  // tokens per image, padded token count, heads
+    float scale;
+    __device__ __forceinline__ void tile_begin(int, int, int) const {}
+    __device__ __forceinline__ void tile_end(int, int, int) const {}
+    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr) const {
+        const int C = H * 64;
+        const int n0 = n_tile * BLOCK_N;
+        const int b = row / T;
+        const int t = row - b * T;
+        for_each_chunk32<BLOCK_N>(taddr, [&](int c, float (&v)[32]) {
+            const int col = n0 + c;
+            if (row < M && col < 3 * C) {
+                float bb[32];
+                load_bias32(bias, col, bb);
+                const int which = col / C;
+                const int h = (col - which * C) >> 6;
+                const int e0 = col & 63;
+                const size_t bh = static_cast<size_t>(b) * H + h;
+                if (which == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (v[j] + bb[j]) * scale;
+                    store_bf16x32(q + (bh * T + t) * 64 + e0, v);
+                } else if (which == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] + bb[j];
+                    store_bf16x32(k + (bh * T + t) * 64 + e0, v);
+                } else {
+                    __nv_bfloat16* dst = vt + (bh * 64 + e0) * Tpad + t;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * Tpad] = __float2bfloat16_rn(v[j] + bb[j]);
+                }
+            }
+        });
+    }
+};
+
+// Patch-embed epilogue (timm PatchEmbed conv-as-GEMM + pos_embed add, prefix tokens skipped):
+//   row = b*P + p  ->  x[b][prefix + p][col] = acc + bias[col] + pos[prefix + p][col]
+template <int BLOCK_N>
+struct EpiPatchEmbed {
+    const float* bias;
+    const float* pos;  // [prefix+P, C]
+    float* out;        // [B, prefix+P, C]
+    int M, P, prefix, C;
+    __device__ __forceinline__ void tile_begin(int, int, int) const {}
+    __device__ __forceinline__ void tile_end(int, int, int) const {}
+    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr) const {
+        const int n0 = n_tile * BLOCK_N;
+        const int b = row / P;
+        const int p = row - b * P;
+        for_each_chunk32<BLOCK_N>(taddr, [&](int c, float (&v)[32]) {
+            const int col = n0 + c;
+            if (row < M && col < C) {
+                float bb[32];
+                load_bias32(bias, col, bb);
+                const float4* ps = reinterpret_cast<const float4*>(pos + static_cast<size_t>(prefix + p) * C + col);
+                float4* o = reinterpret_cast<float4*>(out + (static_cast<size_t>(b) * (prefix + P) + prefix + p) * C + col);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 t = __ldg(ps + j);
+                    t.x += v[4 * j + 0] + bb[4 * j + 0];
+                    t.y += v[4 * j + 1] + bb[4 * j + 1];
+                    t.z += v[4 * j + 2] + bb[4 * j + 2];
+                    t.w += v[4 * j + 3] + bb[4 * j + 3];
+                    o[j] = t;
+                }
+            }
+        });
+    }
+};
+
+// Plain fp32 output (+ optional bias): used by the MDN pi projection and by tests.
+template <int BLOCK_N>
+struct EpiBiasF32 {
+    const float* bias;  // may be null
+    float* out;
+    int ldo, M, N;
+    __device__ __forceinline__ void tile_begin(int, int, int) const {}
+    __device__ __forceinline__ void tile_end(int, int, int) const {}
+    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr) const {
+        const int n0 = n_tile * BLOCK_N;
+        for_each_chunk32<BLOCK_N>(taddr, [&](int c, float (&v)[32]) {
+            const int col = n0 + c;
+            if (row < M && col < N) {
+                float* o = out + static_cast<size_t>(row) * ldo + col;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (col + j < N) o[j] = v[j] + (bias ? __ldg(bias + col + j) : 0.0f);
+                }
+            }
+        });
+    }
+};
+
+}  // namespace vitad

@@ -1,0 +1,101 @@
+#include "host_util.cuh"
+
+#include <stdarg.h>
+
+#include <atomic>
+#include <mutex>
+
+namespace vitad {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols) {
+    auto enc = get_encode();
+    VITAD_REQUIRE(enc != nullptr, VITAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    VITAD_REQUIRE(aligned16(base) && (ld * 2) % 16 == 0, VITAD_ERR_ALIGN,
+                  "TMA operand needs a 16-byte aligned base and pitch (base=%p ld=%llu)", base,
+                  (unsigned long long)ld);
+    VITAD_REQUIRE(box_rows >= 1 && box_rows <= 256 && box_cols * 2 == 128, VITAD_ERR_SHAPE, "bad TMA box %ux%u",
+                  box_rows, box_cols);
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VITAD_REQUIRE(r == CUDA_SUCCESS, VITAD_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: CUresult %d", (int)r);
+    return VITAD_OK;
+}
+
+int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint64_t ld2, uint32_t box_rows, uint32_t box_cols) {
+    auto enc = get_encode();
+    VITAD_REQUIRE(enc != nullptr, VITAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    VITAD_REQUIRE(aligned16(base) && (ld * 2) % 16 == 0 && (ld2 * 2) % 16 == 0, VITAD_ERR_ALIGN,
+                  "TMA operand needs 16-byte aligned base and pitches");
+    VITAD_REQUIRE(box_rows >= 1 && box_rows <= 256 && box_cols * 2 == 128, VITAD_ERR_SHAPE, "bad TMA box %ux%u",
+                  box_rows, box_cols);
+    cuuint64_t gdim[3] = {cols, rows, d2};
+    cuuint64_t gstr[2] = {ld * 2, ld2 * 2};
+    cuuint32_t box[3] = {box_cols, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VITAD_REQUIRE(r == CUDA_SUCCESS, VITAD_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: CUresult %d", (int)r);
+    return VITAD_OK;
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
+int check_device_arch() {
+    static int major = -1;
+    if (major < 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+            major = -1;
+            set_error("no CUDA device available (this library has no CPU path)");
+            return VITAD_ERR_ARCH;
+        }
+    }
+    VITAD_REQUIRE(major == 10, VITAD_ERR_ARCH, "device compute capability %d.x is not sm_100 (B200)", major);
+    return VITAD_OK;
+}
+
+}  // namespace vitad
+
+extern "C" const char* vitad_last_error(void) { return vitad::g_err; }
+extern "C" int vitad_abi_version(void) { return 1; }
+extern "C" uint64_t vitad_launch_count(void) { return vitad::g_launches.load(); }

@@ -1,0 +1,48 @@
+// Host-side helpers shared by the C-ABI entry points: error codes, TMA tensor-map encoding
+// (driver entry point fetched through the runtime, no -lcuda link), launch checks.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vitad.h"
+
+namespace vitad {
+
+void set_error(const char* fmt, ...);
+
+#define VITAD_REQUIRE(cond, code, ...)       \
+    do {                                     \
+        if (!(cond)) {                       \
+            ::vitad::set_error(__VA_ARGS__); \
+            return (code);                   \
+        }                                    \
+    } while (0)
+
+#define VITAD_CUDA_OK(expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            ::vitad::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                               __LINE__);                                                        \
+            return VITAD_ERR_CUDA;                                                               \
+        }                                                                                        \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// 2-D bf16 row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols],
+// 128-byte swizzle (matches make_smem_desc_sw128).  Out-of-bounds box elements read as zero.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols = 64);
+// 3-D variant: [d2, rows, cols] with pitches ld (elements, rows) and ld2 (elements, slabs).
+int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint64_t ld2, uint32_t box_rows, uint32_t box_cols = 64);
+
+int device_sm_count();
+int check_device_arch();  // VITAD_OK only on compute capability 10.x
+
+}  // namespace vitad

@@ -1,0 +1,126 @@
+// vitad_linear_bf16: dispatch of the tcgen05 GEMM main loop with the encoder's fused epilogues.
+#include <atomic>
+
+#include "gemm_epilogues.cuh"
+#include "host_util.cuh"
+
+namespace vitad {
+extern std::atomic<uint64_t> g_launches;
+
+template <int BLOCK_N, class Epi>
+static int launch_gemm(const vitad_linear_args& a, const Epi& epi, cudaStream_t stream) {
+    using S = GemmSmem<BLOCK_N>;
+    CUtensorMap ta, tb;
+    int rc = make_tmap_bf16_2d(&ta, a.a, a.m, a.k, a.lda, kBlockM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tb, a.w, a.n, a.k, a.ldw, BLOCK_N);
+    if (rc) return rc;
+    auto kern = gemm_tc_kernel<BLOCK_N, 1, Epi>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VITAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
+        attr_set = true;
+    }
+    const int num_m = (a.m + kBlockM - 1) / kBlockM;
+    const int num_n = (a.n + BLOCK_N - 1) / BLOCK_N;
+    const int tiles = num_m * num_n;
+    const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+    kern<<<grid, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, a.m, num_n, a.k, epi);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+template <int BLOCK_N>
+static int dispatch_epilogue(const vitad_linear_args& a, cudaStream_t stream) {
+    switch (a.epilogue) {
+        case VITAD_EPI_BIAS_BF16: {
+            EpiBiasBf16<BLOCK_N, false> e{a.bias, static_cast<__nv_bfloat16*>(a.out), a.ldo, a.m, a.n};
+            return launch_gemm<BLOCK_N>(a, e, stream);
+        }
+        case VITAD_EPI_BIAS_GELU_BF16: {
+            EpiBiasBf16<BLOCK_N, true> e{a.bias, static_cast<__nv_bfloat16*>(a.out), a.ldo, a.m, a.n};
+            return launch_gemm<BLOCK_N>(a, e, stream);
+        }
+        case VITAD_EPI_RESIDUAL_F32: {
+            EpiResidualF32<BLOCK_N> e{a.bias, a.resid, static_cast<float*>(a.out), a.ldo, a.m, a.n};
+            return launch_gemm<BLOCK_N>(a, e, stream);
+        }
+        case VITAD_EPI_QKV: {
+            EpiQkv<BLOCK_N> e{a.bias,
+                              static_cast<__nv_bfloat16*>(a.q),
+                              static_cast<__nv_bfloat16*>(a.kmat),
+                              static_cast<__nv_bfloat16*>(a.vt),
+                              a.m,
+                              a.tokens,
+                              a.tokens_pad,
+                              a.heads,
+                              a.q_scale};
+            return launch_gemm<BLOCK_N>(a, e, stream);
+        }
+        case VITAD_EPI_PATCH_EMBED: {
+            EpiPatchEmbed<BLOCK_N> e{a.bias, a.pos, static_cast<float*>(a.out), a.m, a.patches, a.prefix, a.n};
+            return launch_gemm<BLOCK_N>(a, e, stream);
+        }
+        case VITAD_EPI_F32: {
+            EpiBiasF32<BLOCK_N> e{a.bias, static_cast<float*>(a.out), a.ldo, a.m, a.n};
+            return launch_gemm<BLOCK_N>(a, e, stream);
+        }
+        default:
+            set_error("unknown epilogue %d", a.epilogue);
+            return VITAD_ERR_ARG;
+    }
+}
+
+}  // namespace vitad
+
+extern "C" int vitad_linear_bf16(const vitad_linear_args* args, void* stream) {
+    using namespace vitad;
+    VITAD_REQUIRE(args != nullptr, VITAD_ERR_ARG, "null args");
+    const vitad_linear_args& a = *args;
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(a.a && a.w, VITAD_ERR_ARG, "null operand");
+    VITAD_REQUIRE(a.m > 0 && a.n > 0 && a.k > 0, VITAD_ERR_SHAPE, "empty GEMM %dx%dx%d", a.m, a.n, a.k);
+    VITAD_REQUIRE(a.k % 16 == 0, VITAD_ERR_SHAPE, "K=%d must be a multiple of 16", a.k);
+    VITAD_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0 && a.lda >= a.k && a.ldw >= a.k, VITAD_ERR_ALIGN,
+                  "pitches must be >= K and multiples of 8 elements (lda=%d ldw=%d)", a.lda, a.ldw);
+    if (a.epilogue == VITAD_EPI_F32) {
+        VITAD_REQUIRE(a.out && a.ldo >= a.n, VITAD_ERR_ARG, "bad fp32 output");
+    } else {
+        VITAD_REQUIRE(a.n % 32 == 0, VITAD_ERR_SHAPE, "N=%d must be a multiple of 32 for this epilogue", a.n);
+        VITAD_REQUIRE(a.bias && aligned16(a.bias), VITAD_ERR_ARG, "bias missing or misaligned");
+    }
+    switch (a.epilogue) {
+        case VITAD_EPI_BIAS_BF16:
+        case VITAD_EPI_BIAS_GELU_BF16:
+            VITAD_REQUIRE(a.out && aligned16(a.out) && a.ldo % 8 == 0 && a.ldo >= a.n, VITAD_ERR_ALIGN,
+                          "bf16 output must be 16-byte aligned with pitch %% 8 == 0");
+            break;
+        case VITAD_EPI_RESIDUAL_F32:
+            VITAD_REQUIRE(a.out && a.resid && aligned16(a.out) && aligned16(a.resid) && a.ldo % 4 == 0 &&
+                              a.ldo >= a.n,
+                          VITAD_ERR_ALIGN, "fp32 residual/output must be 16-byte aligned");
+            break;
+        case VITAD_EPI_QKV:
+            VITAD_REQUIRE(a.q && a.kmat && a.vt && aligned16(a.q) && aligned16(a.kmat), VITAD_ERR_ARG,
+                          "q/k/vt missing or misaligned");
+            VITAD_REQUIRE(a.heads > 0 && a.n == 3 * a.heads * 64 && a.tokens > 0 && a.m % a.tokens == 0 &&
+                              a.tokens_pad >= a.tokens,
+                          VITAD_ERR_SHAPE, "QKV epilogue needs N = 3*H*64 and M = B*T");
+            break;
+        case VITAD_EPI_PATCH_EMBED:
+            VITAD_REQUIRE(a.out && a.pos && aligned16(a.out) && aligned16(a.pos) && a.patches > 0 &&
+                              a.m % a.patches == 0 && a.prefix >= 0,
+                          VITAD_ERR_ARG, "patch-embed epilogue arguments");
+            break;
+        default:
+            break;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int bn = a.block_n == 0 ? (a.n % 256 == 0 || a.n > 1024 ? 256 : 128) : a.block_n;
+    if (bn == 256) return dispatch_epilogue<256>(a, s);
+    if (bn == 128) return dispatch_epilogue<128>(a, s);
+    set_error("block_n=%d unsupported (128 or 256)", bn);
+    return VITAD_ERR_SHAPE;
+}
