@@ -1,0 +1,215 @@
+"""CPU oracle for the vit-ad scoring path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A functional fp32 restatement (torch on CPU) of what the reference computes between
+``images.to(device)`` and the ``.cpu().numpy()`` calls of its validators.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may import it;
+the product package (vit-ad_b200/) never does.
+
+Pinning: the reference ships no tests or golden vectors, so this oracle is pinned against
+outputs of the reference's own Python classes run in the build container (``oracle/make_golden.py`` →
+``tests/golden/*.npz``; checked by ``tests/test_oracle_cpu.py``).  Two third-party pieces the reference
+imports are not vendored and not installable here — timm 0.6.13 (DeiT) and FrEIA 0.2 (AllInOneBlock);
+their arithmetic is restated from the published sources in ``oracle/shims`` and here, and DeiT is
+cross-checked against ``transformers.DeiTModel``.  For those two boundaries parity is pinned to the
+restatement, not to the original packages.
+
+All ``path:line`` citations are relative to the reference root.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+LOG_SQRT_2PI = 0.5 * math.log(2 * math.pi)
+
+
+# ----------------------------------------------------------------------------------------------
+# DeiT-B distilled 16/224 encoder  (src/classes/transformer/TransformerEncoder.py:145-173; timm 0.6.13)
+# ----------------------------------------------------------------------------------------------
+def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float) -> Tensor:
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def gelu_erf(x: Tensor) -> Tensor:
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def deit_block(sd: dict, pre: str, x: Tensor, heads: int = 12) -> Tensor:
+    """timm Block: x + attn(norm1(x)); x + mlp(norm2(x)).  LayerNorm eps 1e-6."""
+    B, N, C = x.shape
+    hd = C // heads
+    h = layer_norm(x, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-6)
+    qkv = h @ sd[pre + "attn.qkv.weight"].t() + sd[pre + "attn.qkv.bias"]
+    qkv = qkv.reshape(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = torch.softmax((q @ k.transpose(-2, -1)) * hd**-0.5, dim=-1)
+    o = (attn @ v).transpose(1, 2).reshape(B, N, C)
+    x = x + o @ sd[pre + "attn.proj.weight"].t() + sd[pre + "attn.proj.bias"]
+    h = layer_norm(x, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-6)
+    h = gelu_erf(h @ sd[pre + "mlp.fc1.weight"].t() + sd[pre + "mlp.fc1.bias"])
+    return x + h @ sd[pre + "mlp.fc2.weight"].t() + sd[pre + "mlp.fc2.bias"]
+
+
+def deit_forward(sd: dict, images: Tensor, block_index: int = 0, prefix: str = "deit.", depth: int = 12):
+    """EncoderDeit.forward (TransformerEncoder.py:145-173) → (patch_embedding [B,196,768], cls [B,768]).
+
+    block_index == 0: timm forward_features (all blocks, one final norm).  block_index != 0: blocks
+    0..block_index with the final norm applied after EVERY block (:161-163).
+    """
+    p = prefix
+    w = sd[p + "patch_embed.proj.weight"]  # [768,3,16,16]
+    B = images.shape[0]
+    ps = w.shape[-1]
+    g = images.shape[-1] // ps
+    # non-overlapping conv == per-patch GEMM; column order (c, i, j) as in the conv weight
+    patches = images.reshape(B, 3, g, ps, g, ps).permute(0, 2, 4, 1, 3, 5).reshape(B, g * g, 3 * ps * ps)
+    x = patches @ w.reshape(w.shape[0], -1).t() + sd[p + "patch_embed.proj.bias"]
+    x = torch.cat((sd[p + "cls_token"].expand(B, -1, -1), sd[p + "dist_token"].expand(B, -1, -1), x), dim=1)
+    x = x + sd[p + "pos_embed"]
+    if block_index != 0:
+        for i in range(block_index + 1):
+            x = deit_block(sd, f"{p}blocks.{i}.", x)
+            x = layer_norm(x, sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6)
+    else:
+        for i in range(depth):
+            x = deit_block(sd, f"{p}blocks.{i}.", x)
+        x = layer_norm(x, sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6)
+    return x[:, 2:, :], x[:, 0, :]
+
+
+# ----------------------------------------------------------------------------------------------
+# MDN / "GMM" head  (src/classes/MixtureDensityNetwork.py)
+# ----------------------------------------------------------------------------------------------
+def gumbel_noise(shape, generator: torch.Generator) -> Tensor:
+    """Same recipe as torch.nn.functional.gumbel_softmax: g = -log(Exp(1))."""
+    return -torch.empty(shape).exponential_(generator=generator).log()
+
+
+def mdn_log_pi(x: Tensor, sd: dict, gumbel: Tensor) -> Tensor:
+    """log(softmax(pi(x) + g) + 1e-15)   (MixtureDensityNetwork.py:62-64,164; tau = 1)."""
+    pi = x @ sd["pi.weight"].t() + sd["pi.bias"]
+    return torch.log(torch.softmax(pi + gumbel, dim=-1) + 1e-15)
+
+
+def mdn_patch_loglik(x: Tensor, sd: dict, gumbel: Tensor, token_chunk: int = 256) -> Tensor:
+    """L[b,p] = mean_d logsumexp_k( log_pi[b,p,k] + log N(x[b,p,d]; mu[b,p,d,k], sigma[b,p,d,k]) ).
+
+    forward (:151-171): sigma = ELU(W_s x + b_s) + 1 + 1e-15, mu = W_m x + b_m, viewed [B,P,D,K] (k fastest);
+    log_gaussian_density (:35-46); log_likelihood (:49-72); mean over features (:86-88).
+    Token-chunked so the [B,P,D,K] tensors are never materialised whole.
+    """
+    B, P, D = x.shape
+    K = sd["pi.weight"].shape[0]
+    log_pi = mdn_log_pi(x, sd, gumbel).reshape(B * P, K)
+    xf = x.reshape(B * P, D)
+    out = torch.empty(B * P, dtype=x.dtype)
+    ws, bs, wm, bm = sd["sigma.weight"], sd["sigma.bias"], sd["mu.weight"], sd["mu.bias"]
+    for s in range(0, B * P, token_chunk):
+        xc = xf[s : s + token_chunk]
+        sigma = (F.elu(xc @ ws.t() + bs) + 1 + 1e-15).view(-1, D, K)
+        mu = (xc @ wm.t() + bm).view(-1, D, K)
+        dens = -torch.log(sigma) - LOG_SQRT_2PI - 0.5 * torch.pow((xc.unsqueeze(-1) - mu) / sigma, 2)
+        ll = torch.logsumexp(log_pi[s : s + token_chunk].unsqueeze(1) + dens, dim=-1)  # [n, D]
+        out[s : s + token_chunk] = ll.mean(dim=1)
+    return out.view(B, P)
+
+
+def mdn_probability_map(L: Tensor) -> Tensor:
+    """get_probability_map tail (:90-95): subtract the BATCH-global max, exp."""
+    return torch.exp(L - L.max())
+
+
+def bilinear_upsample(x: Tensor, out_size: int, align_corners: bool) -> Tensor:
+    """Explicit bilinear interpolation of [N,1,h,w] → [N,1,S,S] with PyTorch's index conventions
+    (used at ValidatorMDN.py:150-158 with align_corners=True and NormalizingFlow.py:138-143 with False)."""
+    N, C, h, w = x.shape
+
+    def src_index(o: Tensor, in_size: int) -> tuple[Tensor, Tensor, Tensor]:
+        if align_corners:
+            scale = (in_size - 1) / (out_size - 1) if out_size > 1 else 0.0
+            s = o * scale
+        else:
+            scale = in_size / out_size
+            s = torch.clamp((o + 0.5) * scale - 0.5, min=0.0)
+        i0 = torch.clamp(s.floor().long(), max=in_size - 1)
+        i1 = torch.clamp(i0 + 1, max=in_size - 1)
+        lam = (s - i0.to(s.dtype)).to(x.dtype)
+        return i0, i1, lam
+
+    o = torch.arange(out_size, dtype=torch.float32)
+    y0, y1, ly = src_index(o, h)
+    x0, x1, lx = src_index(o, w)
+    top = x[:, :, y0][:, :, :, x0] * (1 - lx) + x[:, :, y0][:, :, :, x1] * lx
+    bot = x[:, :, y1][:, :, :, x0] * (1 - lx) + x[:, :, y1][:, :, :, x1] * lx
+    return top * (1 - ly).view(1, 1, -1, 1) + bot * ly.view(1, 1, -1, 1)
+
+
+def mdn_scores(prob: Tensor, img_size: int, patch_size: int):
+    """ValidatorMdn.valid_loop_transformer tail (src/pipeline/ValidatorMDN.py:133-172):
+    image score = 1 - amin_p(prob); pixel map = 1 - bilinear(prob as g×g, img_size, align_corners=True)."""
+    B = prob.shape[0]
+    g = int(img_size / patch_size)
+    image_scores = 1 - prob.amin(dim=1)
+    pixel = 1 - bilinear_upsample(prob.reshape(B, 1, g, g), img_size, align_corners=True)
+    return image_scores, pixel
+
+
+# ----------------------------------------------------------------------------------------------
+# Normalizing-flow head  (src/classes/NormalizingFlow.py; FrEIA 0.2 AllInOneBlock)
+# ----------------------------------------------------------------------------------------------
+def nf_forward(sd: dict, x: Tensor, flow_steps: int, img_size: int, clamp: float = 2.0):
+    """NormalizingFlow.forward (:118-145) → (loss [], anomaly_score_map [B,1,S,S], z, logdet).
+
+    Per step i (kernel 3 if i even else 1, :96-100):  x1,x2 = split(C - C//2, C//2); a = 0.1*subnet(x1);
+    s = clamp*tanh(a[:, :C//2]); y2 = x2*exp(s) + a[:, C//2:]; y = cat(x1,y2)*scale + offset with
+    scale = 0.1*softplus_{beta=.5}(global_scale); out[:, i] = y[:, perm[i]] (w_perm is a 0/1 matrix);
+    logdet += sum(s) + H*W*sum(log scale).  `layer_norm` exists in the state dict but is not applied (:124-125).
+    """
+    B, C, H, W = x.shape
+    c2 = C // 2
+    c1 = C - c2
+    logdet = torch.zeros(B, dtype=x.dtype)
+    for i in range(flow_steps):
+        p = f"fast_flow_decoder.module_list.{i}."
+        ksz = sd[p + "subnet.0.weight"].shape[-1]
+        x1, x2 = x[:, :c1], x[:, c1:]
+        h = F.relu(F.conv2d(x1, sd[p + "subnet.0.weight"], sd[p + "subnet.0.bias"], padding=ksz // 2))
+        a = 0.1 * F.conv2d(h, sd[p + "subnet.2.weight"], sd[p + "subnet.2.bias"], padding=ksz // 2)
+        s = clamp * torch.tanh(a[:, :c2])
+        y = torch.cat((x1, x2 * torch.exp(s) + a[:, c2:]), dim=1)
+        scale = 0.1 * F.softplus(sd[p + "global_scale"], beta=0.5)
+        y = y * scale + sd[p + "global_offset"]
+        perm = sd[p + "w_perm"].reshape(C, C).argmax(dim=1)  # row i has its single 1 at column perm[i]
+        x = y[:, perm]
+        logdet = logdet + s.sum(dim=(1, 2, 3)) + H * W * torch.log(scale).sum()
+    z = x
+    loss = torch.mean(0.5 * torch.sum(z**2, dim=(1, 2, 3)) - logdet)
+    prob = torch.exp(-0.5 * torch.mean(z**2, dim=1, keepdim=True))
+    amap = bilinear_upsample(1 - prob, img_size, align_corners=False)
+    return loss, amap, z, logdet
+
+
+def nf_scores(amap: Tensor) -> Tensor:
+    """ValidatorNF.valid_loop_transformer_nf (src/pipeline/ValidatorNF.py:137-142): amax over the map."""
+    return amap.amax(dim=(1, 2, 3))
+
+
+def tokens_to_nchw(tokens: Tensor) -> Tensor:
+    """ValidatorNF.py:130-134: [B,P,C] → [B,C,g,g]."""
+    B, P, C = tokens.shape
+    g = int(math.sqrt(P))
+    return tokens.transpose(2, 1).reshape(B, C, g, g)
+
+
+# ----------------------------------------------------------------------------------------------
+# Reconstruction head scoring tail  (src/classes/CnnAutoEncoder.py:49,68-74; ValidatorRecon.py:109-116)
+# ----------------------------------------------------------------------------------------------
+def recon_l2_scores(recon: Tensor, images: Tensor):
+    """MSELoss(reduction='none') → mean over channels (keepdim) → amax per image."""
+    amap = ((recon - images) ** 2).mean(dim=1, keepdim=True)
+    return amap.amax(dim=(1, 2, 3)), amap
