@@ -40,16 +40,16 @@ int vitad_abi_version(void);
 uint64_t vitad_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
- * Dense projection  D = A · Wᵀ (+ fused epilogue), bf16 operands, fp32 accumulate (tcgen05/TMEM,
+ * Dense projection  D = A · Wᵀ (+ fused epilogue), fp16 operands (IEEE half: same tensor-core rate as bf16, 3 more mantissa bits), fp32 accumulate (tcgen05/TMEM,
  * TMA-fed).  Replaces every nn.Linear / conv-as-GEMM on the encoder path:
  *   timm Attention.qkv / Attention.proj / Mlp.fc1 / Mlp.fc2 / PatchEmbed.proj, called through
  *   src/classes/transformer/TransformerEncoder.py:150-165 (EncoderDeit.forward).
- * A: [M,K] bf16 row-major (pitch lda elements), W: [N,K] bf16 row-major (nn.Linear layout).
+ * A: [M,K] fp16 row-major (pitch lda elements), W: [N,K] fp16 row-major (nn.Linear layout).
  * K % 16 == 0, N % 32 == 0 (N % 8 for VITAD_EPI_F32), pitches % 8 == 0.
  * ------------------------------------------------------------------------------------------ */
 typedef enum vitad_epilogue {
-    VITAD_EPI_BIAS_BF16 = 0,      /* out_bf16 = acc + bias                                  */
-    VITAD_EPI_BIAS_GELU_BF16 = 1, /* out_bf16 = gelu_erf(acc + bias)   (timm Mlp.act)       */
+    VITAD_EPI_BIAS_F16 = 0,      /* out_f16 = acc + bias                                  */
+    VITAD_EPI_BIAS_GELU_F16 = 1, /* out_f16 = gelu_erf(acc + bias)   (timm Mlp.act)       */
     VITAD_EPI_RESIDUAL_F32 = 2,   /* out_f32  = resid_f32 + acc + bias (timm Block residual) */
     VITAD_EPI_QKV = 3,            /* head-major q (pre-scaled), k, transposed v             */
     VITAD_EPI_PATCH_EMBED = 4,    /* + bias + pos_embed, written behind the prefix tokens   */
@@ -57,17 +57,17 @@ typedef enum vitad_epilogue {
 } vitad_epilogue;
 
 typedef struct vitad_linear_args {
-    const void* a;      /* bf16 [M,K] */
-    const void* w;      /* bf16 [N,K] */
+    const void* a;      /* fp16 [M,K] */
+    const void* w;      /* fp16 [N,K] */
     const float* bias;  /* fp32 [N]   */
     int m, n, k;
     int lda, ldw;       /* pitches in elements */
     int epilogue;       /* vitad_epilogue */
     int block_n;        /* 0 = library default, else 128 or 256 */
-    void* out;          /* bf16 or fp32 [M,ldo], see epilogue */
+    void* out;          /* fp16 or fp32 [M,ldo], see epilogue */
     int ldo;
     const float* resid; /* RESIDUAL_F32: fp32 [M,ldo] (may alias out) */
-    /* QKV: q,k bf16 [B,H,T,64]; vt bf16 [B,H,64,Tpad]; M = B*T, N = 3*H*64 */
+    /* QKV: q,k fp16 [B,H,T,64]; vt fp16 [B,H,64,Tpad]; M = B*T, N = 3*H*64 */
     void* q;
     void* kmat;
     void* vt;
@@ -78,7 +78,106 @@ typedef struct vitad_linear_args {
     int patches, prefix;
 } vitad_linear_args;
 
-int vitad_linear_bf16(const vitad_linear_args* args, void* stream);
+int vitad_linear_f16(const vitad_linear_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-wise encoder kernels (HBM-bound).
+ * vitad_layernorm: nn.LayerNorm over the last dim (timm Block.norm1/norm2 and VisionTransformer.norm,
+ *   eps 1e-6; Swin uses 1e-5).  x fp32 [*, c] with pitch ldx.  Output row r reads input row
+ *   (r / out_tokens) * in_tokens + skip + r % out_tokens, so the final norm can drop the prefix tokens
+ *   (x[:, 2:, :], TransformerEncoder.py:168).  out_f16 (pitch ld_f16) and/or out_f32 (pitch ld_f32).
+ *   aug_ones > 0: fp16 columns [c, c+aug_ones) = 1 and the rest of the pitch = 0 (MDN bias columns).
+ * vitad_patchify: images fp32 [B,C,S,S] -> fp16 [B*(S/P)^2, C*P*P], column order (c,i,j) = flattened
+ *   Conv2d weight (timm PatchEmbed.proj as a GEMM operand).
+ * vitad_prefix_tokens: x[b][t][:] = tokens[t] + pos[t] for t < prefix (cls, dist tokens).
+ * ------------------------------------------------------------------------------------------ */
+int vitad_layernorm(const float* x, const float* weight, const float* bias, void* out_f16, float* out_f32,
+                    int rows, int c, int ldx, int ld_f16, int ld_f32, int in_tokens, int out_tokens, int skip,
+                    float eps, int aug_ones, void* stream);
+int vitad_patchify(const float* images, void* out_f16, int batch, int channels, int size, int patch, void* stream);
+int vitad_prefix_tokens(const float* tokens, const float* pos, float* x, int batch, int prefix, int t, int c,
+                        void* stream);
+
+/* Fused softmax(Q K^T) V on tcgen05 (timm Attention.forward): q,k fp16 [B,H,T,64] (q pre-scaled),
+ * vt fp16 [B,H,64,tokens_pad] (zero beyond T), out fp16 [B*T, H*64].  T <= 208, head_dim 64. */
+int vitad_attention_f16(const void* q, const void* k, const void* vt, void* out, int batch, int heads, int tokens,
+                        int tokens_pad, int head_dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole DeiT-B distilled encoder forward = EncoderDeit.forward
+ * (src/classes/transformer/TransformerEncoder.py:145-173).  All weight pointers are device pointers;
+ * matrices are fp16 in nn.Linear layout [out,in] (patch_w = conv weight flattened to [dim, 3*P*P]),
+ * vectors fp32.  block_index follows the reference: 0 = all blocks + final norm; i != 0 = blocks 0..i
+ * with the final norm applied after every block.
+ *   out_tokens fp32 [B, P, dim] (= patch_embedding), out_cls fp32 [B, dim] (= latent_space, may be null),
+ *   out_xaug   fp16 [B*P, ld_xaug] (may be null): normalised tokens + two 1-columns, the MDN GEMM operand.
+ * ------------------------------------------------------------------------------------------ */
+#define VITAD_DEIT_MAX_DEPTH 24
+typedef struct vitad_deit_layer {
+    const float *ln1_w, *ln1_b;
+    const void* qkv_w;
+    const float* qkv_b;
+    const void* proj_w;
+    const float* proj_b;
+    const float *ln2_w, *ln2_b;
+    const void* fc1_w;
+    const float* fc1_b;
+    const void* fc2_w;
+    const float* fc2_b;
+} vitad_deit_layer;
+
+typedef struct vitad_deit_weights {
+    int img, patch, dim, heads, hidden, depth, tokens, prefix;
+    const void* patch_w;
+    const float* patch_b;
+    const float* prefix_tokens; /* [prefix, dim]: cls, dist */
+    const float* pos;           /* [tokens, dim] */
+    const float *norm_w, *norm_b;
+    const vitad_deit_layer* layers; /* host array of `depth` entries */
+} vitad_deit_weights;
+
+size_t vitad_deit_workspace_bytes(const vitad_deit_weights* w, int batch);
+int vitad_deit_forward(const vitad_deit_weights* w, const float* images, int batch, int block_index, void* workspace,
+                       size_t workspace_bytes, float* out_tokens, float* out_cls, void* out_xaug, int ld_xaug,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Mixture-density ("GMM") head: GaussianMixtureDensityNetwork.forward + log_likelihood +
+ * get_probability_map (src/classes/MixtureDensityNetwork.py:35-97,151-171) and the score tail of
+ * ValidatorMdn.valid_loop_transformer (src/pipeline/ValidatorMDN.py:133-172).
+ *   vitad_gmm_plan            mixture chunking used by the packed layouts (n_kc chunks of kc slots, kcv valid)
+ *   vitad_gmm_pack_weights    sigma/mu weights+biases (fp32, reference layout [dim*K, dim], k fastest) -> packed fp16
+ *   vitad_gmm_log_pi          lp2[t][slot] = log2(softmax(pi(x)+gumbel)+1e-15); gumbel fp32 [tokens,K] is an
+ *                             explicit input (the reference draws it inside gumbel_softmax, :62)
+ *   vitad_gmm_patch_loglik    L[t] = mean_d logsumexp_k(log pi + log N(x_d; mu_dk, sigma_dk))   (:49-72,:86-88)
+ *   vitad_gmm_finish          prob = exp(L - max over the whole batch) (:90-95); scores[b] = 1 - min_p prob
+ * ------------------------------------------------------------------------------------------ */
+int vitad_gmm_plan(int num_gaussians, int* n_kc, int* kc, int* kcv);
+size_t vitad_gmm_packed_weight_bytes(int dim, int num_gaussians);
+int vitad_gmm_pack_weights(const float* sigma_w, const float* sigma_b, const float* mu_w, const float* mu_b, int dim,
+                           int num_gaussians, void* packed, void* stream);
+/* xaug fp16 [tokens,784] = (fp16(x), 1, 1, 0...) from plain fp32 features x [tokens, ldx]. */
+int vitad_gmm_make_operand(const float* x, int ldx, void* xaug, int tokens, int dim, void* stream);
+int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, const float* pi_b, const float* gumbel, float* lp2,
+                     int tokens, int dim, int num_gaussians, void* stream);
+int vitad_gmm_patch_loglik(const void* xaug, const void* packed, const float* lp2, const float* x, int ldx,
+                           float* ll_ws, int ld_ws, float* L, int tokens, int dim, int num_gaussians, void* stream);
+int vitad_gmm_finish(const float* L, float* prob, float* scores, int batch, int patches, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Anomaly-map tails.
+ * vitad_bilinear_up: in fp32 [n,g,g] -> out fp32 [n,S,S], PyTorch bilinear semantics for both
+ *   align_corners settings; value = post(interp(pre(in))) with pre/post = optional (1 - v); image_max
+ *   (may be null) receives max over each produced map (maps are >= 0 on this path).
+ *     ValidatorMDN.py:137-162,171-172 -> align_corners=1, pre=0, post=1
+ *     NormalizingFlow.py:134-143 + ValidatorNF.py:137-142 -> align_corners=0, pre=1, post=0, image_max
+ * vitad_l2_map_score: map = mean_c (recon - x)^2, image_max = amax(map)
+ *     CnnAutoEncoder.py:49,68-74 (MSELoss 'none') + ValidatorRecon.py:109-116
+ * ------------------------------------------------------------------------------------------ */
+int vitad_bilinear_up(const float* in, float* out, float* image_max, int n, int grid_in, int size_out,
+                      int align_corners, int pre_one_minus, int post_one_minus, void* stream);
+int vitad_l2_map_score(const float* recon, const float* x, float* map, float* image_max, int n, int channels, int hw,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,125 @@
+"""GPU parity of the encoder kernels and of EncoderDeit.forward against the CPU oracle and the
+reference-generated golden fixtures.  Tolerances: the CUDA path rounds GEMM operands to fp16 (fp32
+accumulate, fp32 residual stream); the numbers below are ~4x the error predicted by
+tools/numerics_study.py for that design."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_layernorm_matches_torch():
+    from vitad import ops
+
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(6336, 768, generator=g) * 3 + 0.5).cuda()
+    w = (1 + 0.1 * torch.randn(768, generator=g)).cuda()
+    b = (0.1 * torch.randn(768, generator=g)).cuda()
+    ref = torch.nn.functional.layer_norm(x, (768,), w, b, 1e-6)
+    o16 = torch.empty(6336, 768, device="cuda", dtype=torch.float16)
+    o32 = torch.empty(6336, 768, device="cuda")
+    ops.layernorm(x, w, b, 1e-6, out_f16=o16, out_f32=o32)
+    torch.cuda.synchronize()
+    assert (o32 - ref).abs().max().item() <= 2e-5
+    assert (o16.float() - ref).abs().max().item() <= 4e-3
+
+
+def test_layernorm_token_remap_and_augmentation():
+    from vitad import ops
+
+    B, T, P = 3, 198, 196
+    x = torch.randn(B * T, 768, device="cuda")
+    w = torch.ones(768, device="cuda")
+    b = torch.zeros(768, device="cuda")
+    o16 = torch.full((B * P, 784), 7.0, device="cuda", dtype=torch.float16)
+    o32 = torch.empty(B * P, 768, device="cuda")
+    ops.layernorm(x, w, b, 1e-6, out_f16=o16, out_f32=o32, in_tokens=T, out_tokens=P, skip=2, aug_ones=2)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (768,), w, b, 1e-6).view(B, T, 768)[:, 2:].reshape(B * P, 768)
+    assert (o32 - ref).abs().max().item() <= 2e-5
+    assert (o16[:, :768].float() - ref).abs().max().item() <= 4e-3
+    assert (o16[:, 768:770] == 1).all() and (o16[:, 770:] == 0).all()
+
+
+def test_patchify_matches_unfold():
+    from vitad import ops
+
+    img = torch.rand(3, 3, 224, 224, device="cuda")
+    out = ops.patchify(img, 16)
+    ref = torch.nn.functional.unfold(img, kernel_size=16, stride=16).transpose(1, 2).reshape(3 * 196, 768)
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() <= 5e-4  # fp16 rounding of values in [0,1]
+
+
+@pytest.mark.parametrize("B,T", [(2, 198), (1, 198), (3, 130), (2, 49)])
+def test_attention_matches_torch(B, T):
+    from vitad import ops
+
+    H = 12
+    g = torch.Generator().manual_seed(T)
+    q = (torch.randn(B, H, T, 64, generator=g) * 0.5).half().cuda()
+    k = (torch.randn(B, H, T, 64, generator=g) * 1.0).half().cuda()
+    v = torch.randn(B, H, T, 64, generator=g).half().cuda()
+    vt = torch.zeros(B, H, 64, 256, device="cuda", dtype=torch.float16)
+    vt[..., :T] = v.transpose(-1, -2)
+    out = ops.attention(q, k, vt, T)
+    torch.cuda.synchronize()
+    attn = torch.softmax(q.float() @ k.float().transpose(-1, -2), dim=-1)
+    ref = (attn @ v.float()).transpose(1, 2).reshape(B * T, H * 64)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 4e-3, err
+
+
+def _run_deit(sd, images, block_index=0):
+    from vitad.encoders import EncoderDeit
+
+    enc = EncoderDeit(224)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.cuda().eval()
+    with torch.no_grad():
+        o = enc(images.cuda(), block_index=block_index)
+    torch.cuda.synchronize()
+    return o.patch_embedding.cpu(), o.latent_space.cpu(), o.patch_embedding._vitad_xaug.cpu()
+
+
+@pytest.mark.parametrize("tag,stress", [("default", False), ("stress", True)])
+@pytest.mark.parametrize("block_index", [0, 7])
+def test_deit_forward_matches_reference_golden(tag, stress, block_index):
+    from oracle import weights as W
+
+    g = golden("deit_b2")
+    sd = W.make_deit_state_dict(seed=11, stress=stress)
+    tok, cls, xaug = _run_deit(sd, W.synthetic_images(seed=3, batch=2), block_index)
+    k = f"{tag}_b{block_index}_"
+    # tokens are LayerNorm outputs (unit scale): absolute tolerance
+    assert np.abs(tok[:, ::14].numpy() - g[k + "tokens_sub"]).max() <= 1.5e-2
+    assert np.sqrt(np.mean((tok[:, ::14].numpy() - g[k + "tokens_sub"]) ** 2)) <= 2.5e-3
+    assert np.abs(cls.numpy() - g[k + "cls"]).max() <= 1.5e-2
+    assert np.abs(xaug[:, :768].float().view(2, 196, 768)[:, ::14].numpy() - g[k + "tokens_sub"]).max() <= 2e-2
+    assert (xaug[:, 768:770] == 1).all() and (xaug[:, 770:] == 0).all()
+
+
+def test_deit_forward_matches_oracle_batch_sizes():
+    """Ragged batch sizes (the reference loader has no drop_last): B=1 and B=5 against the CPU oracle."""
+    from oracle import vitad_oracle as O
+    from oracle import weights as W
+
+    sd = W.make_deit_state_dict(seed=12, stress=True)
+    for B in (1, 5):
+        imgs = W.synthetic_images(seed=20 + B, batch=B)
+        tok, cls, _ = _run_deit(sd, imgs)
+        with torch.no_grad():
+            rt, rc = O.deit_forward(sd, imgs)
+        assert (tok - rt).abs().max().item() <= 1.5e-2
+        assert (tok - rt).pow(2).mean().sqrt().item() <= 2.5e-3
+        assert (cls - rc).abs().max().item() <= 1.5e-2
+
+
+def test_encoder_rejects_cpu_input():
+    from vitad.encoders import EncoderDeit
+
+    with pytest.raises(RuntimeError):
+        EncoderDeit(224)(torch.rand(1, 3, 224, 224))

@@ -1,0 +1,134 @@
+"""GPU parity of the fused MDN/GMM head and its score tail against the CPU oracle and the
+reference-generated golden fixtures.  Parity metric for scores/maps: max |a-b| <= 1e-3 * max |b| over the
+batch (north_star's 1e-3 relative, measured against the batch's score range because the arg-max patch
+scores exactly 0)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, gumbel
+
+pytestmark = pytest.mark.gpu
+
+
+def _head(sd, K):
+    from vitad.mdn import GaussianMixtureDensityNetwork
+
+    m = GaussianMixtureDensityNetwork(768, 768, K)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("tag,stress", [("default", False), ("stress", True)])
+def test_gmm_head_k130_matches_reference_golden(tag, stress):
+    from oracle import weights as W
+    from vitad.mdn import get_probability_map, log_likelihood
+
+    g = golden("gmm_head_k130_p49")
+    head = _head(W.make_mdn_state_dict(seed=22, num_gaussians=130, stress=stress), 130)
+    x = torch.randn(3, 49, 768, generator=torch.Generator().manual_seed(9)).cuda()
+    gn = gumbel((3, 49, 130), 800).cuda()
+    with torch.no_grad():
+        r = head(x)
+        L = log_likelihood(x, r.pi, r.sigma, r.mu, gumbel=gn).cpu().numpy()
+        prob = get_probability_map(x, r.pi, r.sigma, r.mu, gumbel=gn).cpu().numpy()
+    spread = g[f"{tag}_L"].max() - g[f"{tag}_L"].min()
+    assert np.abs(L - g[f"{tag}_L"]).max() <= max(1e-3 * spread, 5e-5), (np.abs(L - g[f"{tag}_L"]).max(), spread)
+    assert np.abs(prob - g[f"{tag}_prob"]).max() <= 1e-3
+
+
+@pytest.mark.parametrize("K", [100, 130, 37])
+@pytest.mark.parametrize("B,P", [(2, 196), (1, 49), (5, 196)])
+def test_gmm_patch_loglik_matches_oracle(K, B, P):
+    from oracle import vitad_oracle as O
+    from oracle import weights as W
+
+    sd = W.make_mdn_state_dict(seed=K, num_gaussians=K, stress=True)
+    head = _head(sd, K)
+    x = torch.randn(B, P, 768, generator=torch.Generator().manual_seed(B * 1000 + P))
+    gn = gumbel((B, P, K), 5)
+    with torch.no_grad():
+        ref = O.mdn_patch_loglik(x, sd, gn)
+        L = head.patch_log_likelihood(x.cuda(), gn.cuda()).cpu()
+    spread = (ref.max() - ref.min()).item()
+    err = (L - ref).abs().max().item()
+    assert err <= max(1e-3 * spread, 5e-5), (err, spread)
+
+
+@pytest.mark.parametrize("tag,stress", [("default", False), ("stress", True)])
+def test_gmm_validator_path_matches_reference_golden(tag, stress):
+    """DeiT (CUDA) + GMM head (CUDA) + score tail (CUDA) vs ValidatorMdn.valid_loop_transformer run by the
+    reference: two batches (2 + 1 images)."""
+    from oracle import weights as W
+    from vitad import ops
+    from vitad.encoders import EncoderDeit
+
+    g = golden("gmm_validator_k100")
+    enc = EncoderDeit(224)
+    enc.load_state_dict(W.make_deit_state_dict(seed=11, stress=True))
+    enc = enc.cuda().eval()
+    head = _head(W.make_mdn_state_dict(seed=21, num_gaussians=100, stress=stress), 100)
+    imgs = W.synthetic_images(seed=5, batch=3)
+    scores, maps = [], []
+    with torch.no_grad():
+        for call, (s, e) in enumerate(((0, 2), (2, 3))):
+            f = enc(imgs[s:e].cuda())
+            prob, sc = head.score(f.patch_embedding, gumbel((e - s, 196, 100), 700 + call).cuda())
+            if call == 0:
+                L = head.patch_log_likelihood(f.patch_embedding, gumbel((2, 196, 100), 700).cuda()).cpu().numpy()
+                ref = g[f"{tag}_L_batch0"]
+                assert np.abs(L - ref).max() <= max(2e-3 * (ref.max() - ref.min()), 1e-4)
+            mp, _ = ops.bilinear_up(prob.view(-1, 14, 14), 224, align_corners=True, post_one_minus=True)
+            scores.append(sc.cpu())
+            maps.append(mp.cpu())
+    scores, maps = torch.cat(scores).numpy(), torch.cat(maps).numpy()
+    ref_s, ref_m = g[f"{tag}_image_scores"], g[f"{tag}_pixel_scores_sub"]
+    assert np.abs(scores - ref_s).max() <= 1e-3 * np.abs(ref_s).max(), (scores, ref_s)
+    assert np.abs(maps[:, :, ::8, ::8] - ref_m).max() <= 1e-3 * np.abs(ref_m).max()
+    np.testing.assert_allclose(maps.sum(axis=(1, 2, 3)), g[f"{tag}_pixel_scores_sum"], rtol=2e-3)
+
+
+def test_gmm_finish_and_upsample_match_oracle():
+    from oracle import vitad_oracle as O
+    from vitad import _lib, ops
+
+    L = torch.randn(7, 196, generator=torch.Generator().manual_seed(3)) * 0.3 - 900.0
+    prob = torch.empty(7, 196, device="cuda")
+    scores = torch.empty(7, device="cuda")
+    Lc = L.cuda()
+    _lib.check(_lib.lib.vitad_gmm_finish(Lc.data_ptr(), prob.data_ptr(), scores.data_ptr(), 7, 196,
+                                         torch.cuda.current_stream().cuda_stream))
+    rp = O.mdn_probability_map(L)
+    rs, rm = O.mdn_scores(rp, 224, 16)
+    mp, _ = ops.bilinear_up(prob.view(-1, 14, 14), 224, align_corners=True, post_one_minus=True)
+    torch.cuda.synchronize()
+    assert (prob.cpu() - rp).abs().max().item() <= 2e-6
+    assert (scores.cpu() - rs).abs().max().item() <= 2e-6
+    assert (mp.cpu() - rm).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("align", [True, False])
+@pytest.mark.parametrize("g_in", [14, 7])
+def test_bilinear_matches_torch_interpolate(align, g_in):
+    from vitad import ops
+
+    x = torch.rand(5, g_in, g_in, generator=torch.Generator().manual_seed(1)).cuda()
+    out, mx = ops.bilinear_up(x, 224, align_corners=align, want_max=True)
+    ref = torch.nn.functional.interpolate(x.unsqueeze(1), size=(224, 224), mode="bilinear", align_corners=align)
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() <= 2e-6
+    assert (mx - ref.amax(dim=(1, 2, 3))).abs().max().item() <= 2e-6
+
+
+def test_recon_l2_map_matches_reference_golden():
+    from vitad import ops
+
+    g = golden("recon_l2")
+    gen = torch.Generator().manual_seed(4)
+    images = torch.rand(3, 3, 224, 224, generator=gen)
+    recon = torch.tanh(torch.randn(3, 3, 224, 224, generator=gen))
+    amap, score = ops.l2_map_score(recon.cuda(), images.cuda())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(score.cpu().numpy(), g["image_scores"], rtol=1e-6)
+    np.testing.assert_allclose(amap.cpu().numpy()[:, :, ::8, ::8], g["map_sub"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(amap.sum(dim=(1, 2, 3)).cpu().numpy(), g["map_sum"], rtol=1e-5)

@@ -1,5 +1,5 @@
 """GPU parity of the tcgen05 GEMM + fused epilogues against a plain fp32 torch reference
-(inputs rounded to bf16 so both sides see identical operands; fp32 accumulate on both)."""
+(inputs rounded to fp16 so both sides see identical operands; fp32 accumulate on both)."""
 import pytest
 import torch
 
@@ -8,8 +8,8 @@ pytestmark = pytest.mark.gpu
 
 def _mk(m, n, k, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
-    a = (torch.randn(m, k, generator=g) * 0.5).to(torch.bfloat16).cuda()
-    w = (torch.randn(n, k, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    a = (torch.randn(m, k, generator=g) * 0.5).to(torch.float16).cuda()
+    w = (torch.randn(n, k, generator=g) * 0.05).to(torch.float16).cuda()
     b = (torch.randn(n, generator=g) * 0.1).cuda()
     return a, w, b
 
@@ -23,15 +23,15 @@ def _ref(a, w, b):
     "m,n,k",
     [(128, 256, 64), (128, 256, 768), (6336, 768, 768), (6336, 2304, 768), (200, 3072, 784), (77, 512, 3072)],
 )
-def test_linear_bias_bf16(m, n, k, block_n):
+def test_linear_bias_fp16(m, n, k, block_n):
     from vitad import _lib, ops
 
     a, w, b = _mk(m, n, k)
-    out = ops.linear(a, w, b, _lib.EPI_BIAS_BF16, block_n=block_n)
+    out = ops.linear(a, w, b, _lib.EPI_BIAS_F16, block_n=block_n)
     torch.cuda.synchronize()
     ref = _ref(a, w, b)
     err = (out.float() - ref).abs().max().item()
-    tol = 1e-2 * ref.abs().max().item()  # bf16 output rounding (2^-9 relative)
+    tol = 2e-3 * ref.abs().max().item()  # fp16 output rounding (2^-11 relative)
     assert err <= tol, f"max abs err {err} > {tol}"
 
 
@@ -50,7 +50,7 @@ def test_linear_gelu_and_residual():
     from vitad import _lib, ops
 
     a, w, b = _mk(6336, 3072, 768, seed=2)
-    out = ops.linear(a, w, b, _lib.EPI_BIAS_GELU_BF16)
+    out = ops.linear(a, w, b, _lib.EPI_BIAS_GELU_F16)
     ref = torch.nn.functional.gelu(_ref(a, w, b))
     torch.cuda.synchronize()
     assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
@@ -69,9 +69,9 @@ def test_linear_qkv_layout():
 
     B, T, H, Tpad = 3, 198, 12, 256
     a, w, b = _mk(B * T, 3 * H * 64, 768, seed=4)
-    q = torch.zeros(B, H, T, 64, device="cuda", dtype=torch.bfloat16)
+    q = torch.zeros(B, H, T, 64, device="cuda", dtype=torch.float16)
     k = torch.zeros_like(q)
-    vt = torch.zeros(B, H, 64, Tpad, device="cuda", dtype=torch.bfloat16)
+    vt = torch.zeros(B, H, 64, Tpad, device="cuda", dtype=torch.float16)
     ops.linear_qkv(a, w, b, B, T, H, Tpad, q, k, vt, 0.125)
     torch.cuda.synchronize()
     ref = _ref(a, w, b).reshape(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)  # [3,B,H,T,64]
@@ -101,6 +101,6 @@ def test_linear_rejects_bad_arguments():
 
     a, w, b = _mk(128, 256, 64)
     with pytest.raises(_lib.VitadError):
-        ops.linear(a[:, :40], w[:, :40], b, _lib.EPI_BIAS_BF16)  # K not a multiple of 16
+        ops.linear(a[:, :40], w[:, :40], b, _lib.EPI_BIAS_F16)  # K not a multiple of 16
     with pytest.raises(RuntimeError):
         ops.linear(a.cpu(), w.cpu(), b.cpu())  # no CPU path

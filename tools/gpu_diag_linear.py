@@ -9,8 +9,8 @@ torch.manual_seed(0)
 print("device", torch.cuda.get_device_name(0), "abi", _lib.lib.vitad_abi_version())
 for (m, n, k, bn) in [(128, 256, 64, 256), (128, 128, 64, 128), (256, 512, 128, 256), (6336, 768, 768, 256),
                       (6336, 2304, 768, 256), (6336, 3072, 768, 256), (6336, 768, 3072, 256), (6336, 768, 768, 128)]:
-    a = (torch.randn(m, k) * 0.5).to(torch.bfloat16).cuda()
-    w = (torch.randn(n, k) * 0.05).to(torch.bfloat16).cuda()
+    a = (torch.randn(m, k) * 0.5).to(torch.float16).cuda()
+    w = (torch.randn(n, k) * 0.05).to(torch.float16).cuda()
     b = (torch.randn(n) * 0.1).cuda()
     out = ops.linear(a, w, b, _lib.EPI_F32, block_n=bn)
     torch.cuda.synchronize()
@@ -24,12 +24,12 @@ for (m, n, k, bn) in [(128, 256, 64, 256), (128, 128, 64, 128), (256, 512, 128, 
               bad[:, 1].unique()[:10].tolist())
     # timing
     for _ in range(3):
-        ops.linear(a, w, b, _lib.EPI_BIAS_BF16, block_n=bn)
+        ops.linear(a, w, b, _lib.EPI_BIAS_F16, block_n=bn)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     iters = 20
     for _ in range(iters):
-        ops.linear(a, w, b, _lib.EPI_BIAS_BF16, block_n=bn)
+        ops.linear(a, w, b, _lib.EPI_BIAS_F16, block_n=bn)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters

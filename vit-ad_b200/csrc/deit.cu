@@ -1,0 +1,129 @@
+// vitad_deit_forward: the whole DeiT-B distilled 16/224 encoder forward as one C-ABI call
+// (EncoderDeit.forward, src/classes/transformer/TransformerEncoder.py:145-173; timm 0.6.13
+// VisionTransformerDistilled.forward_features).  Per block: LayerNorm -> QKV GEMM (head-major epilogue)
+// -> fused attention -> proj GEMM (+residual) -> LayerNorm -> fc1 GEMM (+GELU) -> fc2 GEMM (+residual).
+// The residual stream stays fp32 in HBM; GEMM operands are fp16.
+#include "host_util.cuh"
+
+extern "C" int vitad_layernorm(const float*, const float*, const float*, void*, float*, int, int, int, int, int, int,
+                               int, int, float, int, void*);
+extern "C" int vitad_patchify(const float*, void*, int, int, int, int, void*);
+extern "C" int vitad_prefix_tokens(const float*, const float*, float*, int, int, int, int, void*);
+extern "C" int vitad_attention_f16(const void*, const void*, const void*, void*, int, int, int, int, int, void*);
+
+namespace {
+constexpr int kTokPad = 256;  // key padding of the transposed-V buffer
+
+struct Carve {
+    uint8_t* p;
+    size_t used = 0;
+    void* take(size_t bytes) {
+        void* r = p ? p + used : nullptr;
+        used += (bytes + 255) & ~static_cast<size_t>(255);
+        return r;
+    }
+};
+
+struct DeitWs {
+    float* x;
+    void *h, *q, *k, *vt, *mlp, *patches;
+    size_t vt_bytes, total;
+};
+
+DeitWs carve_ws(const vitad_deit_weights& w, int batch, void* base) {
+    Carve c{static_cast<uint8_t*>(base)};
+    const size_t rows = static_cast<size_t>(batch) * w.tokens;
+    const int hd = w.dim / w.heads;
+    DeitWs s;
+    s.x = static_cast<float*>(c.take(rows * w.dim * 4));
+    s.h = c.take(rows * w.dim * 2);
+    s.q = c.take(rows * w.dim * 2);
+    s.k = c.take(rows * w.dim * 2);
+    s.vt_bytes = static_cast<size_t>(batch) * w.heads * hd * kTokPad * 2;
+    s.vt = c.take(s.vt_bytes);
+    s.mlp = c.take(rows * w.hidden * 2);
+    s.patches = c.take(static_cast<size_t>(batch) * (w.tokens - w.prefix) * 3 * w.patch * w.patch * 2);
+    s.total = c.used;
+    return s;
+}
+}  // namespace
+
+extern "C" size_t vitad_deit_workspace_bytes(const vitad_deit_weights* w, int batch) {
+    if (!w || batch <= 0) return 0;
+    return carve_ws(*w, batch, nullptr).total;
+}
+
+extern "C" int vitad_deit_forward(const vitad_deit_weights* wp, const float* images, int batch, int block_index,
+                                  void* workspace, size_t workspace_bytes, float* out_tokens, float* out_cls,
+                                  void* out_xaug, int ld_xaug, void* stream) {
+    using namespace vitad;
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(wp && images && workspace && out_tokens, VITAD_ERR_ARG, "null pointer");
+    const vitad_deit_weights& w = *wp;
+    VITAD_REQUIRE(w.dim == 768 && w.heads == 12 && w.patch == 16 && w.img % w.patch == 0 && w.depth >= 1 &&
+                      w.depth <= VITAD_DEIT_MAX_DEPTH && w.layers,
+                  VITAD_ERR_SHAPE, "unsupported DeiT geometry (dim %d heads %d patch %d depth %d)", w.dim, w.heads,
+                  w.patch, w.depth);
+    const int g = w.img / w.patch, P = g * g, T = P + w.prefix;
+    VITAD_REQUIRE(T == w.tokens && T <= 208, VITAD_ERR_SHAPE, "tokens=%d inconsistent with img/patch/prefix", w.tokens);
+    VITAD_REQUIRE(block_index >= 0 && block_index < w.depth, VITAD_ERR_SHAPE, "block_index %d out of range", block_index);
+    VITAD_REQUIRE(batch > 0, VITAD_ERR_SHAPE, "empty batch");
+    VITAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, VITAD_ERR_ALIGN, "workspace must be 256-byte aligned");
+    DeitWs ws = carve_ws(w, batch, workspace);
+    VITAD_REQUIRE(workspace_bytes >= ws.total, VITAD_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.total);
+    VITAD_REQUIRE(!out_xaug || ld_xaug >= w.dim + 16, VITAD_ERR_SHAPE, "xaug pitch");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int rows = batch * T, C = w.dim;
+
+    // patch embedding: gather patches -> GEMM with (+bias +pos_embed) epilogue into x[:, prefix:, :]
+    VITAD_CUDA_OK(cudaMemsetAsync(ws.vt, 0, ws.vt_bytes, s));
+    if ((rc = vitad_patchify(images, ws.patches, batch, 3, w.img, w.patch, s))) return rc;
+    vitad_linear_args a;
+    memset(&a, 0, sizeof(a));
+    a.a = ws.patches, a.w = w.patch_w, a.bias = w.patch_b;
+    a.m = batch * P, a.n = C, a.k = 3 * w.patch * w.patch, a.lda = a.k, a.ldw = a.k;
+    a.epilogue = VITAD_EPI_PATCH_EMBED, a.out = ws.x, a.ldo = C, a.pos = w.pos, a.patches = P, a.prefix = w.prefix;
+    if ((rc = vitad_linear_f16(&a, s))) return rc;
+    if ((rc = vitad_prefix_tokens(w.prefix_tokens, w.pos, ws.x, batch, w.prefix, T, C, s))) return rc;
+
+    const int last = block_index != 0 ? block_index : w.depth - 1;
+    for (int i = 0; i <= last; ++i) {
+        const vitad_deit_layer& L = w.layers[i];
+        if ((rc = vitad_layernorm(ws.x, L.ln1_w, L.ln1_b, ws.h, nullptr, rows, C, C, C, 0, rows, rows, 0, 1e-6f, 0, s)))
+            return rc;
+        memset(&a, 0, sizeof(a));
+        a.a = ws.h, a.w = L.qkv_w, a.bias = L.qkv_b, a.m = rows, a.n = 3 * C, a.k = C, a.lda = C, a.ldw = C;
+        a.epilogue = VITAD_EPI_QKV, a.q = ws.q, a.kmat = ws.k, a.vt = ws.vt;
+        a.tokens = T, a.tokens_pad = kTokPad, a.heads = w.heads, a.q_scale = 0.125f;
+        if ((rc = vitad_linear_f16(&a, s))) return rc;
+        if ((rc = vitad_attention_f16(ws.q, ws.k, ws.vt, ws.h, batch, w.heads, T, kTokPad, C / w.heads, s))) return rc;
+        memset(&a, 0, sizeof(a));
+        a.a = ws.h, a.w = L.proj_w, a.bias = L.proj_b, a.m = rows, a.n = C, a.k = C, a.lda = C, a.ldw = C;
+        a.epilogue = VITAD_EPI_RESIDUAL_F32, a.out = ws.x, a.resid = ws.x, a.ldo = C;
+        if ((rc = vitad_linear_f16(&a, s))) return rc;
+        if ((rc = vitad_layernorm(ws.x, L.ln2_w, L.ln2_b, ws.h, nullptr, rows, C, C, C, 0, rows, rows, 0, 1e-6f, 0, s)))
+            return rc;
+        memset(&a, 0, sizeof(a));
+        a.a = ws.h, a.w = L.fc1_w, a.bias = L.fc1_b, a.m = rows, a.n = w.hidden, a.k = C, a.lda = C, a.ldw = C;
+        a.epilogue = VITAD_EPI_BIAS_GELU_F16, a.out = ws.mlp, a.ldo = w.hidden;
+        if ((rc = vitad_linear_f16(&a, s))) return rc;
+        memset(&a, 0, sizeof(a));
+        a.a = ws.mlp, a.w = L.fc2_w, a.bias = L.fc2_b, a.m = rows, a.n = C, a.k = w.hidden, a.lda = w.hidden,
+        a.ldw = w.hidden;
+        a.epilogue = VITAD_EPI_RESIDUAL_F32, a.out = ws.x, a.resid = ws.x, a.ldo = C;
+        if ((rc = vitad_linear_f16(&a, s))) return rc;
+        // block_index != 0: the final norm is applied after EVERY block, in place (TransformerEncoder.py:161-163)
+        if (block_index != 0 && i < last)
+            if ((rc = vitad_layernorm(ws.x, w.norm_w, w.norm_b, nullptr, ws.x, rows, C, C, 0, C, rows, rows, 0, 1e-6f, 0, s)))
+                return rc;
+    }
+    // final norm straight into the outputs: patch tokens (prefix dropped, :168), MDN operand, cls token (:169)
+    if ((rc = vitad_layernorm(ws.x, w.norm_w, w.norm_b, out_xaug, out_tokens, batch * P, C, C, ld_xaug, C, T, P,
+                              w.prefix, 1e-6f, out_xaug ? 2 : 0, s)))
+        return rc;
+    if (out_cls)
+        if ((rc = vitad_layernorm(ws.x, w.norm_w, w.norm_b, nullptr, out_cls, batch, C, C, 0, C, T, 1, 0, 1e-6f, 0, s)))
+            return rc;
+    return VITAD_OK;
+}

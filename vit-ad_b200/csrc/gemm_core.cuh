@@ -1,4 +1,4 @@
-// Persistent, warp-specialised bf16 GEMM main loop for sm_100a:
+// Persistent, warp-specialised fp16-operand / fp32-accumulate GEMM main loop for sm_100a:
 //   D[m][n] = sum_k A[m][k] * B[n][k]       (A: [M,K] row-major, B: [N,K] row-major = nn.Linear weight)
 // One CTA per SM, 192 threads:
 //   warp 0      TMA producer   (one lane issues cp.async.bulk.tensor for A and B k-blocks)
@@ -16,7 +16,7 @@
 namespace vitad {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kBlockK = 64;  // 64 fp16 = 128 bytes = one swizzle row
 constexpr int kGemmThreads = 192;
 constexpr int kSmemBudget = 227 * 1024;
 
@@ -115,7 +115,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+            constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -132,7 +132,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const uint32_t b_addr = smem_u32(smem_b + stage * S::kBBytes);
                         const int nk = min(4, num_k16 - kb * 4);
                         for (int k = 0; k < nk; ++k) {
-                            umma_bf16_ss(d_tmem, make_smem_desc_sw128(a_addr + k * 32),
+                            umma_f16_ss(d_tmem, make_smem_desc_sw128(a_addr + k * 32),
                                          make_smem_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
@@ -162,6 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             epi.tile_begin(m_blk, n_tile, row);
             for (int sub = 0; sub < SUBTILES; ++sub) {
                 mbar_wait(&tmem_full[acc], acc_phase);
+                __syncwarp();
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
                 epi.sub(sub, m_blk, n_tile, row, taddr);

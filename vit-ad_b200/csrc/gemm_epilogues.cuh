@@ -19,24 +19,24 @@ __device__ __forceinline__ void load_bias32(const float* __restrict__ bias, int 
     }
 }
 
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
+__device__ __forceinline__ void store_h32(__half* dst, const float (&v)[32]) {
     uint4* p = reinterpret_cast<uint4*>(dst);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         uint4 u;
-        u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-        u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-        u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        u.x = pack_h2(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack_h2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_h2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_h2(v[8 * j + 6], v[8 * j + 7]);
         p[j] = u;
     }
 }
 
-// out_bf16[row][col] = act(acc + bias[col]);  act = identity or exact-erf GELU (timm Mlp: nn.GELU()).
+// out_f16[row][col] = act(acc + bias[col]);  act = identity or exact-erf GELU (timm Mlp: nn.GELU()).
 template <int BLOCK_N, bool GELU>
-struct EpiBiasBf16 {
+struct EpiBiasH {
     const float* bias;
-    __nv_bfloat16* out;
+    __half* out;
     int ldo, M, N;
     __device__ __forceinline__ void tile_begin(int, int, int) const {}
     __device__ __forceinline__ void tile_end(int, int, int) const {}
@@ -52,7 +52,7 @@ struct EpiBiasBf16 {
                     float x = v[j] + b[j];
                     v[j] = GELU ? gelu_erf(x) : x;
                 }
-                store_bf16x32(out + static_cast<size_t>(row) * ldo + col, v);
+                store_h32(out + static_cast<size_t>(row) * ldo + col, v);
             }
         });
     }
@@ -99,9 +99,9 @@ struct EpiResidualF32 {
 template <int BLOCK_N>
 struct EpiQkv {
     const float* bias;
-    __nv_bfloat16* q;
-    __nv_bfloat16* k;
-    __nv_bfloat16* vt;
+    __half* q;
+    __half* k;
+    __half* vt;
     int M, T, Tpad, H;  // tokens per image, padded token count, heads
     float scale;
     __device__ __forceinline__ void tile_begin(int, int, int) const {}
@@ -123,15 +123,15 @@ struct EpiQkv {
                 if (which == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = (v[j] + bb[j]) * scale;
-                    store_bf16x32(q + (bh * T + t) * 64 + e0, v);
+                    store_h32(q + (bh * T + t) * 64 + e0, v);
                 } else if (which == 1) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = v[j] + bb[j];
-                    store_bf16x32(k + (bh * T + t) * 64 + e0, v);
+                    store_h32(k + (bh * T + t) * 64 + e0, v);
                 } else {
-                    __nv_bfloat16* dst = vt + (bh * 64 + e0) * Tpad + t;
+                    __half* dst = vt + (bh * 64 + e0) * Tpad + t;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * Tpad] = __float2bfloat16_rn(v[j] + bb[j]);
+                    for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * Tpad] = to_h(v[j] + bb[j]);
                 }
             }
         });

@@ -30,7 +30,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     return fn;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+int make_tmap_f16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols) {
     auto enc = get_encode();
     VITAD_REQUIRE(enc != nullptr, VITAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -43,14 +43,14 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
     cuuint64_t gstr[1] = {ld * 2};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VITAD_REQUIRE(r == CUDA_SUCCESS, VITAD_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: CUresult %d", (int)r);
     return VITAD_OK;
 }
 
-int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld,
+int make_tmap_f16_3d(CUtensorMap* map, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint64_t ld2, uint32_t box_rows, uint32_t box_cols) {
     auto enc = get_encode();
     VITAD_REQUIRE(enc != nullptr, VITAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -62,7 +62,7 @@ int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d2, uint64_t 
     cuuint64_t gstr[2] = {ld * 2, ld2 * 2};
     cuuint32_t box[3] = {box_cols, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VITAD_REQUIRE(r == CUDA_SUCCESS, VITAD_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: CUresult %d", (int)r);

@@ -1,4 +1,4 @@
-// vitad_linear_bf16: dispatch of the tcgen05 GEMM main loop with the encoder's fused epilogues.
+// vitad_linear_f16: dispatch of the tcgen05 GEMM main loop with the encoder's fused epilogues.
 #include <atomic>
 
 #include "gemm_epilogues.cuh"
@@ -11,9 +11,9 @@ template <int BLOCK_N, class Epi>
 static int launch_gemm(const vitad_linear_args& a, const Epi& epi, cudaStream_t stream) {
     using S = GemmSmem<BLOCK_N>;
     CUtensorMap ta, tb;
-    int rc = make_tmap_bf16_2d(&ta, a.a, a.m, a.k, a.lda, kBlockM);
+    int rc = make_tmap_f16_2d(&ta, a.a, a.m, a.k, a.lda, kBlockM);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tb, a.w, a.n, a.k, a.ldw, BLOCK_N);
+    rc = make_tmap_f16_2d(&tb, a.w, a.n, a.k, a.ldw, BLOCK_N);
     if (rc) return rc;
     auto kern = gemm_tc_kernel<BLOCK_N, 1, Epi>;
     static bool attr_set = false;
@@ -34,12 +34,12 @@ static int launch_gemm(const vitad_linear_args& a, const Epi& epi, cudaStream_t 
 template <int BLOCK_N>
 static int dispatch_epilogue(const vitad_linear_args& a, cudaStream_t stream) {
     switch (a.epilogue) {
-        case VITAD_EPI_BIAS_BF16: {
-            EpiBiasBf16<BLOCK_N, false> e{a.bias, static_cast<__nv_bfloat16*>(a.out), a.ldo, a.m, a.n};
+        case VITAD_EPI_BIAS_F16: {
+            EpiBiasH<BLOCK_N, false> e{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n};
             return launch_gemm<BLOCK_N>(a, e, stream);
         }
-        case VITAD_EPI_BIAS_GELU_BF16: {
-            EpiBiasBf16<BLOCK_N, true> e{a.bias, static_cast<__nv_bfloat16*>(a.out), a.ldo, a.m, a.n};
+        case VITAD_EPI_BIAS_GELU_F16: {
+            EpiBiasH<BLOCK_N, true> e{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n};
             return launch_gemm<BLOCK_N>(a, e, stream);
         }
         case VITAD_EPI_RESIDUAL_F32: {
@@ -48,9 +48,9 @@ static int dispatch_epilogue(const vitad_linear_args& a, cudaStream_t stream) {
         }
         case VITAD_EPI_QKV: {
             EpiQkv<BLOCK_N> e{a.bias,
-                              static_cast<__nv_bfloat16*>(a.q),
-                              static_cast<__nv_bfloat16*>(a.kmat),
-                              static_cast<__nv_bfloat16*>(a.vt),
+                              static_cast<__half*>(a.q),
+                              static_cast<__half*>(a.kmat),
+                              static_cast<__half*>(a.vt),
                               a.m,
                               a.tokens,
                               a.tokens_pad,
@@ -74,7 +74,7 @@ static int dispatch_epilogue(const vitad_linear_args& a, cudaStream_t stream) {
 
 }  // namespace vitad
 
-extern "C" int vitad_linear_bf16(const vitad_linear_args* args, void* stream) {
+extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
     using namespace vitad;
     VITAD_REQUIRE(args != nullptr, VITAD_ERR_ARG, "null args");
     const vitad_linear_args& a = *args;
@@ -92,10 +92,10 @@ extern "C" int vitad_linear_bf16(const vitad_linear_args* args, void* stream) {
         VITAD_REQUIRE(a.bias && aligned16(a.bias), VITAD_ERR_ARG, "bias missing or misaligned");
     }
     switch (a.epilogue) {
-        case VITAD_EPI_BIAS_BF16:
-        case VITAD_EPI_BIAS_GELU_BF16:
+        case VITAD_EPI_BIAS_F16:
+        case VITAD_EPI_BIAS_GELU_F16:
             VITAD_REQUIRE(a.out && aligned16(a.out) && a.ldo % 8 == 0 && a.ldo >= a.n, VITAD_ERR_ALIGN,
-                          "bf16 output must be 16-byte aligned with pitch %% 8 == 0");
+                          "fp16 output must be 16-byte aligned with pitch %% 8 == 0");
             break;
         case VITAD_EPI_RESIDUAL_F32:
             VITAD_REQUIRE(a.out && a.resid && aligned16(a.out) && aligned16(a.resid) && a.ldo % 4 == 0 &&

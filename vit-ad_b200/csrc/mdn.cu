@@ -1,0 +1,446 @@
+// Mixture-density ("GMM") head, fused:  src/classes/MixtureDensityNetwork.py:35-97,151-171 and the
+// score tail of src/pipeline/ValidatorMDN.py:133-172.
+//
+// The reference materialises sigma and mu as two [B,P,768,K] fp32 tensors (1.9 GB each at B=32, K=100)
+// and then makes ~10 elementwise passes over them.  Here the two 768 -> 768*K projections run as ONE
+// tcgen05 GEMM per (128-token tile, feature d): the packed weight tile holds the K sigma rows and the K
+// mu rows of feature d side by side, so the accumulator tile in TMEM is [128 tokens x (sigma_k | mu_k)],
+// and the epilogue turns it straight into  LL[t,d] = logsumexp_k(log pi[t,k] + log N(x[t,d]; mu, sigma))
+// without sigma/mu ever leaving the SM.  Biases ride in two extra K columns (hi/lo fp16 split) of the
+// operands, so the epilogue starts from complete pre-activations.
+//
+// Packed layouts (mixtures are split into n_kc chunks of KCV = ceil(K/n_kc) valid + padding to KC):
+//   Wpk   fp16 [768][n_kc][2 (sigma,mu)][KC][KA=784]   cols 0..767 weight row (d*K+k), 768/769 bias hi/lo
+//   xaug  fp16 [M][KA]                                  cols 0..767 LayerNorm output, 768/769 = 1, rest 0
+//   lp2   fp32 [M][n_kc*KC]                             log2(softmax(pi+g)+1e-15); padding = -1e30
+#include <atomic>
+
+#include "gemm_core.cuh"
+#include "host_util.cuh"
+
+namespace vitad {
+extern std::atomic<uint64_t> g_launches;
+
+constexpr float kLog2eF = 1.4426950408889634f;
+constexpr float kLn2F = 0.6931471805599453f;
+constexpr float kHalfLog2Pi = 0.9189385332046727f;  // 0.5*log(2*pi)
+constexpr float kLog2SigmaFloor = -49.82892142331043f;  // log2(1e-15): sigma = ELU+1+1e-15 never goes below
+constexpr float kPadLogPi = -1e30f;
+constexpr int kMdnKA = 784;  // 768 + 16: K extent of the packed operands
+
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// Epilogue of the fused projection: per thread one token row, per tile one feature d.
+template <int KC>
+struct EpiMdn {
+    const float* lp2;
+    const float* x;
+    float* ll;  // [768][ldl]
+    int ldp, ldx, ldl, M;
+    float m_run, s_run, xv;
+
+    __device__ __forceinline__ void tile_begin(int, int d, int row) {
+        m_run = -INFINITY;
+        s_run = 0.f;
+        xv = row < M ? __ldg(x + static_cast<size_t>(row) * ldx + d) : 0.f;
+    }
+
+    template <int W>
+    __device__ __forceinline__ void chunk(const uint32_t* as, const uint32_t* am, const float* lp) {
+        float v[W];
+        float cm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const float a = __uint_as_float(as[j]);
+            // log2(sigma), sigma = ELU(a)+1:  a > 0 -> log2(1+a);  a <= 0 -> a*log2(e)   (one MUFU)
+            float t2 = lg2f(fmaxf(a, 0.f) + 1.f) + fminf(a, 0.f) * kLog2eF;
+            t2 = fmaxf(t2, kLog2SigmaFloor);
+            const float inv_s = ex2f(-t2);
+            const float z = (xv - __uint_as_float(am[j])) * inv_s;
+            v[j] = (lp[j] - t2) - (0.5f * kLog2eF) * z * z;
+            cm = fmaxf(cm, v[j]);
+        }
+        const float m_new = fmaxf(m_run, cm);
+        float acc = s_run * ex2f(m_run - m_new);
+#pragma unroll
+        for (int j = 0; j < W; ++j) acc += ex2f(v[j] - m_new);
+        s_run = acc;
+        m_run = m_new;
+    }
+
+    __device__ __forceinline__ void sub(int kc, int, int, int row, uint32_t taddr) {
+        const bool valid = row < M;
+        const float* lprow = lp2 + static_cast<size_t>(valid ? row : 0) * ldp + kc * KC;
+        constexpr int kFull = KC / 16;
+#pragma unroll 1
+        for (int c = 0; c < kFull; ++c) {
+            uint32_t as[16], am[16];
+            tmem_ld_x16(taddr + c * 16, as);
+            tmem_ld_x16(taddr + KC + c * 16, am);
+            float lp[16];
+            const float4* l4 = reinterpret_cast<const float4*>(lprow + c * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 t = __ldg(l4 + j);
+                lp[4 * j + 0] = t.x;
+                lp[4 * j + 1] = t.y;
+                lp[4 * j + 2] = t.z;
+                lp[4 * j + 3] = t.w;
+            }
+            tmem_ld_wait();
+            chunk<16>(as, am, lp);
+        }
+        if constexpr (KC % 16 == 8) {
+            uint32_t as[8], am[8];
+            tmem_ld_x8(taddr + kFull * 16, as);
+            tmem_ld_x8(taddr + KC + kFull * 16, am);
+            float lp[8];
+            const float4* l4 = reinterpret_cast<const float4*>(lprow + kFull * 16);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float4 t = __ldg(l4 + j);
+                lp[4 * j + 0] = t.x;
+                lp[4 * j + 1] = t.y;
+                lp[4 * j + 2] = t.z;
+                lp[4 * j + 3] = t.w;
+            }
+            tmem_ld_wait();
+            chunk<8>(as, am, lp);
+        }
+    }
+
+    __device__ __forceinline__ void tile_end(int, int d, int row) {
+        if (row < M) ll[static_cast<size_t>(d) * ldl + row] = (m_run + lg2f(s_run)) * kLn2F - kHalfLog2Pi;
+    }
+};
+
+// ------------------------------------------------------------------------------ weight packing
+__global__ void __launch_bounds__(256) gmm_pack_kernel(const float* __restrict__ ws, const float* __restrict__ bs,
+                                                       const float* __restrict__ wm, const float* __restrict__ bm,
+                                                       __half* __restrict__ wpk, int D, int K, int n_kc, int KC,
+                                                       int KCV, size_t total) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int col = static_cast<int>(idx % kMdnKA);
+    size_t r = idx / kMdnKA;
+    const int j = static_cast<int>(r % KC);
+    r /= KC;
+    const int which = static_cast<int>(r & 1);
+    r >>= 1;
+    const int kc = static_cast<int>(r % n_kc);
+    const int d = static_cast<int>(r / n_kc);
+    const int k = kc * KCV + j;
+    float val = 0.f;
+    if (j < KCV && k < K) {
+        const size_t src_row = static_cast<size_t>(d) * K + k;  // view(B,P,D,K): k fastest
+        const float* w = which ? wm : ws;
+        const float* b = which ? bm : bs;
+        if (col < D) {
+            val = w[src_row * D + col];
+        } else if (col == D) {
+            val = __half2float(__float2half_rn(b[src_row]));
+        } else if (col == D + 1) {
+            const float hi = __half2float(__float2half_rn(b[src_row]));
+            val = b[src_row] - hi;
+        }
+    }
+    wpk[idx] = __float2half_rn(val);
+}
+
+// xaug[t][:] = (fp16(x[t][0..D)), 1, 1, 0...) for callers that hand the head plain fp32 features
+// (the encoder's final LayerNorm emits this operand directly on the fast path).
+__global__ void __launch_bounds__(256) gmm_operand_kernel(const float* __restrict__ x, int ldx,
+                                                          __half* __restrict__ xaug, int M, int D) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // 4 columns per thread
+    const int per_row = kMdnKA / 4;
+    if (idx >= static_cast<size_t>(M) * per_row) return;
+    const size_t t = idx / per_row;
+    const int c = static_cast<int>(idx - t * per_row) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < D)
+        v = *reinterpret_cast<const float4*>(x + t * ldx + c);
+    else if (c == D)
+        v.x = 1.f, v.y = 1.f;
+    uint2 u;
+    u.x = pack_h2(v.x, v.y);
+    u.y = pack_h2(v.z, v.w);
+    *reinterpret_cast<uint2*>(xaug + t * kMdnKA + c) = u;
+}
+
+// ---------------------------------------------------------------------------- mixing weights
+// lp2[t][kmap(k)] = log2( softmax_k(x[t].Wpi[k] + bpi[k] + g[t][k]) + 1e-15 )   — fp32 on CUDA cores: the
+// logits enter every feature's logsumexp with the same sign, so they need better than fp16-GEMM accuracy.
+// CTA = 32 tokens x up to 160 mixtures; 256 threads, thread (ty,tx) accumulates tokens ty*4..+3 x mixtures tx+32*j.
+constexpr int kPiBM = 32, kPiBK = 32, kPiMaxK = 160;
+__global__ void __launch_bounds__(256) gmm_logpi_kernel(const float* __restrict__ x, int ldx,
+                                                        const float* __restrict__ wpi, const float* __restrict__ bpi,
+                                                        const float* __restrict__ gumbel, float* __restrict__ lp2,
+                                                        int M, int D, int K, int n_kc, int KC, int KCV) {
+    __shared__ float xs[kPiBM][kPiBK + 1];
+    __shared__ float wsh[kPiMaxK][kPiBK + 1];
+    __shared__ float logit[kPiBM][kPiMaxK + 1];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int m0 = blockIdx.x * kPiBM;
+    float acc[4][5];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < D; k0 += kPiBK) {
+        for (int i = threadIdx.x; i < kPiBM * kPiBK; i += 256) {
+            const int r = i / kPiBK, c = i % kPiBK;
+            xs[r][c] = (m0 + r < M) ? x[static_cast<size_t>(m0 + r) * ldx + k0 + c] : 0.f;
+        }
+        for (int i = threadIdx.x; i < kPiMaxK * kPiBK; i += 256) {
+            const int r = i / kPiBK, c = i % kPiBK;
+            wsh[r][c] = (r < K) ? wpi[static_cast<size_t>(r) * D + k0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < kPiBK; ++k) {
+            float xv[4], wv[5];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = xs[ty * 4 + i][k];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) wv[j] = wsh[tx + 32 * j][k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) logit[ty * 4 + i][tx + 32 * j] = acc[i][j];
+    __syncthreads();
+    // softmax + log per token: warp ty handles tokens ty*4..+3
+    const int ldp = n_kc * KC;
+    for (int i = 0; i < 4; ++i) {
+        const int r = ty * 4 + i;
+        const int t = m0 + r;
+        if (t >= M) break;
+        float z[5];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int k = tx + 32 * j;
+            z[j] = (k < K) ? logit[r][k] + bpi[k] + gumbel[static_cast<size_t>(t) * K + k] : -INFINITY;
+            mx = fmaxf(mx, z[j]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float e[5], sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            e[j] = (tx + 32 * j < K) ? expf(z[j] - mx) : 0.f;
+            sum += e[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        float* dst = lp2 + static_cast<size_t>(t) * ldp;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int k = tx + 32 * j;
+            if (k < K) {
+                const int kc = k / KCV;
+                dst[kc * KC + (k - kc * KCV)] = log2f(e[j] / sum + 1e-15f);
+            }
+        }
+        // padding slots of this row
+        for (int s = tx; s < ldp; s += 32) {
+            const int kc = s / KC, j = s - kc * KC;
+            if (j >= KCV || kc * KCV + j >= K) dst[s] = kPadLogPi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- score tail
+// L[t] = mean_d LL[d][t]   (torch.mean over features, MixtureDensityNetwork.py:86-88); fixed summation order.
+__global__ void __launch_bounds__(256) gmm_mean_kernel(const float* __restrict__ ll, int ldl, float* __restrict__ L,
+                                                       int M, int D) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int d = 0;
+    for (; d + 3 < D; d += 4) {
+        s0 += ll[static_cast<size_t>(d) * ldl + t];
+        s1 += ll[static_cast<size_t>(d + 1) * ldl + t];
+        s2 += ll[static_cast<size_t>(d + 2) * ldl + t];
+        s3 += ll[static_cast<size_t>(d + 3) * ldl + t];
+    }
+    for (; d < D; ++d) s0 += ll[static_cast<size_t>(d) * ldl + t];
+    L[t] = ((s0 + s1) + (s2 + s3)) / D;
+}
+
+// One CTA: batch-global max (MixtureDensityNetwork.py:90-92), prob = exp(L - max) (:93-95),
+// image score = 1 - min_p prob (ValidatorMDN.py:133,170).
+__global__ void __launch_bounds__(1024) gmm_finish_kernel(const float* __restrict__ L, float* __restrict__ prob,
+                                                          float* __restrict__ scores, int B, int P) {
+    __shared__ float red[32];
+    __shared__ float gmax;
+    const int M = B * P;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) mx = fmaxf(mx, L[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (threadIdx.x == 0) gmax = v;
+    }
+    __syncthreads();
+    const float g = gmax;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) prob[i] = expf(L[i] - g);
+    // per-image min over patches: one warp per image
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = warp; b < B; b += (blockDim.x >> 5)) {
+        float mn = INFINITY;
+        for (int p = lane; p < P; p += 32) mn = fminf(mn, expf(L[b * P + p] - g));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (lane == 0) scores[b] = 1.0f - mn;
+    }
+}
+
+template <int KC, int NKC>
+static int launch_mdn(const void* xaug, const void* wpk, const float* lp2, const float* x, int ldx, float* ll, int ldl,
+                      int M, int D, cudaStream_t stream) {
+    constexpr int BN = 2 * KC;
+    using S = GemmSmem<BN>;
+    using Epi = EpiMdn<KC>;
+    CUtensorMap ta, tb;
+    int rc = make_tmap_f16_2d(&ta, xaug, M, kMdnKA, kMdnKA, kBlockM);
+    if (rc) return rc;
+    rc = make_tmap_f16_2d(&tb, wpk, static_cast<uint64_t>(D) * NKC * BN, kMdnKA, kMdnKA, BN);
+    if (rc) return rc;
+    auto kern = gemm_tc_kernel<BN, NKC, Epi>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VITAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
+        attr_set = true;
+    }
+    Epi epi{lp2, x, ll, NKC * KC, ldx, ldl, M, 0.f, 0.f, 0.f};
+    const int num_m = (M + kBlockM - 1) / kBlockM;
+    const int tiles = num_m * D;
+    const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+    kern<<<grid, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, M, D, kMdnKA, epi);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+}  // namespace vitad
+
+using namespace vitad;
+
+extern "C" int vitad_gmm_plan(int num_gaussians, int* n_kc, int* kc, int* kcv) {
+    VITAD_REQUIRE(n_kc && kc && kcv, VITAD_ERR_ARG, "null pointer");
+    VITAD_REQUIRE(num_gaussians >= 1 && num_gaussians <= 144, VITAD_ERR_SHAPE,
+                  "num_gaussians=%d unsupported (1..144)", num_gaussians);
+    if (num_gaussians <= 112) {
+        *n_kc = 1, *kc = 112, *kcv = num_gaussians;
+    } else {
+        *n_kc = 2, *kc = 72, *kcv = (num_gaussians + 1) / 2;
+    }
+    return VITAD_OK;
+}
+
+extern "C" size_t vitad_gmm_packed_weight_bytes(int dim, int num_gaussians) {
+    int n_kc, kc, kcv;
+    if (vitad_gmm_plan(num_gaussians, &n_kc, &kc, &kcv)) return 0;
+    return static_cast<size_t>(dim) * n_kc * 2 * kc * kMdnKA * sizeof(__half);
+}
+
+extern "C" int vitad_gmm_pack_weights(const float* sigma_w, const float* sigma_b, const float* mu_w, const float* mu_b,
+                                      int dim, int num_gaussians, void* packed, void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(sigma_w && sigma_b && mu_w && mu_b && packed, VITAD_ERR_ARG, "null pointer");
+    VITAD_REQUIRE(dim == 768, VITAD_ERR_SHAPE, "dim=%d unsupported (768)", dim);
+    int n_kc, kc, kcv;
+    rc = vitad_gmm_plan(num_gaussians, &n_kc, &kc, &kcv);
+    if (rc) return rc;
+    const size_t total = static_cast<size_t>(dim) * n_kc * 2 * kc * kMdnKA;
+    gmm_pack_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        sigma_w, sigma_b, mu_w, mu_b, static_cast<__half*>(packed), dim, num_gaussians, n_kc, kc, kcv, total);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+extern "C" int vitad_gmm_make_operand(const float* x, int ldx, void* xaug, int tokens, int dim, void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(x && xaug && tokens > 0, VITAD_ERR_ARG, "null pointer");
+    VITAD_REQUIRE(dim == 768 && ldx % 4 == 0 && aligned16(x) && aligned16(xaug), VITAD_ERR_ALIGN,
+                  "dim must be 768 and x 16-byte aligned with pitch %% 4 == 0");
+    const size_t total = static_cast<size_t>(tokens) * (kMdnKA / 4);
+    gmm_operand_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ldx, static_cast<__half*>(xaug), tokens, dim);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+extern "C" int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, const float* pi_b, const float* gumbel,
+                                float* lp2, int tokens, int dim, int num_gaussians, void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(x && pi_w && pi_b && gumbel && lp2, VITAD_ERR_ARG, "null pointer");
+    VITAD_REQUIRE(dim % kPiBK == 0 && tokens > 0, VITAD_ERR_SHAPE, "dim %% 32 != 0 or no tokens");
+    int n_kc, kc, kcv;
+    rc = vitad_gmm_plan(num_gaussians, &n_kc, &kc, &kcv);
+    if (rc) return rc;
+    gmm_logpi_kernel<<<(tokens + kPiBM - 1) / kPiBM, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, num_gaussians, n_kc, kc, kcv);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+// xaug fp16 [tokens,784]; packed from vitad_gmm_pack_weights; lp2 from vitad_gmm_log_pi; x fp32 [tokens,ldx];
+// ll_ws fp32 workspace [768][ld_ws] with ld_ws >= tokens; L fp32 [tokens] = mean_d logsumexp_k(...).
+extern "C" int vitad_gmm_patch_loglik(const void* xaug, const void* packed, const float* lp2, const float* x, int ldx,
+                                      float* ll_ws, int ld_ws, float* L, int tokens, int dim, int num_gaussians,
+                                      void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(xaug && packed && lp2 && x && ll_ws && L, VITAD_ERR_ARG, "null pointer");
+    VITAD_REQUIRE(dim == 768 && tokens > 0 && ld_ws >= tokens, VITAD_ERR_SHAPE, "dim=%d tokens=%d ld_ws=%d", dim,
+                  tokens, ld_ws);
+    VITAD_REQUIRE(aligned16(lp2), VITAD_ERR_ALIGN, "lp2 alignment");
+    int n_kc, kc, kcv;
+    rc = vitad_gmm_plan(num_gaussians, &n_kc, &kc, &kcv);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n_kc == 1)
+        rc = launch_mdn<112, 1>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
+    else
+        rc = launch_mdn<72, 2>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
+    if (rc) return rc;
+    gmm_mean_kernel<<<(tokens + 255) / 256, 256, 0, s>>>(ll_ws, ld_ws, L, tokens, dim);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+// L fp32 [batch*patches] -> prob fp32 [batch*patches] (exp(L - max over the whole batch)), scores fp32 [batch].
+extern "C" int vitad_gmm_finish(const float* L, float* prob, float* scores, int batch, int patches, void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(L && prob && scores && batch > 0 && patches > 0, VITAD_ERR_ARG, "gmm_finish args");
+    gmm_finish_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(L, prob, scores, batch, patches);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}

@@ -4,7 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -102,8 +102,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, one elected thread issues.
-__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 x fp16 -> fp32, one elected thread issues.
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -118,14 +118,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
-// Instruction descriptor for kind::f16, bf16 A/B (both K-major), fp32 accumulate, tile M x N.
-// Field layout: see SURVEY/DESIGN; c_format[4,6) a_format[7,10) b_format[10,13) n>>3 [17,23) m>>4 [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+// Instruction descriptor for kind::f16, fp16 A/B (both K-major), fp32 accumulate, tile M x N.
+// Field layout: c_format[4,6)=1 (f32)  a_format[7,10)=0 (f16)  b_format[10,13)=0 (f16)  n>>3 [17,23)  m>>4 [24,29).
+// Operands are IEEE fp16, not bf16: same tensor-core rate, 3 more mantissa bits (numerics).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) |
            (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-// Shared-memory matrix descriptor, K-major operand stored as rows of 128 bytes (64 bf16) with the
+// Shared-memory matrix descriptor, K-major operand stored as rows of 128 bytes (64 fp16) with the
 // 128-byte swizzle TMA writes; 8-row groups are 1024 bytes apart (SBO). `addr` is the byte address
 // of the first row (1024-aligned tile base + k*32 bytes for the k-th 16-element slice).
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t addr) {
@@ -174,9 +175,17 @@ __device__ __forceinline__ float lg2f(float x) {
     return y;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+// Two floats -> packed fp16x2 (lo in bits [0,16)), round-to-nearest, saturating to +-65504.
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ __half to_h(float x) {
+    uint32_t r = pack_h2(x, 0.0f);
+    __half_raw h;
+    h.x = static_cast<unsigned short>(r & 0xffff);
+    return __half(h);
 }
 
 }  // namespace vitad

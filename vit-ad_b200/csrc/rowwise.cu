@@ -1,0 +1,187 @@
+// Bandwidth-bound row-wise kernels of the encoder path: LayerNorm (fp32 residual stream -> fp16 GEMM
+// operand and/or fp32), patch gathering (im2col for the 16x16/s16 patch-embed conv), prefix tokens.
+// One warp per row, 128-bit loads, warp-shuffle reductions; grids sized in whole waves of 148 SMs
+// where the row count allows.
+#include <atomic>
+
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+namespace vitad {
+extern std::atomic<uint64_t> g_launches;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// y = (x - mean) / sqrt(var + eps) * w + b over the last dim C (biased variance, as nn.LayerNorm).
+// Output row r reads input row  (r / out_tokens) * in_tokens + skip + (r % out_tokens)  so the final
+// norm can drop the prefix tokens (x[:, 2:, :], TransformerEncoder.py:168) while normalising.
+// out_h: fp16 [rows, ldh]; columns [C, C+aug_ones) are set to 1 and [C+aug_ones, ldh) to 0 when
+// aug_ones > 0 (the MDN GEMM folds its biases into two extra K columns).  out_f: fp32 [rows, ldf].
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, __half* __restrict__ out_h,
+                                                        float* __restrict__ out_f, int rows, int C, int ldx, int ldh,
+                                                        int ldf, int in_tokens, int out_tokens, int skip, float eps,
+                                                        int aug_ones) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int bi = warp / out_tokens;
+    const int in_row = bi * in_tokens + skip + (warp - bi * out_tokens);
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(in_row) * ldx);
+    const int nv = C >> 2;
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nv) {
+            v[j] = xr[i];
+            s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        }
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nv) {
+            const float a = v[j].x - mean, bb = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+            q += (a * a + bb * bb) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    const float4* wr = reinterpret_cast<const float4*>(w);
+    const float4* br = reinterpret_cast<const float4*>(b);
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nv) {
+            const float4 ww = __ldg(wr + i), bb = __ldg(br + i);
+            float4 y;
+            y.x = (v[j].x - mean) * rstd * ww.x + bb.x;
+            y.y = (v[j].y - mean) * rstd * ww.y + bb.y;
+            y.z = (v[j].z - mean) * rstd * ww.z + bb.z;
+            y.w = (v[j].w - mean) * rstd * ww.w + bb.w;
+            if (out_f) reinterpret_cast<float4*>(out_f + static_cast<size_t>(warp) * ldf)[i] = y;
+            if (out_h) {
+                uint2 u;
+                u.x = pack_h2(y.x, y.y);
+                u.y = pack_h2(y.z, y.w);
+                reinterpret_cast<uint2*>(out_h + static_cast<size_t>(warp) * ldh)[i] = u;
+            }
+        }
+    }
+    if (out_h && aug_ones > 0) {
+        for (int c = C + lane; c < ldh; c += 32)
+            out_h[static_cast<size_t>(warp) * ldh + c] = to_h(c < C + aug_ones ? 1.0f : 0.0f);
+    }
+}
+
+// Patch gathering for the non-overlapping PxP/sP conv (timm PatchEmbed.proj): images fp32 [B,Cin,S,S]
+// -> A fp16 [B*g*g, Cin*P*P], column order (c, i, j) = the conv weight's flattened order.
+// One thread moves 8 consecutive j (two float4 loads, one 16-byte store).
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, __half* __restrict__ out, int B,
+                                                       int Cin, int S, int P, size_t total8) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total8) return;
+    const int g = S / P;
+    const int kcols = Cin * P * P;
+    const int per_row = kcols >> 3;
+    const size_t row = idx / per_row;
+    const int col = static_cast<int>(idx - row * per_row) << 3;
+    const int c = col / (P * P);
+    const int rem = col - c * P * P;
+    const int i = rem / P, j = rem - i * P;
+    const int bimg = static_cast<int>(row / (g * g));
+    const int p = static_cast<int>(row - static_cast<size_t>(bimg) * g * g);
+    const int py = p / g, px = p - py * g;
+    const float* src = img + ((static_cast<size_t>(bimg) * Cin + c) * S + (py * P + i)) * S + px * P + j;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 b2 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    uint4 u;
+    u.x = pack_h2(a.x, a.y);
+    u.y = pack_h2(a.z, a.w);
+    u.z = pack_h2(b2.x, b2.y);
+    u.w = pack_h2(b2.z, b2.w);
+    *reinterpret_cast<uint4*>(out + row * kcols + col) = u;
+}
+
+// x[b][t][:] = tok[t][:] + pos[t][:] for the `prefix` leading tokens (cls, dist) of every image.
+__global__ void prefix_tokens_kernel(const float* __restrict__ tok, const float* __restrict__ pos,
+                                     float* __restrict__ x, int B, int prefix, int T, int C) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = B * prefix * C;
+    if (idx >= total) return;
+    const int c = idx % C;
+    const int t = (idx / C) % prefix;
+    const int b = idx / (C * prefix);
+    x[(static_cast<size_t>(b) * T + t) * C + c] = tok[t * C + c] + pos[t * C + c];
+}
+
+}  // namespace vitad
+
+using namespace vitad;
+
+extern "C" int vitad_layernorm(const float* x, const float* weight, const float* bias, void* out_f16, float* out_f32,
+                               int rows, int c, int ldx, int ld_f16, int ld_f32, int in_tokens, int out_tokens,
+                               int skip, float eps, int aug_ones, void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(x && weight && bias && (out_f16 || out_f32), VITAD_ERR_ARG, "null pointer");
+    VITAD_REQUIRE(rows > 0 && c > 0 && c % 4 == 0 && c <= 1536, VITAD_ERR_SHAPE, "C=%d must be %%4 and <= 1536", c);
+    VITAD_REQUIRE(ldx % 4 == 0 && aligned16(x) && aligned16(weight) && aligned16(bias), VITAD_ERR_ALIGN,
+                  "layernorm input alignment");
+    VITAD_REQUIRE(!out_f16 || (ld_f16 % 4 == 0 && ld_f16 >= c + aug_ones && (reinterpret_cast<uintptr_t>(out_f16) & 7) == 0),
+                  VITAD_ERR_ALIGN, "fp16 output pitch/alignment");
+    VITAD_REQUIRE(!out_f32 || (ld_f32 % 4 == 0 && ld_f32 >= c && aligned16(out_f32)), VITAD_ERR_ALIGN,
+                  "fp32 output pitch/alignment");
+    VITAD_REQUIRE(in_tokens > 0 && out_tokens > 0 && skip >= 0 && skip + out_tokens <= in_tokens, VITAD_ERR_SHAPE,
+                  "token remap");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int blocks = (rows + 7) / 8;
+    if (c <= 768)
+        layernorm_kernel<6><<<blocks, 256, 0, s>>>(x, weight, bias, static_cast<__half*>(out_f16), out_f32, rows, c,
+                                                  ldx, ld_f16, ld_f32, in_tokens, out_tokens, skip, eps, aug_ones);
+    else
+        layernorm_kernel<12><<<blocks, 256, 0, s>>>(x, weight, bias, static_cast<__half*>(out_f16), out_f32, rows, c,
+                                                   ldx, ld_f16, ld_f32, in_tokens, out_tokens, skip, eps, aug_ones);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+extern "C" int vitad_patchify(const float* images, void* out_f16, int batch, int channels, int size, int patch,
+                              void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(images && out_f16, VITAD_ERR_ARG, "null pointer");
+    VITAD_REQUIRE(batch > 0 && channels > 0 && patch % 8 == 0 && size % patch == 0, VITAD_ERR_SHAPE,
+                  "patchify needs patch %% 8 == 0 and size %% patch == 0");
+    VITAD_REQUIRE(aligned16(images) && aligned16(out_f16), VITAD_ERR_ALIGN, "patchify alignment");
+    const int g = size / patch;
+    const size_t total8 = static_cast<size_t>(batch) * g * g * channels * patch * patch / 8;
+    const unsigned blocks = static_cast<unsigned>((total8 + 255) / 256);
+    patchify_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(images, static_cast<__half*>(out_f16), batch,
+                                                                         channels, size, patch, total8);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+extern "C" int vitad_prefix_tokens(const float* tokens, const float* pos, float* x, int batch, int prefix, int t, int c,
+                                   void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(tokens && pos && x && batch > 0 && prefix > 0 && prefix <= t, VITAD_ERR_ARG, "prefix tokens args");
+    const int total = batch * prefix * c;
+    prefix_tokens_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(tokens, pos, x, batch,
+                                                                                            prefix, t, c);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}

@@ -30,8 +30,8 @@ lib.vitad_last_error.restype = C.c_char_p
 lib.vitad_abi_version.restype = C.c_int
 lib.vitad_launch_count.restype = C.c_uint64
 
-EPI_BIAS_BF16 = 0
-EPI_BIAS_GELU_BF16 = 1
+EPI_BIAS_F16 = 0
+EPI_BIAS_GELU_F16 = 1
 EPI_RESIDUAL_F32 = 2
 EPI_QKV = 3
 EPI_PATCH_EMBED = 4
@@ -66,8 +66,8 @@ class LinearArgs(C.Structure):
     ]
 
 
-lib.vitad_linear_bf16.argtypes = [C.POINTER(LinearArgs), C.c_void_p]
-lib.vitad_linear_bf16.restype = C.c_int
+lib.vitad_linear_f16.argtypes = [C.POINTER(LinearArgs), C.c_void_p]
+lib.vitad_linear_f16.restype = C.c_int
 
 
 def check(rc: int) -> None:
@@ -77,3 +77,65 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(lib.vitad_launch_count())
+
+
+# ---------------------------------------------------------------------------------- encoder kernels
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+lib.vitad_layernorm.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]
+lib.vitad_layernorm.restype = _i
+lib.vitad_patchify.argtypes = [_vp, _vp, _i, _i, _i, _i, _vp]
+lib.vitad_patchify.restype = _i
+lib.vitad_prefix_tokens.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _vp]
+lib.vitad_prefix_tokens.restype = _i
+lib.vitad_attention_f16.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
+lib.vitad_attention_f16.restype = _i
+
+DEIT_MAX_DEPTH = 24
+
+
+class DeitLayer(C.Structure):
+    _fields_ = [(n, _vp) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w",
+                                   "fc1_b", "fc2_w", "fc2_b")]
+
+
+class DeitWeights(C.Structure):
+    _fields_ = [(n, _i) for n in ("img", "patch", "dim", "heads", "hidden", "depth", "tokens", "prefix")] + [
+        ("patch_w", _vp), ("patch_b", _vp), ("prefix_tokens", _vp), ("pos", _vp), ("norm_w", _vp), ("norm_b", _vp),
+        ("layers", C.POINTER(DeitLayer)),
+    ]
+
+
+lib.vitad_deit_workspace_bytes.argtypes = [C.POINTER(DeitWeights), _i]
+lib.vitad_deit_workspace_bytes.restype = _sz
+lib.vitad_deit_forward.argtypes = [C.POINTER(DeitWeights), _vp, _i, _i, _vp, _sz, _vp, _vp, _vp, _i, _vp]
+lib.vitad_deit_forward.restype = _i
+
+# ---------------------------------------------------------------------------------------- GMM head
+lib.vitad_gmm_plan.argtypes = [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]
+lib.vitad_gmm_plan.restype = _i
+lib.vitad_gmm_packed_weight_bytes.argtypes = [_i, _i]
+lib.vitad_gmm_packed_weight_bytes.restype = _sz
+lib.vitad_gmm_pack_weights.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]
+lib.vitad_gmm_pack_weights.restype = _i
+lib.vitad_gmm_make_operand.argtypes = [_vp, _i, _vp, _i, _i, _vp]
+lib.vitad_gmm_make_operand.restype = _i
+lib.vitad_gmm_log_pi.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]
+lib.vitad_gmm_log_pi.restype = _i
+lib.vitad_gmm_patch_loglik.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp]
+lib.vitad_gmm_patch_loglik.restype = _i
+lib.vitad_gmm_finish.argtypes = [_vp, _vp, _vp, _i, _i, _vp]
+lib.vitad_gmm_finish.restype = _i
+
+# ------------------------------------------------------------------------------------- score maps
+lib.vitad_bilinear_up.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
+lib.vitad_bilinear_up.restype = _i
+lib.vitad_l2_map_score.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]
+lib.vitad_l2_map_score.restype = _i
+
+MDN_KA = 784  # K extent of the packed MDN operands (768 + 16)
+
+
+def gmm_plan(num_gaussians: int):
+    n_kc, kc, kcv = _i(), _i(), _i()
+    check(lib.vitad_gmm_plan(num_gaussians, C.byref(n_kc), C.byref(kc), C.byref(kcv)))
+    return n_kc.value, kc.value, kcv.value

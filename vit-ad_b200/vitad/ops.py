@@ -27,19 +27,19 @@ def linear(
     a: torch.Tensor,
     w: torch.Tensor,
     bias: torch.Tensor | None,
-    epilogue: int = _lib.EPI_BIAS_BF16,
+    epilogue: int = _lib.EPI_BIAS_F16,
     out: torch.Tensor | None = None,
     resid: torch.Tensor | None = None,
     block_n: int = 0,
 ) -> torch.Tensor:
-    """out = epilogue(a @ w.T + bias).  a: bf16 [M,K]; w: bf16 [N,K]; bias: fp32 [N]."""
+    """out = epilogue(a @ w.T + bias).  a: fp16 [M,K]; w: fp16 [N,K]; bias: fp32 [N]."""
     _need_cuda(a, w, bias, out, resid)
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.dtype == torch.float16 and w.dtype == torch.float16
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
     m, k = a.shape
     n = w.shape[0]
     if out is None:
-        dt = torch.float32 if epilogue in (_lib.EPI_RESIDUAL_F32, _lib.EPI_F32) else torch.bfloat16
+        dt = torch.float32 if epilogue in (_lib.EPI_RESIDUAL_F32, _lib.EPI_F32) else torch.float16
         out = torch.empty((m, n), device=a.device, dtype=dt)
     args = _lib.LinearArgs()
     args.a, args.w, args.bias = a.data_ptr(), w.data_ptr(), _ptr(bias)
@@ -48,7 +48,7 @@ def linear(
     args.epilogue, args.block_n = epilogue, block_n
     args.out, args.ldo = out.data_ptr(), out.stride(0)
     args.resid = _ptr(resid)
-    check(lib.vitad_linear_bf16(C.byref(args), _stream()))
+    check(lib.vitad_linear_f16(C.byref(args), _stream()))
     return out
 
 
@@ -56,7 +56,7 @@ def linear_qkv(
     a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, batch: int, tokens: int, heads: int, tokens_pad: int,
     q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, q_scale: float, block_n: int = 0,
 ) -> None:
-    """Fused qkv projection writing q/k as [B,H,T,64] and v transposed as [B,H,64,Tpad] (bf16)."""
+    """Fused qkv projection writing q/k as [B,H,T,64] and v transposed as [B,H,64,Tpad] (fp16)."""
     _need_cuda(a, w, bias, q, k, vt)
     m, kk = a.shape
     assert m == batch * tokens
@@ -67,7 +67,7 @@ def linear_qkv(
     args.epilogue, args.block_n = _lib.EPI_QKV, block_n
     args.q, args.kmat, args.vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
     args.tokens, args.tokens_pad, args.heads, args.q_scale = tokens, tokens_pad, heads, q_scale
-    check(lib.vitad_linear_bf16(C.byref(args), _stream()))
+    check(lib.vitad_linear_f16(C.byref(args), _stream()))
 
 
 def linear_patch_embed(
@@ -83,4 +83,61 @@ def linear_patch_embed(
     args.epilogue, args.block_n = _lib.EPI_PATCH_EMBED, block_n
     args.out, args.ldo = out.data_ptr(), w.shape[0]
     args.pos, args.patches, args.prefix = pos.data_ptr(), patches, prefix
-    check(lib.vitad_linear_bf16(C.byref(args), _stream()))
+    check(lib.vitad_linear_f16(C.byref(args), _stream()))
+
+
+# ------------------------------------------------------------------------------- encoder kernels
+def layernorm(x, weight, bias, eps, out_f16=None, out_f32=None, in_tokens=None, out_tokens=None, skip=0, aug_ones=0):
+    """LayerNorm over the last dim of fp32 x [rows_in, C]; see include/vitad.h for the row remap."""
+    _need_cuda(x, weight, bias, out_f16, out_f32)
+    rows_in, c = x.shape
+    if in_tokens is None:
+        in_tokens = out_tokens = rows_in
+    rows = (rows_in // in_tokens) * out_tokens
+    check(lib.vitad_layernorm(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), _ptr(out_f16), _ptr(out_f32), rows, c,
+                              x.stride(0), out_f16.stride(0) if out_f16 is not None else 0,
+                              out_f32.stride(0) if out_f32 is not None else 0, in_tokens, out_tokens, skip, eps,
+                              aug_ones, _stream()))
+
+
+def patchify(images, patch):
+    _need_cuda(images)
+    b, c, s, _ = images.shape
+    g = s // patch
+    out = torch.empty((b * g * g, c * patch * patch), device=images.device, dtype=torch.float16)
+    check(lib.vitad_patchify(images.data_ptr(), out.data_ptr(), b, c, s, patch, _stream()))
+    return out
+
+
+def attention(q, k, vt, tokens):
+    """q,k fp16 [B,H,T,64] (q pre-scaled); vt fp16 [B,H,64,Tpad] zero-padded -> fp16 [B*T, H*64]."""
+    _need_cuda(q, k, vt)
+    b, h, t, hd = q.shape
+    out = torch.empty((b * t, h * hd), device=q.device, dtype=torch.float16)
+    check(lib.vitad_attention_f16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), b, h, tokens,
+                                  vt.shape[-1], hd, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------- score maps
+def bilinear_up(x, size, align_corners, pre_one_minus=False, post_one_minus=False, want_max=False):
+    """x fp32 [N,g,g] -> ([N,1,size,size], per-image max or None)."""
+    _need_cuda(x)
+    n, g, _ = x.shape
+    out = torch.empty((n, 1, size, size), device=x.device, dtype=torch.float32)
+    mx = torch.empty((n,), device=x.device, dtype=torch.float32) if want_max else None
+    check(lib.vitad_bilinear_up(x.data_ptr(), out.data_ptr(), _ptr(mx), n, g, size, int(align_corners),
+                                int(pre_one_minus), int(post_one_minus), _stream()))
+    return out, mx
+
+
+def l2_map_score(recon, x):
+    """mean_c (recon - x)^2 -> ([N,1,H,W] map, [N] per-image max)."""
+    _need_cuda(recon, x)
+    n, c, h, w = x.shape
+    recon, x = recon.contiguous(), x.contiguous()
+    amap = torch.empty((n, 1, h, w), device=x.device, dtype=torch.float32)
+    mx = torch.empty((n,), device=x.device, dtype=torch.float32)
+    check(lib.vitad_l2_map_score(recon.data_ptr(), x.data_ptr(), amap.data_ptr(), mx.data_ptr(), n, c, h * w,
+                                 _stream()))
+    return amap, mx
