@@ -1,0 +1,120 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/vitad.h declares
+(no compute without a GPU), the product path refuses CPU tensors, state_dict key layouts match the
+reference's, the metrics wrapper, and the world_size-2 gloo gather."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from vitad import _lib
+
+    header = open(os.path.join(ROOT, "include", "vitad.h")).read()
+    names = sorted(set(re.findall(r"\b(vitad_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} declared in include/vitad.h but not exported"
+    assert _lib.lib.vitad_abi_version() == 1
+    assert _lib.gmm_plan(100) == (1, 112, 100) and _lib.gmm_plan(130) == (2, 72, 65)
+    with pytest.raises(_lib.VitadError):
+        _lib.gmm_plan(500)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_entry_points_fail_loudly_without_gpu():
+    import ctypes as C
+
+    from vitad import _lib
+
+    args = _lib.LinearArgs()
+    rc = _lib.lib.vitad_linear_f16(C.byref(args), None)
+    assert rc == -4 and b"CPU path" in _lib.lib.vitad_last_error()  # VITAD_ERR_ARCH
+
+
+def test_modules_refuse_cpu_tensors():
+    from vitad.encoders import EncoderDeit
+    from vitad.mdn import GaussianMixtureDensityNetwork
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        EncoderDeit(224)(torch.rand(1, 3, 224, 224))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        GaussianMixtureDensityNetwork(768, 768, 100)(torch.rand(1, 196, 768))
+
+
+def test_state_dict_layouts_match_reference_keys():
+    from oracle import weights as W
+    from vitad.encoders import EncoderDeit
+    from vitad.mdn import GaussianMixtureDensityNetwork
+
+    enc = EncoderDeit(224)
+    ref = W.make_deit_state_dict(seed=0)  # key layout proven against the reference in oracle/make_golden.py
+    assert set(enc.state_dict().keys()) == set(ref.keys())
+    for k, v in enc.state_dict().items():
+        assert tuple(v.shape) == tuple(ref[k].shape), k
+    enc.load_state_dict(ref, strict=True)
+    assert enc.img_size == 224 and enc.patch_size == 16 and enc.size_patch_embedding == 768
+    assert enc.num_embedded_patches == 196 and enc.architecture == "transformer_encoder"
+    head = GaussianMixtureDensityNetwork(768, 768, 130)
+    ref = W.make_mdn_state_dict(seed=0, num_gaussians=130)
+    assert {k: tuple(v.shape) for k, v in head.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.items()}
+    assert torch.all(head.mu.bias == 0.001)
+
+
+def test_metrics_match_sklearn_direct_calls():
+    from sklearn import metrics as skm
+
+    from vitad.metrics import calc_all_metrics
+
+    rng = np.random.RandomState(0)
+    n = 24
+    labels = (rng.rand(n) > 0.5).astype(np.int64)
+    scores = rng.rand(n) + 0.5 * labels
+    pl = (rng.rand(n, 1, 16, 16) > 0.9).astype(np.float32)
+    ps = rng.rand(n, 1, 16, 16).astype(np.float32) + 0.3 * pl
+    out = calc_all_metrics({"image_scores": scores, "image_labels": labels, "pixel_scores": ps, "pixel_labels": pl},
+                           fp_thres=0.3, dataset_name="t")
+    assert out["image_auroc_score"] == pytest.approx(skm.roc_auc_score(labels, scores), abs=1e-12)
+    assert out["pixel_auroc_score"] == pytest.approx(skm.roc_auc_score(pl.ravel(), ps.ravel()), abs=1e-12)
+    assert 0.0 <= out["pro_score_0.3fp"] <= 1.0 and 0.0 <= out["image_prauc_score"] <= 1.0
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, os.path.join(sys.argv[1], "vit-ad_b200"))
+import numpy as np, torch
+from vitad.parallel import init_from_env, gather_results
+from vitad.validators import _BatchSharding
+rank, world, _ = init_from_env(backend="gloo")
+sizes = [4, 4, 4, 4, 3]                       # five batches, short tail (no drop_last in the reference loader)
+starts = np.cumsum([0] + sizes)
+shard = _BatchSharding(rank, world)
+mine = [b for b in range(len(sizes)) if shard.mine(b)]
+ids = np.concatenate([np.arange(starts[b], starts[b + 1]) for b in mine])
+res = {"image_scores": ids.astype(np.float32) * 0.5, "pixel_scores": np.tile(ids.astype(np.float32)[:, None, None, None], (1, 1, 4, 4)),
+       "image_labels": (ids % 2).astype(np.int64), "pixel_labels": np.zeros((len(ids), 1, 4, 4), np.float32),
+       "batch_index": np.asarray(mine), "batch_sizes": np.asarray([sizes[b] for b in mine])}
+full = gather_results(res, num_batches=len(sizes), device=torch.device("cpu"))
+n = sum(sizes)
+assert np.array_equal(full["image_scores"], np.arange(n, dtype=np.float32) * 0.5), full["image_scores"]
+assert np.array_equal(full["image_labels"], np.arange(n) % 2)
+assert full["pixel_scores"].shape == (n, 1, 4, 4) and np.array_equal(full["pixel_scores"][:, 0, 0, 0], np.arange(n, dtype=np.float32))
+torch.distributed.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_batch_sharded_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29531", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2

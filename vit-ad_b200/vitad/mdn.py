@@ -130,8 +130,13 @@ class GaussianMixtureDensityNetwork(nn.Module):
         ld_ws = (M + 31) // 32 * 32
         ll_ws = torch.empty((D, ld_ws), device=x.device, dtype=torch.float32)
         L = torch.empty((M,), device=x.device, dtype=torch.float32)
+        hook = getattr(self, "timing_hook", None)  # (start, end) CUDA events around the dominant kernel (bench.py)
+        if hook is not None:
+            hook[0].record()
         check(lib.vitad_gmm_patch_loglik(xaug.data_ptr(), pk["w"].data_ptr(), lp2.data_ptr(), xf.data_ptr(),
                                          xf.stride(0), ll_ws.data_ptr(), ld_ws, L.data_ptr(), M, D, K, _stream()))
+        if hook is not None:
+            hook[1].record()
         return L.view(B, P)
 
     def score(self, x: Tensor, gumbel: Tensor | None = None):
