@@ -38,6 +38,9 @@ const char* vitad_last_error(void);
 int vitad_abi_version(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 uint64_t vitad_launch_count(void);
+/* GEMM-class kernels run on CTA pairs (tcgen05 cta_group::2, 256-row tiles) by default; 0 selects the
+ * single-CTA 128-row kernels (kept for A/B measurements and for problems of <= 128 rows). */
+void vitad_set_cta_pair(int enable);
 
 /* ------------------------------------------------------------------------------------------
  * Dense projection  D = A · Wᵀ (+ fused epilogue), fp16 operands (IEEE half: same tensor-core rate as bf16, 3 more mantissa bits), fp32 accumulate (tcgen05/TMEM,

@@ -104,3 +104,20 @@ def test_linear_rejects_bad_arguments():
         ops.linear(a[:, :40], w[:, :40], b, _lib.EPI_BIAS_F16)  # K not a multiple of 16
     with pytest.raises(RuntimeError):
         ops.linear(a.cpu(), w.cpu(), b.cpu())  # no CPU path
+
+
+@pytest.mark.parametrize("pair", [0, 1])
+def test_cta_pair_and_single_cta_kernels_agree(pair):
+    """Both GEMM variants (cta_group::2 pairs / single CTA) against the fp32 reference, ragged M."""
+    from vitad import _lib, ops
+
+    _lib.lib.vitad_set_cta_pair(pair)
+    try:
+        for m, n, k in [(6336, 768, 768), (300, 256, 3072), (129, 2304, 768), (6272, 512, 784)]:
+            a, w, b = _mk(m, n, k, seed=m)
+            out = ops.linear(a, w, b, _lib.EPI_F32)
+            torch.cuda.synchronize()
+            ref = _ref(a, w, b)
+            assert (out - ref).abs().max().item() <= 1e-4 * ref.abs().max().item(), (pair, m, n, k)
+    finally:
+        _lib.lib.vitad_set_cta_pair(1)

@@ -40,9 +40,10 @@ struct EpiBiasH {
     int ldo, M, N;
     __device__ __forceinline__ void tile_begin(int, int, int) const {}
     __device__ __forceinline__ void tile_end(int, int, int) const {}
-    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr) const {
+    static constexpr bool kSplitColumns = true;
+    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr, int c0, int c1) const {
         const int n0 = n_tile * BLOCK_N;
-        for_each_chunk32<BLOCK_N>(taddr, [&](int c, float (&v)[32]) {
+        for_each_chunk32(taddr, c0, c1, [&](int c, float (&v)[32]) {
             const int col = n0 + c;
             if (row < M && col < N) {
                 float b[32];
@@ -67,9 +68,10 @@ struct EpiResidualF32 {
     int ld, M, N;
     __device__ __forceinline__ void tile_begin(int, int, int) const {}
     __device__ __forceinline__ void tile_end(int, int, int) const {}
-    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr) const {
+    static constexpr bool kSplitColumns = true;
+    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr, int c0, int c1) const {
         const int n0 = n_tile * BLOCK_N;
-        for_each_chunk32<BLOCK_N>(taddr, [&](int c, float (&v)[32]) {
+        for_each_chunk32(taddr, c0, c1, [&](int c, float (&v)[32]) {
             const int col = n0 + c;
             if (row < M && col < N) {
                 float b[32];
@@ -106,12 +108,13 @@ struct EpiQkv {
     float scale;
     __device__ __forceinline__ void tile_begin(int, int, int) const {}
     __device__ __forceinline__ void tile_end(int, int, int) const {}
-    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr) const {
+    static constexpr bool kSplitColumns = true;
+    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr, int c0, int c1) const {
         const int C = H * 64;
         const int n0 = n_tile * BLOCK_N;
         const int b = row / T;
         const int t = row - b * T;
-        for_each_chunk32<BLOCK_N>(taddr, [&](int c, float (&v)[32]) {
+        for_each_chunk32(taddr, c0, c1, [&](int c, float (&v)[32]) {
             const int col = n0 + c;
             if (row < M && col < 3 * C) {
                 float bb[32];
@@ -148,11 +151,12 @@ struct EpiPatchEmbed {
     int M, P, prefix, C;
     __device__ __forceinline__ void tile_begin(int, int, int) const {}
     __device__ __forceinline__ void tile_end(int, int, int) const {}
-    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr) const {
+    static constexpr bool kSplitColumns = true;
+    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr, int c0, int c1) const {
         const int n0 = n_tile * BLOCK_N;
         const int b = row / P;
         const int p = row - b * P;
-        for_each_chunk32<BLOCK_N>(taddr, [&](int c, float (&v)[32]) {
+        for_each_chunk32(taddr, c0, c1, [&](int c, float (&v)[32]) {
             const int col = n0 + c;
             if (row < M && col < C) {
                 float bb[32];
@@ -181,9 +185,10 @@ struct EpiBiasF32 {
     int ldo, M, N;
     __device__ __forceinline__ void tile_begin(int, int, int) const {}
     __device__ __forceinline__ void tile_end(int, int, int) const {}
-    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr) const {
+    static constexpr bool kSplitColumns = true;
+    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr, int c0, int c1) const {
         const int n0 = n_tile * BLOCK_N;
-        for_each_chunk32<BLOCK_N>(taddr, [&](int c, float (&v)[32]) {
+        for_each_chunk32(taddr, c0, c1, [&](int c, float (&v)[32]) {
             const int col = n0 + c;
             if (row < M && col < N) {
                 float* o = out + static_cast<size_t>(row) * ldo + col;

@@ -9,6 +9,7 @@ namespace vitad {
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_use_pair{1};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -99,3 +100,4 @@ int check_device_arch() {
 extern "C" const char* vitad_last_error(void) { return vitad::g_err; }
 extern "C" int vitad_abi_version(void) { return 1; }
 extern "C" uint64_t vitad_launch_count(void) { return vitad::g_launches.load(); }
+extern "C" void vitad_set_cta_pair(int enable) { vitad::g_use_pair.store(enable ? 1 : 0); }

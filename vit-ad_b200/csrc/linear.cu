@@ -2,13 +2,43 @@
 #include <atomic>
 
 #include "gemm_epilogues.cuh"
+#include "gemm_pair.cuh"
 #include "host_util.cuh"
 
 namespace vitad {
 extern std::atomic<uint64_t> g_launches;
 
+extern std::atomic<int> g_use_pair;
+
+// CTA-pair (cta_group::2) launch: 256-row tiles, cluster of two CTAs.
+template <int BLOCK_N, class Epi>
+static int launch_gemm_pair(const vitad_linear_args& a, const Epi& epi, cudaStream_t stream) {
+    using S = PairSmem<BLOCK_N>;
+    CUtensorMap ta, tb;
+    int rc = make_tmap_f16_2d(&ta, a.a, a.m, a.k, a.lda, kBlockM);
+    if (rc) return rc;
+    rc = make_tmap_f16_2d(&tb, a.w, a.n, a.k, a.ldw, BLOCK_N / 2);
+    if (rc) return rc;
+    auto kern = gemm2_tc_kernel<BLOCK_N, 1, Epi>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VITAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
+        attr_set = true;
+    }
+    const int num_m = (a.m + 2 * kBlockM - 1) / (2 * kBlockM);
+    const int num_n = (a.n + BLOCK_N - 1) / BLOCK_N;
+    const int tiles = num_m * num_n;
+    const int max_clusters = device_sm_count() / 2;
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    kern<<<2 * clusters, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, a.m, num_n, a.k, epi);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
 template <int BLOCK_N, class Epi>
 static int launch_gemm(const vitad_linear_args& a, const Epi& epi, cudaStream_t stream) {
+    if (g_use_pair.load() && a.m > kBlockM) return launch_gemm_pair<BLOCK_N>(a, epi, stream);
     using S = GemmSmem<BLOCK_N>;
     CUtensorMap ta, tb;
     int rc = make_tmap_f16_2d(&ta, a.a, a.m, a.k, a.lda, kBlockM);

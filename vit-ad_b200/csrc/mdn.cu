@@ -15,11 +15,12 @@
 //   lp2   fp32 [M][n_kc*KC]                             log2(softmax(pi+g)+1e-15); padding = -1e30
 #include <atomic>
 
-#include "gemm_core.cuh"
+#include "gemm_pair.cuh"
 #include "host_util.cuh"
 
 namespace vitad {
 extern std::atomic<uint64_t> g_launches;
+extern std::atomic<int> g_use_pair;
 
 constexpr float kLog2eF = 1.4426950408889634f;
 constexpr float kLn2F = 0.6931471805599453f;
@@ -73,7 +74,21 @@ struct EpiMdn {
         m_run = m_new;
     }
 
-    __device__ __forceinline__ void sub(int kc, int, int, int row, uint32_t taddr) {
+    static constexpr bool kSplitColumns = false;  // group g owns accumulator stage g (see gemm_core.cuh)
+
+    // Two-chunk mixtures (K > 112): each epilogue group holds the running (max, sum) of one chunk.
+    __device__ __forceinline__ void merge(int group, float2* slot) {
+        if (group == 1) {
+            *slot = make_float2(m_run, s_run);
+        } else {
+            const float2 o = *slot;
+            const float m_new = fmaxf(m_run, o.x);
+            s_run = s_run * ex2f(m_run - m_new) + o.y * ex2f(o.x - m_new);
+            m_run = m_new;
+        }
+    }
+
+    __device__ __forceinline__ void sub(int kc, int, int, int row, uint32_t taddr, int, int) {
         const bool valid = row < M;
         const float* lprow = lp2 + static_cast<size_t>(valid ? row : 0) * ldp + kc * KC;
         constexpr int kFull = KC / 16;
@@ -323,13 +338,33 @@ static int launch_mdn(const void* xaug, const void* wpk, const float* lp2, const
     if (rc) return rc;
     rc = make_tmap_f16_2d(&tb, wpk, static_cast<uint64_t>(D) * NKC * BN, kMdnKA, kMdnKA, BN);
     if (rc) return rc;
+    Epi epi{lp2, x, ll, NKC * KC, ldx, ldl, M, 0.f, 0.f, 0.f};
+    if (g_use_pair.load() && M > kBlockM) {
+        // CTA pairs: rank 0 stages the sigma rows of feature d, rank 1 the mu rows (the two halves of the tile)
+        using SP = PairSmem<BN>;
+        rc = make_tmap_f16_2d(&tb, wpk, static_cast<uint64_t>(D) * NKC * BN, kMdnKA, kMdnKA, BN / 2);
+        if (rc) return rc;
+        auto kern2 = gemm2_tc_kernel<BN, NKC, Epi>;
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            VITAD_CUDA_OK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::kTotalBytes));
+            attr2_set = true;
+        }
+        const int num_m2 = (M + 2 * kBlockM - 1) / (2 * kBlockM);
+        const int tiles2 = num_m2 * D;
+        const int max_clusters = device_sm_count() / 2;
+        const int clusters = tiles2 < max_clusters ? tiles2 : max_clusters;
+        kern2<<<2 * clusters, kGemmThreads, SP::kTotalBytes, stream>>>(ta, tb, M, D, kMdnKA, epi);
+        VITAD_CUDA_OK(cudaGetLastError());
+        g_launches.fetch_add(1);
+        return VITAD_OK;
+    }
     auto kern = gemm_tc_kernel<BN, NKC, Epi>;
     static bool attr_set = false;
     if (!attr_set) {
         VITAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
         attr_set = true;
     }
-    Epi epi{lp2, x, ll, NKC * KC, ldx, ldl, M, 0.f, 0.f, 0.f};
     const int num_m = (M + kBlockM - 1) / kBlockM;
     const int tiles = num_m * D;
     const int grid = tiles < device_sm_count() ? tiles : device_sm_count();

@@ -14,6 +14,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// True in exactly one lane of a fully converged warp.  Role loops run warp-uniformly and predicate only the
+// issuing instruction with this, so operands of TMA / tcgen05 instructions stay in uniform registers (a loop
+// executed by `if (lane == 0)` forces a vector->uniform register round trip per operand and made the MMA
+// issue path ~2x slower than the tensor pipe it feeds).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -129,6 +142,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
 // Shared-memory matrix descriptor, K-major operand stored as rows of 128 bytes (64 fp16) with the
 // 128-byte swizzle TMA writes; 8-row groups are 1024 bytes apart (SBO). `addr` is the byte address
 // of the first row (1024-aligned tile base + k*32 bytes for the k-th 16-element slice).
+// Split form: the high word is constant, the low word advances by 2 per 16-element k-slice (32 bytes >> 4).
+constexpr uint32_t kSmemDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t smem_desc_join(uint32_t lo) {
+    return (static_cast<uint64_t>(kSmemDescHiSw128) << 32) | lo;
+}
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t addr) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);  // start address

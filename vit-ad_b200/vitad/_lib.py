@@ -29,6 +29,8 @@ lib = _load()
 lib.vitad_last_error.restype = C.c_char_p
 lib.vitad_abi_version.restype = C.c_int
 lib.vitad_launch_count.restype = C.c_uint64
+lib.vitad_set_cta_pair.argtypes = [C.c_int]
+lib.vitad_set_cta_pair.restype = None
 
 EPI_BIAS_F16 = 0
 EPI_BIAS_GELU_F16 = 1
