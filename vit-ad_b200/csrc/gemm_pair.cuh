@@ -112,7 +112,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     constexpr bool kSplit = Epi::kSplitColumns;
     static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "invalid UMMA N for M=256");
     static_assert(SUBTILES == 1 || SUBTILES == 2, "one or two sub-blocks per tile");
-    static_assert(!kSplit || BLOCK_N % 64 == 0, "column split needs two halves of whole 32-column chunks");
+    static_assert(!kSplit || BLOCK_N % 32 == 0, "column split needs two halves of whole 16-column chunks");
     constexpr uint32_t kTmemCols = tmem_cols_pow2(2 * BLOCK_N);
     constexpr int kPairM = 2 * kBlockM;
 

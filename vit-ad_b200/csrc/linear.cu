@@ -1,4 +1,10 @@
-// vitad_linear_f16: dispatch of the tcgen05 GEMM main loop with the encoder's fused epilogues.
+// vitad_linear_f16: dispatch of the tcgen05 GEMM main loops with the encoder's fused epilogues.
+//
+// Tile choice.  The encoder's GEMMs are small (M = 6336 at batch 32, N in {768, 2304, 3072}), so the
+// persistent schedule is dominated by wave quantisation: with 256-row CTA-pair tiles there are 25 row
+// blocks, and N = 768 at BLOCK_N = 256 gives 75 tiles for 74 SM pairs (two waves, the second almost empty).
+// pick_block_n() minimises ceil(tiles / SM pairs) * BLOCK_N over the instantiated widths; BLOCK_N = 96
+// divides 768/2304/3072 and lands within 2-10% of the ideal split for all three.
 #include <atomic>
 
 #include "gemm_epilogues.cuh"
@@ -7,7 +13,6 @@
 
 namespace vitad {
 extern std::atomic<uint64_t> g_launches;
-
 extern std::atomic<int> g_use_pair;
 
 // CTA-pair (cta_group::2) launch: 256-row tiles, cluster of two CTAs.
@@ -102,6 +107,26 @@ static int dispatch_epilogue(const vitad_linear_args& a, cudaStream_t stream) {
     }
 }
 
+// Minimise (waves of the persistent schedule) x (tile width); ties go to the wider tile.
+static int pick_block_n(int m, int n) {
+    const bool pair = g_use_pair.load() && m > kBlockM;
+    const int rows = pair ? 2 * kBlockM : kBlockM;
+    const int workers = pair ? device_sm_count() / 2 : device_sm_count();
+    const int num_m = (m + rows - 1) / rows;
+    const int cand[3] = {256, 128, 96};
+    int best = 256;
+    long best_cost = -1;
+    for (int bn : cand) {
+        const long tiles = static_cast<long>(num_m) * ((n + bn - 1) / bn);
+        const long cost = ((tiles + workers - 1) / workers) * bn;
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = bn;
+        }
+    }
+    return best;
+}
+
 }  // namespace vitad
 
 extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
@@ -148,9 +173,10 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
             break;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int bn = a.block_n == 0 ? (a.n % 256 == 0 || a.n > 1024 ? 256 : 128) : a.block_n;
+    const int bn = a.block_n == 0 ? pick_block_n(a.m, a.n) : a.block_n;
     if (bn == 256) return dispatch_epilogue<256>(a, s);
     if (bn == 128) return dispatch_epilogue<128>(a, s);
-    set_error("block_n=%d unsupported (128 or 256)", bn);
+    if (bn == 96) return dispatch_epilogue<96>(a, s);
+    set_error("block_n=%d unsupported (96, 128 or 256)", bn);
     return VITAD_ERR_SHAPE;
 }
