@@ -41,6 +41,11 @@ uint64_t vitad_launch_count(void);
 /* GEMM-class kernels run on CTA pairs (tcgen05 cta_group::2, 256-row tiles) by default; 0 selects the
  * single-CTA 128-row kernels (kept for A/B measurements and for problems of <= 128 rows). */
 void vitad_set_cta_pair(int enable);
+/* Optional in-library profiler: CUDA events around every launch site of this library.
+ * vitad_profile_enable(1) clears and starts recording, vitad_profile_report() synchronises the device and
+ * writes "name count total_us" lines (+ a "__span__" line: first start .. last end) into buf. */
+void vitad_profile_enable(int on);
+int vitad_profile_report(char* buf, int size);
 
 /* ------------------------------------------------------------------------------------------
  * Dense projection  D = A · Wᵀ (+ fused epilogue), fp16 operands (IEEE half: same tensor-core rate as bf16, 3 more mantissa bits), fp32 accumulate (tcgen05/TMEM,

@@ -214,6 +214,7 @@ extern "C" int vitad_attention_f16(const void* q, const void* k, const void* vt,
         attr_set = true;
     }
     dim3 grid((tokens + 127) / 128, BH);
+    ProfScope prof("attention", static_cast<cudaStream_t>(stream));
     kern<<<grid, 128, S::kTotal, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, static_cast<__half*>(out), tokens,
                                                                      heads);
     VITAD_CUDA_OK(cudaGetLastError());

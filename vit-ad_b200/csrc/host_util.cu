@@ -101,3 +101,63 @@ extern "C" const char* vitad_last_error(void) { return vitad::g_err; }
 extern "C" int vitad_abi_version(void) { return 1; }
 extern "C" uint64_t vitad_launch_count(void) { return vitad::g_launches.load(); }
 extern "C" void vitad_set_cta_pair(int enable) { vitad::g_use_pair.store(enable ? 1 : 0); }
+
+// ------------------------------------------------------------------------------------ profiler
+#include <map>
+#include <string>
+#include <vector>
+namespace vitad {
+struct ProfRec {
+    std::string name;
+    cudaEvent_t e0, e1;
+};
+static std::atomic<int> g_prof_on{0};
+static std::vector<ProfRec> g_prof;
+ProfScope::ProfScope(const char* name, cudaStream_t s) : idx(-1), stream(s) {
+    if (!g_prof_on.load()) return;
+    ProfRec r;
+    r.name = name;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, s);
+    g_prof.push_back(r);
+    idx = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof[idx].e1, stream);
+}
+}  // namespace vitad
+
+extern "C" void vitad_profile_enable(int on) {
+    using namespace vitad;
+    for (auto& r : g_prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    g_prof_on.store(on ? 1 : 0);
+}
+
+// Writes "name count total_us\n" lines plus a "__span__" line (first start .. last end) into buf.
+extern "C" int vitad_profile_report(char* buf, int size) {
+    using namespace vitad;
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<int, double>> agg;
+    std::vector<std::string> order;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        if (!agg.count(r.name)) order.push_back(r.name);
+        agg[r.name].first += 1;
+        agg[r.name].second += ms * 1e3;
+    }
+    int off = 0;
+    for (auto& n : order)
+        off += snprintf(buf + off, off < size ? size - off : 0, "%s %d %.1f\n", n.c_str(), agg[n].first, agg[n].second);
+    if (!g_prof.empty()) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_prof.front().e0, g_prof.back().e1);
+        off += snprintf(buf + off, off < size ? size - off : 0, "__span__ 1 %.1f\n", ms * 1e3);
+    }
+    return off;
+}

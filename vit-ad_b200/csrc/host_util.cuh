@@ -46,3 +46,13 @@ int device_sm_count();
 int check_device_arch();  // VITAD_OK only on compute capability 10.x
 
 }  // namespace vitad
+
+// ---- optional in-library profiler (CUDA events around every launch site; off by default) ----
+namespace vitad {
+struct ProfScope {
+    ProfScope(const char* name, cudaStream_t stream);
+    ~ProfScope();
+    int idx;
+    cudaStream_t stream;
+};
+}  // namespace vitad

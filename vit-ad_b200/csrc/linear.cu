@@ -174,6 +174,9 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int bn = a.block_n == 0 ? pick_block_n(a.m, a.n) : a.block_n;
+    char pname[64];
+    snprintf(pname, sizeof(pname), "gemm_epi%d_n%d_k%d_bn%d", a.epilogue, a.n, a.k, bn);
+    ProfScope prof(pname, s);
     if (bn == 256) return dispatch_epilogue<256>(a, s);
     if (bn == 128) return dispatch_epilogue<128>(a, s);
     if (bn == 96) return dispatch_epilogue<96>(a, s);

@@ -436,6 +436,7 @@ extern "C" int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, cons
     int n_kc, kc, kcv;
     rc = vitad_gmm_plan(num_gaussians, &n_kc, &kc, &kcv);
     if (rc) return rc;
+    ProfScope prof("gmm_logpi", static_cast<cudaStream_t>(stream));
     gmm_logpi_kernel<<<(tokens + kPiBM - 1) / kPiBM, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, num_gaussians, n_kc, kc, kcv);
     VITAD_CUDA_OK(cudaGetLastError());
@@ -458,11 +459,15 @@ extern "C" int vitad_gmm_patch_loglik(const void* xaug, const void* packed, cons
     rc = vitad_gmm_plan(num_gaussians, &n_kc, &kc, &kcv);
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (n_kc == 1)
-        rc = launch_mdn<112, 1>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
-    else
-        rc = launch_mdn<72, 2>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
+    {
+        ProfScope prof("gmm_fused", s);
+        if (n_kc == 1)
+            rc = launch_mdn<112, 1>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
+        else
+            rc = launch_mdn<72, 2>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
+    }
     if (rc) return rc;
+    ProfScope prof2("gmm_mean", s);
     gmm_mean_kernel<<<(tokens + 255) / 256, 256, 0, s>>>(ll_ws, ld_ws, L, tokens, dim);
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);

@@ -144,6 +144,7 @@ extern "C" int vitad_layernorm(const float* x, const float* weight, const float*
                   "token remap");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int blocks = (rows + 7) / 8;
+    ProfScope prof("layernorm", s);
     if (c <= 768)
         layernorm_kernel<6><<<blocks, 256, 0, s>>>(x, weight, bias, static_cast<__half*>(out_f16), out_f32, rows, c,
                                                   ldx, ld_f16, ld_f32, in_tokens, out_tokens, skip, eps, aug_ones);
