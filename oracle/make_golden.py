@@ -202,12 +202,32 @@ def case_recon_l2():
          image_scores=score.numpy())
 
 
+def case_recon_validator():
+    """ValidatorRecon.valid_loop_mse with get_model('ae_deit_small') (DeiT stress weights + small CNN decoder), B=2."""
+    from src.pipeline.ValidatorRecon import ValidatorRecon
+    from src.util.ModelHelper import get_model
+
+    model = get_model("ae_deit_small", 224, requires_grad=True)
+    sd = {("encoder." + k): v for k, v in W.make_deit_state_dict(seed=11, stress=True).items()}
+    sd.update(W.make_small_decoder_state_dict(seed=41))
+    imgs = W.synthetic_images(seed=8, batch=2)
+    pl, il = synthetic_labels(2, seed=0)
+    batches = [(imgs, pl, il)]
+    props = {"dataset": "synthetic", "dataclass": "x", "fp_thres": 0.3}
+    val = ValidatorRecon(model, ListLoader(batches), props, weights_object=sd)
+    with torch.no_grad():
+        res = val.valid_loop_mse(batches)
+    save("recon_validator", image_scores=res["image_scores"], pixel_scores_sub=res["pixel_scores"][:, :, ::8, ::8],
+         pixel_scores_sum=res["pixel_scores"].sum(axis=(1, 2, 3)), recons_sub=res["recons"][:, :, ::8, ::8])
+
+
 CASES = {
     "deit": case_deit,
     "gmm_validator": case_gmm_validator,
     "gmm_head_k130": case_gmm_head_k130,
     "nf_validator": case_nf_validator,
     "recon_l2": case_recon_l2,
+    "recon_validator": case_recon_validator,
 }
 
 if __name__ == "__main__":

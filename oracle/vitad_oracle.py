@@ -209,6 +209,22 @@ def tokens_to_nchw(tokens: Tensor) -> Tensor:
 # ----------------------------------------------------------------------------------------------
 # Reconstruction head scoring tail  (src/classes/CnnAutoEncoder.py:49,68-74; ValidatorRecon.py:109-116)
 # ----------------------------------------------------------------------------------------------
+def small_decoder_forward(sd: dict, z: Tensor, prefix: str = "decoder.", fmap: int = 7, eps: float = 1e-5) -> Tensor:
+    """DecoderVanillaCNN.forward in eval mode (src/classes/CnnDecoder.py:16-117): Linear-ReLU-Linear-ReLU,
+    unflatten to [768,f,f], 5 x (ConvTranspose2d k3 s2 p1 op1, BatchNorm(running stats), ReLU), Tanh last."""
+    p = prefix
+    h = F.relu(z @ sd[p + "decoder_lin.0.weight"].t() + sd[p + "decoder_lin.0.bias"])
+    h = F.relu(h @ sd[p + "decoder_lin.2.weight"].t() + sd[p + "decoder_lin.2.bias"])
+    h = h.reshape(z.shape[0], 768, fmap, fmap)
+    for i in range(5):
+        c, bn = f"{p}decoder_cnn.{3 * i}.", f"{p}decoder_cnn.{3 * i + 1}."
+        h = F.conv_transpose2d(h, sd[c + "weight"], sd[c + "bias"], stride=2, padding=1, output_padding=1)
+        h = (h - sd[bn + "running_mean"].view(1, -1, 1, 1)) / torch.sqrt(sd[bn + "running_var"].view(1, -1, 1, 1) + eps)
+        h = h * sd[bn + "weight"].view(1, -1, 1, 1) + sd[bn + "bias"].view(1, -1, 1, 1)
+        h = torch.tanh(h) if i == 4 else F.relu(h)
+    return h
+
+
 def recon_l2_scores(recon: Tensor, images: Tensor):
     """MSELoss(reduction='none') → mean over channels (keepdim) → amax per image."""
     amap = ((recon - images) ** 2).mean(dim=1, keepdim=True)

@@ -127,6 +127,34 @@ def make_nf_state_dict(seed: int, channels: int = 768, grid: int = 14, hidden_ra
     return sd
 
 
+def make_small_decoder_state_dict(seed: int, z_space: int = 768, fmap: int = 7, prefix: str = "decoder.") -> dict:
+    """DecoderVanillaCNN(z_space=768, first_feature_map_size=7) (CnnDecoder.py:16-117): init_weights = xavier-normal
+    weights, bias 0.001; BatchNorm affine 1/0 with non-trivial (seeded) running statistics so eval-mode BN is
+    exercised.  The Sequential re-registers the conv modules, so both key spellings are emitted."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    sd["decoder_lin.0.weight"] = _xavier_normal(g, (2 * z_space, z_space))
+    sd["decoder_lin.0.bias"] = torch.full((2 * z_space,), 0.001)
+    sd["decoder_lin.2.weight"] = _xavier_normal(g, (768 * fmap * fmap, 2 * z_space))
+    sd["decoder_lin.2.bias"] = torch.full((768 * fmap * fmap,), 0.001)
+    chans = [768, 384, 192, 96, 48, 3]
+    for i in range(5):
+        cin, cout = chans[i], chans[i + 1]
+        # ConvTranspose2d weight is [in, out, k, k]; xavier fans as torch computes them for that shape
+        std = math.sqrt(2.0 / ((cin + cout) * 9))
+        w = torch.randn(cin, cout, 3, 3, generator=g) * std
+        b = torch.full((cout,), 0.001)
+        for name in (f"recon_conv{i + 1}", f"decoder_cnn.{3 * i}"):
+            sd[name + ".weight"], sd[name + ".bias"] = w, b
+        bn = f"decoder_cnn.{3 * i + 1}."
+        sd[bn + "weight"] = 1 + 0.1 * torch.randn(cout, generator=g)
+        sd[bn + "bias"] = 0.05 * torch.randn(cout, generator=g)
+        sd[bn + "running_mean"] = 0.01 * torch.randn(cout, generator=g)
+        sd[bn + "running_var"] = 0.01 + 0.01 * torch.rand(cout, generator=g)
+        sd[bn + "num_batches_tracked"] = torch.tensor(1)
+    return {prefix + k: v for k, v in sd.items()}
+
+
 def synthetic_images(seed: int, batch: int, size: int = 224) -> torch.Tensor:
     """fp32 NCHW in [0,1] — the loader's ToTensor contract (GeneralDataset.py:38-59)."""
     g = torch.Generator().manual_seed(1000 + seed)

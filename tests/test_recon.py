@@ -1,0 +1,60 @@
+"""Reconstruction path (config 4): the oracle and the CUDA drop-in against ValidatorRecon.valid_loop_mse of the
+reference (golden fixture recon_validator.npz: ae_deit_small = DeiT + small CNN decoder, B=2)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden
+from oracle import vitad_oracle as O
+from oracle import weights as W
+
+
+def _weights():
+    sd = {("encoder." + k): v for k, v in W.make_deit_state_dict(seed=11, stress=True).items()}
+    sd.update(W.make_small_decoder_state_dict(seed=41))
+    return sd
+
+
+def test_recon_oracle_matches_reference_golden():
+    g = golden("recon_validator")
+    sd = _weights()
+    imgs = W.synthetic_images(seed=8, batch=2)
+    with torch.no_grad():
+        _, cls = O.deit_forward(sd, imgs, prefix="encoder.deit.")
+        recon = O.small_decoder_forward(sd, cls)
+        score, amap = O.recon_l2_scores(recon, imgs)
+    np.testing.assert_allclose(recon.numpy()[:, :, ::8, ::8], g["recons_sub"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(score.numpy(), g["image_scores"], rtol=1e-4)
+    np.testing.assert_allclose(amap.numpy()[:, :, ::8, ::8], g["pixel_scores_sub"], rtol=1e-3, atol=1e-6)
+
+
+def test_get_model_names_and_state_dict_keys():
+    from vitad.model_helper import get_model, get_possible_models
+
+    assert {"enc_deit", "ae_deit", "ae_deit_small"} <= set(get_possible_models())
+    assert get_model("nope") is None
+    model = get_model("ae_deit_small", 224)
+    assert set(model.state_dict().keys()) == set(_weights().keys())
+    assert model.architecture == "transformer" and type(model.decoder).__name__ == "DecoderVanillaCNN"
+    with pytest.raises(NotImplementedError):
+        get_model("ae_deit", 224)  # reverse-ResNet decoder: not provided
+
+
+@pytest.mark.gpu
+def test_recon_validator_matches_reference_golden():
+    from vitad.model_helper import get_model
+    from vitad.validators import ValidatorRecon
+
+    g = golden("recon_validator")
+    model = get_model("ae_deit_small", 224)
+    imgs = W.synthetic_images(seed=8, batch=2)
+    batches = [(imgs, torch.zeros(2, 1, 224, 224), torch.tensor([0, 1]))]
+    props = {"dataset": "synthetic", "dataclass": "x", "fp_thres": 0.3}
+    val = ValidatorRecon(model, None, props, weights_object=_weights())
+    res = val.valid_loop_mse(batches)
+    assert set(res) >= {"image_scores", "pixel_scores", "image_labels", "pixel_labels", "origs", "recons"}
+    assert res["pixel_scores"].shape == (2, 1, 224, 224) and res["recons"].shape == (2, 3, 224, 224)
+    # the cls token comes from the fp16-operand encoder; the decoder amplifies it through 7 layers
+    assert np.abs(res["recons"][:, :, ::8, ::8] - g["recons_sub"]).max() <= 2e-3
+    assert np.abs(res["image_scores"] - g["image_scores"]).max() <= 1e-3 * np.abs(g["image_scores"]).max()
+    assert np.abs(res["pixel_scores"][:, :, ::8, ::8] - g["pixel_scores_sub"]).max() <= 1e-3 * g["pixel_scores_sub"].max()

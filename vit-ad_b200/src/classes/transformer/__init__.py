@@ -1,0 +1,3 @@
+from ..._overlay import extend
+
+__path__ = extend(list(__path__), "classes", "transformer")

@@ -116,3 +116,62 @@ class ValidatorMdn:
         loader = self.dataloader.get_dataloader(centering=centering)
         result = self.valid_loop_transformer(loader)
         return calc_all_metrics(result, fp_thres=self.props.get("fp_thres", 0.3), dataset_name=self.dataset_name)
+
+
+def _collect(loop_body, dataloader, shard, with_recons=False):
+    """Shared batch loop: `loop_body(images, batch_index)` → (scores, maps[, recons]) device tensors."""
+    acc = {k: [] for k in ("image_scores", "pixel_scores", "image_labels", "pixel_labels", "origs", "recons")}
+    index, sizes = [], []
+    with torch.no_grad():
+        for bi, (images, pixel_labels, image_labels) in enumerate(dataloader):
+            if not shard.mine(bi):
+                continue
+            out = loop_body(images, bi)
+            acc["image_scores"].append(out[0].cpu().numpy())
+            acc["pixel_scores"].append(out[1].cpu().numpy())
+            if with_recons:
+                acc["recons"].append(out[2].cpu().numpy())
+            acc["image_labels"].append(np.asarray(image_labels))
+            acc["pixel_labels"].append(np.asarray(pixel_labels))
+            acc["origs"].append(np.asarray(images.cpu() if torch.is_tensor(images) else images))
+            index.append(bi)
+            sizes.append(int(out[0].shape[0]))
+    res = {k: np.concatenate(v, axis=0) for k, v in acc.items() if v}
+    res["batch_index"], res["batch_sizes"] = np.asarray(index), np.asarray(sizes)
+    return res
+
+
+class ValidatorRecon:
+    """Drop-in for src/pipeline/ValidatorRecon.py:21-136: reconstruction → per-pixel L2 map → amax."""
+
+    def __init__(self, model, dataloader, props: dict, weights_object: dict | None = None,
+                 weights_base_path: str = "", weights_name: str = "", rank: int = 0, world_size: int = 1):
+        self.model = model
+        self.dataloader = dataloader
+        self.dataset_name = f"{props['dataset']}_{props['dataclass']}"
+        self.run_name = f"recon_{type(model.decoder).__name__}"
+        self.props = props
+        self.device = _require_cuda()
+        self.shard = _BatchSharding(rank, world_size)
+        if weights_object is not None:
+            model.load_state_dict(weights_object)
+        elif weights_name:
+            model.load_state_dict(torch.load(os.path.join(weights_base_path, weights_name),
+                                             map_location=torch.device("cpu")))
+
+    def score_batch(self, images: torch.Tensor, batch_index: int = 0):
+        """ValidatorRecon.py:107-116 → (image_scores [B], pixel_scores [B,1,S,S], reconstruction)."""
+        images = images.to(self.device, non_blocking=True).to(torch.float32)
+        output = self.model(images)
+        amap, score = self.model.anomaly_map_and_score(output.reconstruction, images)
+        return score, amap, output.reconstruction
+
+    def valid_loop_mse(self, dataloader: Iterable) -> dict:
+        self.model.to(self.device).eval()
+        return _collect(self.score_batch, dataloader, self.shard, with_recons=True)
+
+    def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
+        from .metrics import calc_all_metrics
+
+        result = self.valid_loop_mse(self.dataloader.get_dataloader(centering=centering))
+        return calc_all_metrics(result, fp_thres=self.props.get("fp_thres", 0.3), dataset_name=self.dataset_name)
