@@ -61,7 +61,8 @@ typedef enum vitad_epilogue {
     VITAD_EPI_RESIDUAL_F32 = 2,   /* out_f32  = resid_f32 + acc + bias (timm Block residual) */
     VITAD_EPI_QKV = 3,            /* head-major q (pre-scaled), k, transposed v             */
     VITAD_EPI_PATCH_EMBED = 4,    /* + bias + pos_embed, written behind the prefix tokens   */
-    VITAD_EPI_F32 = 5             /* out_f32 = acc (+ bias if non-null)                     */
+    VITAD_EPI_F32 = 5,            /* out_f32 = acc (+ bias if non-null)                     */
+    VITAD_EPI_BIAS_RELU_F16 = 6   /* out_f16 = relu(acc + bias)  (FastFlow subnet, NormalizingFlow.py:61-82) */
 } vitad_epilogue;
 
 typedef struct vitad_linear_args {
@@ -171,6 +172,42 @@ int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, const float* pi
 int vitad_gmm_patch_loglik(const void* xaug, const void* packed, const float* lp2, const float* x, int ldx,
                            float* ll_ws, int ld_ws, float* L, int tokens, int dim, int num_gaussians, void* stream);
 int vitad_gmm_finish(const float* L, float* prob, float* scores, int batch, int patches, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Normalizing-flow (FastFlow) head: NormalizingFlow.forward (src/classes/NormalizingFlow.py:118-145) over
+ * FrEIA 0.2 AllInOneBlock steps (:84-116).  Per-step device pointers (packed by the host mirror,
+ * vitad/nf.py):
+ *   w0p fp16 [64, taps*384]   first subnet conv, rows = hidden channels (61 padded to 64), cols (tap, c_in)
+ *   b0p fp32 [64]
+ *   w2p fp16 [768, taps*64]   second subnet conv x 0.1, rows interleaved per 96-row tile: 48 s-channels, 48 t-channels
+ *   b2p fp32 [768]            same order, x 0.1
+ *   scale, offset fp32 [768]  0.1*softplus_{beta=.5}(global_scale), global_offset
+ *   inv_perm int32 [768]      y channel j is stored at stream row inv_perm[j]  (w_perm as an index)
+ * tokens fp32 [batch*grid*grid, 768] (= patch_embedding); outputs: one_minus_prob fp32 [batch*grid*grid]
+ * (= 1 - exp(-0.5 mean_c z^2), feed to vitad_bilinear_up with align_corners=0) and loss_terms fp32 [batch]
+ * (= 0.5*sum z^2 - log|det J|; the reference's loss is their mean).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct vitad_nf_step {
+    const void* w0p;
+    const float* b0p;
+    const void* w2p;
+    const float* b2p;
+    const float* scale;
+    const float* offset;
+    const int* inv_perm;
+    int ksize; /* 1 or 3 */
+} vitad_nf_step;
+
+typedef struct vitad_nf_weights {
+    int channels, grid, hidden_pad, steps;
+    float clamp;        /* affine_clamping (2.0) */
+    float logdet_const; /* sum over steps of grid*grid*sum(log scale) */
+    const vitad_nf_step* step; /* host array of `steps` entries */
+} vitad_nf_weights;
+
+size_t vitad_nf_workspace_bytes(const vitad_nf_weights* w, int batch);
+int vitad_nf_forward(const vitad_nf_weights* w, const float* tokens, int batch, void* workspace,
+                     size_t workspace_bytes, float* one_minus_prob, float* loss_terms, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Anomaly-map tails.

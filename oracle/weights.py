@@ -150,7 +150,7 @@ def make_small_decoder_state_dict(seed: int, z_space: int = 768, fmap: int = 7, 
         sd[bn + "weight"] = 1 + 0.1 * torch.randn(cout, generator=g)
         sd[bn + "bias"] = 0.05 * torch.randn(cout, generator=g)
         sd[bn + "running_mean"] = 0.01 * torch.randn(cout, generator=g)
-        sd[bn + "running_var"] = 0.01 + 0.01 * torch.rand(cout, generator=g)
+        sd[bn + "running_var"] = 0.5 + torch.rand(cout, generator=g)
         sd[bn + "num_batches_tracked"] = torch.tensor(1)
     return {prefix + k: v for k, v in sd.items()}
 

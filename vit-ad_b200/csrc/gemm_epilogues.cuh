@@ -60,8 +60,8 @@ __device__ __forceinline__ void store_h(__half* dst, const float (&v)[W]) {
     }
 }
 
-// out_f16[row][col] = act(acc + bias[col]);  act = identity or exact-erf GELU (timm Mlp: nn.GELU()).
-template <int BLOCK_N, bool GELU>
+// out_f16[row][col] = act(acc + bias[col]);  ACT: 0 identity, 1 exact-erf GELU (timm Mlp: nn.GELU()), 2 ReLU.
+template <int BLOCK_N, int ACT>
 struct EpiBiasH {
     static constexpr int W = EpiChunk<BLOCK_N>::kW;
     static constexpr bool kSplitColumns = true;
@@ -80,7 +80,7 @@ struct EpiBiasH {
 #pragma unroll
                 for (int j = 0; j < W; ++j) {
                     float x = v[j] + b[j];
-                    v[j] = GELU ? gelu_erf(x) : x;
+                    v[j] = ACT == 1 ? gelu_erf(x) : (ACT == 2 ? fmaxf(x, 0.f) : x);
                 }
                 store_h<W>(out + static_cast<size_t>(row) * ldo + col, v);
             }

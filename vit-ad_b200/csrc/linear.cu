@@ -70,11 +70,15 @@ template <int BLOCK_N>
 static int dispatch_epilogue(const vitad_linear_args& a, cudaStream_t stream) {
     switch (a.epilogue) {
         case VITAD_EPI_BIAS_F16: {
-            EpiBiasH<BLOCK_N, false> e{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n};
+            EpiBiasH<BLOCK_N, 0> e{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n};
             return launch_gemm<BLOCK_N>(a, e, stream);
         }
         case VITAD_EPI_BIAS_GELU_F16: {
-            EpiBiasH<BLOCK_N, true> e{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n};
+            EpiBiasH<BLOCK_N, 1> e{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n};
+            return launch_gemm<BLOCK_N>(a, e, stream);
+        }
+        case VITAD_EPI_BIAS_RELU_F16: {
+            EpiBiasH<BLOCK_N, 2> e{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n};
             return launch_gemm<BLOCK_N>(a, e, stream);
         }
         case VITAD_EPI_RESIDUAL_F32: {
@@ -149,6 +153,7 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
     switch (a.epilogue) {
         case VITAD_EPI_BIAS_F16:
         case VITAD_EPI_BIAS_GELU_F16:
+        case VITAD_EPI_BIAS_RELU_F16:
             VITAD_REQUIRE(a.out && aligned16(a.out) && a.ldo % 8 == 0 && a.ldo >= a.n, VITAD_ERR_ALIGN,
                           "fp16 output must be 16-byte aligned with pitch %% 8 == 0");
             break;

@@ -1,0 +1,319 @@
+// Normalizing-flow (FastFlow) head: src/classes/NormalizingFlow.py:84-145 with FrEIA 0.2 AllInOneBlock steps.
+//
+// Per step i (kernel 3x3 on even, 1x1 on odd steps, :96-100):
+//   x1,x2 = split(x, 384|384);  h = relu(conv_k(x1));  a = 0.1*conv_k(h);  s = clamp*tanh(a[:, :384])
+//   y = cat(x1, x2*exp(s) + a[:, 384:]) * scale + offset;   x' = y[:, perm]   (w_perm is a 0/1 matrix)
+//   logdet += sum(s) + H*W*sum(log scale)
+// Design:
+//   * the activation stream lives channel-major in HBM (xT fp32 [768][tokens]) so the channel permutation is a
+//     ROW permutation of the epilogue's (token-coalesced) stores — the reference spends 4.6 GFLOP/img on a dense
+//     768x768 conv of zeros and ones for it;
+//   * both subnet convolutions are tcgen05 GEMMs over token-major fp16 operands (3x3: im2col rows with zero
+//     padding at the 14x14 borders); conv1 uses the bias+ReLU epilogue, conv2's weight rows are interleaved so one
+//     96-column accumulator tile holds [s(48 channels) | t(48 channels)], and its epilogue (EpiNfCouple) does the
+//     coupling, the global affine, the permuted store and the per-token sum of s;
+//   * log-det partial sums are written per (channel tile, token) and reduced in fixed order (deterministic).
+#include <atomic>
+
+#include "gemm_pair.cuh"
+#include "host_util.cuh"
+
+namespace vitad {
+extern std::atomic<uint64_t> g_launches;
+extern std::atomic<int> g_use_pair;
+
+constexpr int kNfTile = 96;   // accumulator columns per tile: 48 s-channels | 48 t-channels
+constexpr int kNfHalf = 48;
+
+struct EpiNfCouple {
+    static constexpr bool kSplitColumns = false;  // a thread needs the s and the t column of its channel
+    const float* xin;    // [C][ld]
+    float* xout;         // [C][ld]
+    const float* b2p;    // [C] bias in interleaved tile order, pre-scaled by 0.1
+    const float* scale;  // [C] 0.1*softplus_{0.5}(global_scale)
+    const float* offset; // [C]
+    const int* inv_perm; // [C] y channel j is stored at stream row inv_perm[j]
+    float* sjac;         // [C/2/48][ld] per-token partial sums of s
+    int ld, M, c_half;
+    float clamp;
+    float ssum;
+
+    __device__ __forceinline__ void tile_begin(int, int, int) { ssum = 0.f; }
+    __device__ __forceinline__ void merge(int, float2*) {}
+    __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr, int, int) {
+        const bool valid = row < M;
+        const int r = valid ? row : 0;
+#pragma unroll 1
+        for (int q = 0; q < kNfHalf; q += 16) {
+            uint32_t as[16], at[16];
+            tmem_ld_x16(taddr + q, as);
+            tmem_ld_x16(taddr + kNfHalf + q, at);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int c = n_tile * kNfHalf + q + j;
+                const float a_s = __uint_as_float(as[j]) + __ldg(b2p + n_tile * kNfTile + q + j);
+                const float a_t = __uint_as_float(at[j]) + __ldg(b2p + n_tile * kNfTile + kNfHalf + q + j);
+                const float sv = clamp * tanhf(a_s);
+                const float x1v = xin[static_cast<size_t>(c) * ld + r];
+                const float x2v = xin[static_cast<size_t>(c_half + c) * ld + r];
+                const float y2 = x2v * expf(sv) + a_t;
+                if (valid) {
+                    xout[static_cast<size_t>(__ldg(inv_perm + c)) * ld + row] = x1v * __ldg(scale + c) + __ldg(offset + c);
+                    xout[static_cast<size_t>(__ldg(inv_perm + c_half + c)) * ld + row] =
+                        y2 * __ldg(scale + c_half + c) + __ldg(offset + c_half + c);
+                }
+                ssum += sv;
+            }
+        }
+    }
+    __device__ __forceinline__ void tile_end(int, int n_tile, int row) {
+        if (row < M) sjac[static_cast<size_t>(n_tile) * ld + row] = ssum;
+    }
+};
+
+// in [rows][cols] fp32 row-major -> out [cols][ld] (transpose), 32x32 tiles through shared memory.
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                            int rows, int cols, int ld_out) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8)
+        if (r0 + i < rows && c0 + tx < cols) tile[i][tx] = in[static_cast<size_t>(r0 + i) * cols + c0 + tx];
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows) out[static_cast<size_t>(c0 + i) * ld_out + r0 + tx] = tile[tx][i];
+}
+
+// xT [.. >= c1][ld] fp32 -> out fp16 [M][c1] (first c1 channels, token-major GEMM operand).
+__global__ void __launch_bounds__(256) stream_to_operand_kernel(const float* __restrict__ xT, int ld,
+                                                                __half* __restrict__ out, int M, int c1) {
+    __shared__ float tile[32][33];
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < c1 && t0 + tx < M) tile[i][tx] = xT[static_cast<size_t>(c0 + i) * ld + t0 + tx];
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (t0 + i < M && c0 + tx < c1) out[static_cast<size_t>(t0 + i) * c1 + c0 + tx] = to_h(tile[tx][i]);
+}
+
+// 3x3 im2col on a g x g grid per image, zero padding: in fp16 [M][cw] -> out fp16 [M][9*cw], column (tap, c),
+// tap = ky*3+kx.  One thread moves 8 channels (16 bytes).
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const __half* __restrict__ in, __half* __restrict__ out, int M,
+                                                        int cw, int g, size_t total) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int v_per_tap = cw >> 3;
+    const int v = static_cast<int>(idx % v_per_tap);
+    size_t r = idx / v_per_tap;
+    const int tap = static_cast<int>(r % 9);
+    const int t = static_cast<int>(r / 9);
+    const int p = t % (g * g);
+    const int y = p / g + tap / 3 - 1, x = p % g + tap % 3 - 1;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < g && x >= 0 && x < g) {
+        const int src = t - p + y * g + x;
+        val = *reinterpret_cast<const uint4*>(in + static_cast<size_t>(src) * cw + v * 8);
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * 9 * cw + tap * cw + v * 8) = val;
+}
+
+// One block per image: omp[t] = 1 - exp(-0.5*mean_c z^2) (NormalizingFlow.py:134-137) and
+// loss_term[b] = 0.5*sum z^2 - (sum of s partials + logdet_const) (:130-132).
+__global__ void __launch_bounds__(256) nf_finish_kernel(const float* __restrict__ zT, int ld,
+                                                        const float* __restrict__ sjac, int n_partials,
+                                                        float logdet_const, int P, int C, float* __restrict__ omp,
+                                                        float* __restrict__ loss_terms) {
+    __shared__ float red_z[8], red_s[8];
+    const int b = blockIdx.x;
+    float zz_tot = 0.f, s_tot = 0.f;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        const int t = b * P + p;
+        float zz = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float z = zT[static_cast<size_t>(c) * ld + t];
+            zz = fmaf(z, z, zz);
+        }
+        omp[t] = 1.0f - expf(-0.5f * (zz / C));
+        zz_tot += zz;
+        float s = 0.f;
+        for (int k = 0; k < n_partials; ++k) s += sjac[static_cast<size_t>(k) * ld + t];
+        s_tot += s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        zz_tot += __shfl_xor_sync(0xffffffffu, zz_tot, o);
+        s_tot += __shfl_xor_sync(0xffffffffu, s_tot, o);
+    }
+    if ((threadIdx.x & 31) == 0) red_z[threadIdx.x >> 5] = zz_tot, red_s[threadIdx.x >> 5] = s_tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float z = 0.f, s = 0.f;
+        for (int i = 0; i < (blockDim.x >> 5); ++i) z += red_z[i], s += red_s[i];
+        loss_terms[b] = 0.5f * z - (s + logdet_const);
+    }
+}
+
+static int launch_couple(const void* a2, const void* w2p, int M, int C, int K2, const EpiNfCouple& epi,
+                         cudaStream_t stream) {
+    CUtensorMap ta, tb;
+    int rc = make_tmap_f16_2d(&ta, a2, M, K2, K2, kBlockM);
+    if (rc) return rc;
+    const int n_tiles = C / kNfTile;
+    if (g_use_pair.load() && M > kBlockM) {
+        using S = PairSmem<kNfTile>;
+        rc = make_tmap_f16_2d(&tb, w2p, C, K2, K2, kNfTile / 2);
+        if (rc) return rc;
+        auto kern = gemm2_tc_kernel<kNfTile, 1, EpiNfCouple>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            VITAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
+            attr_set = true;
+        }
+        const int tiles = ((M + 2 * kBlockM - 1) / (2 * kBlockM)) * n_tiles;
+        const int maxc = device_sm_count() / 2;
+        const int clusters = tiles < maxc ? tiles : maxc;
+        kern<<<2 * clusters, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, M, n_tiles, K2, epi);
+    } else {
+        using S = GemmSmem<kNfTile>;
+        rc = make_tmap_f16_2d(&tb, w2p, C, K2, K2, kNfTile);
+        if (rc) return rc;
+        auto kern = gemm_tc_kernel<kNfTile, 1, EpiNfCouple>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            VITAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
+            attr_set = true;
+        }
+        const int tiles = ((M + kBlockM - 1) / kBlockM) * n_tiles;
+        const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+        kern<<<grid, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, M, n_tiles, K2, epi);
+    }
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+namespace {
+struct NfWs {
+    float *xa, *xb, *sjac;
+    void *x1h, *a1, *h, *a2;
+    int ld;
+    size_t total;
+};
+NfWs carve_nf(const vitad_nf_weights& w, int batch, void* base) {
+    uint8_t* p = static_cast<uint8_t*>(base);
+    size_t used = 0;
+    auto take = [&](size_t bytes) {
+        void* r = p ? p + used : nullptr;
+        used += (bytes + 255) & ~static_cast<size_t>(255);
+        return r;
+    };
+    const size_t M = static_cast<size_t>(batch) * w.grid * w.grid;
+    NfWs s;
+    s.ld = static_cast<int>((M + 31) / 32 * 32);
+    const int c1 = w.channels - w.channels / 2;
+    s.xa = static_cast<float*>(take(static_cast<size_t>(w.channels) * s.ld * 4));
+    s.xb = static_cast<float*>(take(static_cast<size_t>(w.channels) * s.ld * 4));
+    s.sjac = static_cast<float*>(take(static_cast<size_t>(w.steps) * (w.channels / kNfTile) * s.ld * 4));
+    s.x1h = take(M * c1 * 2);
+    s.a1 = take(M * 9 * c1 * 2);
+    s.h = take(M * w.hidden_pad * 2);
+    s.a2 = take(M * 9 * w.hidden_pad * 2);
+    s.total = used;
+    return s;
+}
+}  // namespace
+
+}  // namespace vitad
+
+using namespace vitad;
+
+extern "C" size_t vitad_nf_workspace_bytes(const vitad_nf_weights* w, int batch) {
+    if (!w || batch <= 0) return 0;
+    return carve_nf(*w, batch, nullptr).total;
+}
+
+extern "C" int vitad_nf_forward(const vitad_nf_weights* wp, const float* tokens, int batch, void* workspace,
+                                size_t workspace_bytes, float* one_minus_prob, float* loss_terms, void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(wp && tokens && workspace && one_minus_prob && loss_terms, VITAD_ERR_ARG, "null pointer");
+    const vitad_nf_weights& w = *wp;
+    VITAD_REQUIRE(w.channels == 768 && w.hidden_pad == 64 && w.grid > 0 && w.steps > 0 && w.step, VITAD_ERR_SHAPE,
+                  "unsupported flow geometry (channels %d hidden_pad %d)", w.channels, w.hidden_pad);
+    VITAD_REQUIRE(batch > 0, VITAD_ERR_SHAPE, "empty batch");
+    VITAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, VITAD_ERR_ALIGN, "workspace alignment");
+    NfWs ws = carve_nf(w, batch, workspace);
+    VITAD_REQUIRE(workspace_bytes >= ws.total, VITAD_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, ws.total);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int P = w.grid * w.grid, M = batch * P, C = w.channels, c_half = C / 2, c1 = C - c_half;
+
+    // tokens [M][C] -> channel-major stream (the reference's transpose(2,1).reshape, ValidatorNF.py:130-134)
+    {
+        ProfScope prof("nf_transpose", s);
+        dim3 grid((M + 31) / 32, (C + 31) / 32);
+        transpose_f32_kernel<<<grid, 256, 0, s>>>(tokens, ws.xa, M, C, ws.ld);
+        VITAD_CUDA_OK(cudaGetLastError());
+        g_launches.fetch_add(1);
+    }
+    float* xin = ws.xa;
+    float* xout = ws.xb;
+    for (int i = 0; i < w.steps; ++i) {
+        const vitad_nf_step& st = w.step[i];
+        VITAD_REQUIRE(st.ksize == 1 || st.ksize == 3, VITAD_ERR_SHAPE, "subnet kernel size %d", st.ksize);
+        {
+            ProfScope prof("nf_operand", s);
+            dim3 grid((M + 31) / 32, (c1 + 31) / 32);
+            stream_to_operand_kernel<<<grid, 256, 0, s>>>(xin, ws.ld, static_cast<__half*>(ws.x1h), M, c1);
+            VITAD_CUDA_OK(cudaGetLastError());
+            g_launches.fetch_add(1);
+        }
+        const void* a1 = ws.x1h;
+        int k1 = c1;
+        if (st.ksize == 3) {
+            ProfScope prof("nf_im2col", s);
+            const size_t total = static_cast<size_t>(M) * 9 * (c1 / 8);
+            im2col3x3_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+                static_cast<const __half*>(ws.x1h), static_cast<__half*>(ws.a1), M, c1, w.grid, total);
+            VITAD_CUDA_OK(cudaGetLastError());
+            g_launches.fetch_add(1);
+            a1 = ws.a1;
+            k1 = 9 * c1;
+        }
+        vitad_linear_args la;
+        memset(&la, 0, sizeof(la));
+        la.a = a1, la.w = st.w0p, la.bias = st.b0p, la.m = M, la.n = w.hidden_pad, la.k = k1, la.lda = k1, la.ldw = k1;
+        la.epilogue = VITAD_EPI_BIAS_RELU_F16, la.out = ws.h, la.ldo = w.hidden_pad, la.block_n = 96;
+        if ((rc = vitad_linear_f16(&la, s))) return rc;
+        const void* a2 = ws.h;
+        int k2 = w.hidden_pad;
+        if (st.ksize == 3) {
+            ProfScope prof("nf_im2col", s);
+            const size_t total = static_cast<size_t>(M) * 9 * (w.hidden_pad / 8);
+            im2col3x3_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+                static_cast<const __half*>(ws.h), static_cast<__half*>(ws.a2), M, w.hidden_pad, w.grid, total);
+            VITAD_CUDA_OK(cudaGetLastError());
+            g_launches.fetch_add(1);
+            a2 = ws.a2;
+            k2 = 9 * w.hidden_pad;
+        }
+        EpiNfCouple epi{xin,     xout,  st.b2p, st.scale, st.offset, st.inv_perm,
+                        ws.sjac + static_cast<size_t>(i) * (C / kNfTile) * ws.ld, ws.ld, M, c_half, w.clamp, 0.f};
+        {
+            ProfScope prof("nf_couple_gemm", s);
+            if ((rc = launch_couple(a2, st.w2p, M, C, k2, epi, s))) return rc;
+        }
+        float* t = xin;
+        xin = xout;
+        xout = t;
+    }
+    {
+        ProfScope prof("nf_finish", s);
+        nf_finish_kernel<<<batch, 256, 0, s>>>(xin, ws.ld, ws.sjac, w.steps * (C / kNfTile), w.logdet_const, P, C,
+                                               one_minus_prob, loss_terms);
+        VITAD_CUDA_OK(cudaGetLastError());
+        g_launches.fetch_add(1);
+    }
+    return VITAD_OK;
+}

@@ -134,6 +134,21 @@ lib.vitad_bilinear_up.restype = _i
 lib.vitad_l2_map_score.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]
 lib.vitad_l2_map_score.restype = _i
 
+# ---------------------------------------------------------------------------- normalizing flow
+class NfStep(C.Structure):
+    _fields_ = [(n, _vp) for n in ("w0p", "b0p", "w2p", "b2p", "scale", "offset", "inv_perm")] + [("ksize", _i)]
+
+
+class NfWeights(C.Structure):
+    _fields_ = [("channels", _i), ("grid", _i), ("hidden_pad", _i), ("steps", _i), ("clamp", _f),
+                ("logdet_const", _f), ("step", C.POINTER(NfStep))]
+
+
+lib.vitad_nf_workspace_bytes.argtypes = [C.POINTER(NfWeights), _i]
+lib.vitad_nf_workspace_bytes.restype = _sz
+lib.vitad_nf_forward.argtypes = [C.POINTER(NfWeights), _vp, _i, _vp, _sz, _vp, _vp, _vp]
+lib.vitad_nf_forward.restype = _i
+
 MDN_KA = 784  # K extent of the packed MDN operands (768 + 16)
 
 

@@ -141,6 +141,43 @@ def _collect(loop_body, dataloader, shard, with_recons=False):
     return res
 
 
+BLOCK_INDEX_DEIT = 0  # src/pipeline/ValidatorNF.py:23
+
+
+class ValidatorNF:
+    """Drop-in for src/pipeline/ValidatorNF.py:26-164 (transformer encoders)."""
+
+    def __init__(self, nf_model: list, feature_extractor, dataloader, props: dict, weights_object: list | None = None,
+                 weights_base_path: str = "", weights_name: list | str = "", rank: int = 0, world_size: int = 1):
+        self.nf_model = nf_model
+        self.dataloader = dataloader
+        self.feature_extractor = feature_extractor
+        self.dataset_name = f"{props['dataset']}_{props['dataclass']}"
+        self.run_name = "nf"
+        self.props = props
+        self.device = _require_cuda()
+        self.shard = _BatchSharding(rank, world_size)
+        _load_weights(self.nf_model, weights_object, weights_base_path, weights_name)
+
+    def score_batch(self, images: torch.Tensor, batch_index: int = 0):
+        """ValidatorNF.py:123-142 → (image_scores [B], anomaly maps [B,1,S,S])."""
+        images = images.to(self.device, non_blocking=True)
+        embedding = self.feature_extractor(images, block_index=BLOCK_INDEX_DEIT).patch_embedding
+        result = self.nf_model[0].forward_tokens(embedding)
+        return result.image_max, result.anomaly_score_map
+
+    def valid_loop_transformer_nf(self, dataloader: Iterable) -> dict:
+        self.nf_model[0].to(self.device).eval()
+        self.feature_extractor.to(self.device).eval()
+        return _collect(self.score_batch, dataloader, self.shard)
+
+    def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
+        from .metrics import calc_all_metrics
+
+        result = self.valid_loop_transformer_nf(self.dataloader.get_dataloader(centering=centering))
+        return calc_all_metrics(result, fp_thres=self.props.get("fp_thres", 0.3), dataset_name=self.dataset_name)
+
+
 class ValidatorRecon:
     """Drop-in for src/pipeline/ValidatorRecon.py:21-136: reconstruction → per-pixel L2 map → amax."""
 
