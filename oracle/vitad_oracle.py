@@ -83,6 +83,109 @@ def deit_forward(sd: dict, images: Tensor, block_index: int = 0, prefix: str = "
 
 
 # ----------------------------------------------------------------------------------------------
+# EsViT Swin-T (window 14) encoder  (src/classes/transformer/SwinTransformerModule.py; EncoderEsVit,
+# src/classes/transformer/TransformerEncoder.py:211-273).  Evaluated in .eval() mode: the reference leaves the
+# encoder in train mode during MDN/NF validation, where DropPath(0.1) makes its features random
+#  — a deliberate, documented deviation.
+# ----------------------------------------------------------------------------------------------
+SWIN_DEPTHS = (2, 2, 6, 2)
+SWIN_HEADS = (3, 6, 12, 24)
+SWIN_EMBED = 96
+SWIN_WINDOW = 14
+
+
+def swin_relative_position_index(ws: int) -> Tensor:
+    """WindowAttention.__init__ (SwinTransformerModule.py:117-131)."""
+    coords = torch.stack(torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")).flatten(1)
+    rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += ws - 1
+    rel[:, :, 1] += ws - 1
+    rel[:, :, 0] *= 2 * ws - 1
+    return rel.sum(-1)
+
+
+def swin_region_ids(H: int, ws: int, shift: int) -> Tensor:
+    """Region label of every position of the shifted frame (create_attn_mask, :316-347): [H, H] in 0..8."""
+    ids = torch.zeros(H, H, dtype=torch.long)
+    bounds = (slice(0, -ws), slice(-ws, -shift), slice(-shift, None))
+    cnt = 0
+    for hs in bounds:
+        for wsl in bounds:
+            ids[hs, wsl] = cnt
+            cnt += 1
+    return ids
+
+
+def swin_windows(x: Tensor, ws: int) -> Tensor:
+    """window_partition (:50-63): [B,H,W,C] → [B*nW, ws*ws, C]."""
+    B, H, W, C = x.shape
+    return x.view(B, H // ws, ws, W // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, C)
+
+
+def swin_block(sd: dict, pre: str, x: Tensor, H: int, heads: int, ws: int, shift: int) -> Tensor:
+    """SwinTransformerBlock.forward (:349-416) + WindowAttention.forward (:144-193), eval mode, no padding
+    (every stage resolution of a 224 input is a multiple of its window)."""
+    B, L, C = x.shape
+    hd = C // heads
+    T = ws * ws
+    h = layer_norm(x, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-5).view(B, H, H, C)
+    if shift > 0:
+        h = torch.roll(h, shifts=(-shift, -shift), dims=(1, 2))
+    win = swin_windows(h, ws)  # [B*nW, T, C]
+    qkv = (win @ sd[pre + "attn.qkv.weight"].t() + sd[pre + "attn.qkv.bias"]).reshape(-1, T, 3, heads, hd)
+    qkv = qkv.permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0] * hd**-0.5, qkv[1], qkv[2]
+    attn = q @ k.transpose(-2, -1)
+    bias = sd[pre + "attn.relative_position_bias_table"][sd[pre + "attn.relative_position_index"].view(-1)]
+    attn = attn + bias.view(T, T, heads).permute(2, 0, 1).unsqueeze(0)
+    if shift > 0:
+        ids = swin_windows(swin_region_ids(H, ws, shift).view(1, H, H, 1).float(), ws).view(-1, T)  # [nW, T]
+        mask = (ids.unsqueeze(1) - ids.unsqueeze(2) != 0).float() * -100.0  # [nW, T, T]
+        nW = mask.shape[0]
+        attn = (attn.view(B, nW, heads, T, T) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, T, T)
+    attn = torch.softmax(attn, dim=-1)
+    o = (attn @ v).transpose(1, 2).reshape(-1, T, C)
+    o = o @ sd[pre + "attn.proj.weight"].t() + sd[pre + "attn.proj.bias"]
+    o = o.view(B, H // ws, H // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, H, C)  # window_reverse
+    if shift > 0:
+        o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+    x = x + o.reshape(B, L, C)
+    h = layer_norm(x, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-5)
+    h = gelu_erf(h @ sd[pre + "mlp.fc1.weight"].t() + sd[pre + "mlp.fc1.bias"])
+    return x + h @ sd[pre + "mlp.fc2.weight"].t() + sd[pre + "mlp.fc2.bias"]
+
+
+def swin_forward(sd: dict, images: Tensor, prefix: str = "esvit."):
+    """EncoderEsVit.forward (TransformerEncoder.py:269-273) = SwinTransformer.forward_features (:821-837) →
+    (patch_embedding = x_region [B,49,768], latent_space = avg-pooled [B,768])."""
+    p = prefix
+    B = images.shape[0]
+    w = sd[p + "patch_embed.proj.weight"]  # [96,3,4,4]
+    ps = w.shape[-1]
+    g = images.shape[-1] // ps
+    patches = images.reshape(B, 3, g, ps, g, ps).permute(0, 2, 4, 1, 3, 5).reshape(B, g * g, 3 * ps * ps)
+    x = patches @ w.reshape(w.shape[0], -1).t() + sd[p + "patch_embed.proj.bias"]
+    x = layer_norm(x, sd[p + "patch_embed.norm.weight"], sd[p + "patch_embed.norm.bias"], 1e-5)
+    H = g
+    for s, (depth, heads) in enumerate(zip(SWIN_DEPTHS, SWIN_HEADS)):
+        ws = min(SWIN_WINDOW, H)
+        for b in range(depth):
+            shift = 0 if (b % 2 == 0 or H <= SWIN_WINDOW) else SWIN_WINDOW // 2
+            x = swin_block(sd, f"{p}layers.{s}.blocks.{b}.", x, H, heads, ws, shift)
+        if s < len(SWIN_DEPTHS) - 1:  # PatchMerging.forward (:478-505)
+            C = x.shape[-1]
+            xv = x.view(B, H, H, C)
+            xm = torch.cat([xv[:, 0::2, 0::2], xv[:, 1::2, 0::2], xv[:, 0::2, 1::2], xv[:, 1::2, 1::2]], -1)
+            xm = xm.view(B, -1, 4 * C)
+            d = f"{p}layers.{s}.downsample."
+            xm = layer_norm(xm, sd[d + "norm.weight"], sd[d + "norm.bias"], 1e-5)
+            x = xm @ sd[d + "reduction.weight"].t()
+            H //= 2
+    x_region = layer_norm(x, sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5)
+    return x_region, x_region.mean(dim=1)
+
+
+# ----------------------------------------------------------------------------------------------
 # MDN / "GMM" head  (src/classes/MixtureDensityNetwork.py)
 # ----------------------------------------------------------------------------------------------
 def gumbel_noise(shape, generator: torch.Generator) -> Tensor:

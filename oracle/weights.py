@@ -74,6 +74,52 @@ def make_deit_state_dict(seed: int = 0, stress: bool = False, depth: int = 12, p
     return {prefix + k: v for k, v in sd.items()}
 
 
+def make_esvit_state_dict(seed: int = 0, stress: bool = False, prefix: str = "esvit.") -> dict:
+    """Vendored SwinTransformer(embed 96, depths 2/2/6/2, heads 3/6/12/24, window 14, num_classes 3) as EncoderEsVit
+    builds it (TransformerEncoder.py:228-240): Linear trunc-normal(.02)/zero bias, LayerNorm 1/0, bias tables
+    trunc-normal(.02) (SwinTransformerModule.py:132,800-808); 185 keys incl. the relative_position_index buffers."""
+    from oracle.vitad_oracle import SWIN_DEPTHS, SWIN_EMBED, SWIN_HEADS, SWIN_WINDOW, swin_relative_position_index
+
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def ln(name, c):
+        sd[name + ".weight"] = 1 + 0.1 * torch.randn(c, generator=g) if stress else torch.ones(c)
+        sd[name + ".bias"] = 0.1 * torch.randn(c, generator=g) if stress else torch.zeros(c)
+
+    def lin(name, out_f, in_f, bias=True):
+        sd[name + ".weight"] = _tn(g, (out_f, in_f), 0.02)
+        if bias:
+            sd[name + ".bias"] = 0.02 * torch.randn(out_f, generator=g) if stress else torch.zeros(out_f)
+
+    sd["patch_embed.proj.weight"] = _kaiming_uniform(g, (SWIN_EMBED, 3, 4, 4), 48)
+    sd["patch_embed.proj.bias"] = _kaiming_uniform(g, (SWIN_EMBED,), 48)
+    ln("patch_embed.norm", SWIN_EMBED)
+    res = 56
+    for s, (depth, heads) in enumerate(zip(SWIN_DEPTHS, SWIN_HEADS)):
+        C = SWIN_EMBED * 2**s
+        ws = min(SWIN_WINDOW, res)
+        for b in range(depth):
+            p = f"layers.{s}.blocks.{b}."
+            ln(p + "norm1", C)
+            sd[p + "attn.relative_position_bias_table"] = _tn(g, ((2 * ws - 1) ** 2, heads), 0.5 if stress else 0.02)
+            sd[p + "attn.relative_position_index"] = swin_relative_position_index(ws)
+            lin(p + "attn.qkv", 3 * C, C)
+            if stress:
+                sd[p + "attn.qkv.weight"][: 2 * C] *= 3.0
+            lin(p + "attn.proj", C, C)
+            ln(p + "norm2", C)
+            lin(p + "mlp.fc1", 4 * C, C)
+            lin(p + "mlp.fc2", C, 4 * C)
+        if s < 3:
+            lin(f"layers.{s}.downsample.reduction", 2 * C, 4 * C, bias=False)
+            ln(f"layers.{s}.downsample.norm", 4 * C)
+            res //= 2
+    ln("norm", 768)
+    lin("head", 3, 768)
+    return {prefix + k: v for k, v in sd.items()}
+
+
 def make_mdn_state_dict(seed: int, num_gaussians: int, dim: int = 768, stress: bool = False) -> dict:
     """GaussianMixtureDensityNetwork.__init__ (MixtureDensityNetwork.py:117-149): xavier-normal weights;
     pi/sigma biases keep the nn.Linear default, mu bias = 0.001 (HelperFunctions.py:19-23)."""

@@ -130,3 +130,15 @@ def test_bilinear_restatement_matches_torch(align, g_in):
     x = torch.rand(3, 1, g_in, g_in, generator=torch.Generator().manual_seed(1))
     ref = torch.nn.functional.interpolate(x, size=(224, 224), mode="bilinear", align_corners=align)
     np.testing.assert_allclose(O.bilinear_upsample(x, 224, align).numpy(), ref.numpy(), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,stress", [("default", False), ("stress", True)])
+def test_esvit_oracle_matches_reference_golden(tag, stress):
+    """Swin-T W14 restatement vs the reference's vendored SwinTransformerModule (eval mode)."""
+    g = golden("esvit_b2")
+    sd = W.make_esvit_state_dict(seed=51, stress=stress)
+    with torch.no_grad():
+        tok, latent = O.swin_forward(sd, W.synthetic_images(seed=9, batch=2))
+    np.testing.assert_allclose(tok.numpy()[:, ::3], g[f"{tag}_tokens"], rtol=0, atol=3e-4)
+    np.testing.assert_allclose(tok.sum(-1).numpy(), g[f"{tag}_token_sum"], rtol=0, atol=5e-3)
+    np.testing.assert_allclose(latent.numpy(), g[f"{tag}_latent"], rtol=0, atol=3e-4)
