@@ -85,6 +85,12 @@ typedef struct vitad_linear_args {
     /* PATCH_EMBED: out fp32 [B,prefix+P,N]; pos fp32 [prefix+P,N]; M = B*P */
     const float* pos;
     int patches, prefix;
+    /* QKV, optional (0 = DeiT defaults: head_dim 64, one window of `tokens`): Swin window attention.
+     * q,k become [B*windows,H,win_tokens,head_dim], vt [B*windows,H,head_dim,tokens_pad]; tok2win int32 [tokens]
+     * maps a token of the image to window*win_tokens + position (cyclic shift + window_partition,
+     * SwinTransformerModule.py:360-384). */
+    int head_dim, windows, win_tokens;
+    const int* tok2win;
 } vitad_linear_args;
 
 int vitad_linear_f16(const vitad_linear_args* args, void* stream);
@@ -107,10 +113,23 @@ int vitad_patchify(const float* images, void* out_f16, int batch, int channels, 
 int vitad_prefix_tokens(const float* tokens, const float* pos, float* x, int batch, int prefix, int t, int c,
                         void* stream);
 
-/* Fused softmax(Q K^T) V on tcgen05 (timm Attention.forward): q,k fp16 [B,H,T,64] (q pre-scaled),
- * vt fp16 [B,H,64,tokens_pad] (zero beyond T), out fp16 [B*T, H*64].  T <= 208, head_dim 64. */
-int vitad_attention_f16(const void* q, const void* k, const void* vt, void* out, int batch, int heads, int tokens,
-                        int tokens_pad, int head_dim, void* stream);
+/* Fused softmax(Q K^T + bias + mask) V on tcgen05.
+ *   DeiT: timm Attention.forward (windows = 1, bias/region/win2tok null).
+ *   Swin: WindowAttention.forward + shift mask + window_reverse/roll (SwinTransformerModule.py:144-193,316-347,
+ *         392-408).
+ * q,k fp16 [BW,H,T,hd] (q pre-scaled), vt fp16 [BW,H,hd,tokens_pad] (zero beyond T), BW = batch*windows;
+ * out fp16 [batch*windows*T, H*hd] in ORIGINAL token order: row = b*(windows*T) + win2tok[window*T + pos].
+ * bias fp32 [H,T,T] (relative-position bias, dense) or null; region int8 [windows,T] region label per window
+ * position (scores between different labels get -100) or null.  T <= 208, hd in {32, 64}. */
+typedef struct vitad_attention_args {
+    const void *q, *k, *vt;
+    void* out;
+    int batch_windows, heads, tokens, tokens_pad, head_dim, windows;
+    const float* bias;
+    const signed char* region;
+    const int* win2tok;
+} vitad_attention_args;
+int vitad_attention_f16(const vitad_attention_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Whole DeiT-B distilled encoder forward = EncoderDeit.forward
@@ -148,6 +167,54 @@ typedef struct vitad_deit_weights {
 size_t vitad_deit_workspace_bytes(const vitad_deit_weights* w, int batch);
 int vitad_deit_forward(const vitad_deit_weights* w, const float* images, int batch, int block_index, void* workspace,
                        size_t workspace_bytes, float* out_tokens, float* out_cls, void* out_xaug, int ld_xaug,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole EsViT Swin-T encoder forward = EncoderEsVit.forward (TransformerEncoder.py:269-273) =
+ * SwinTransformer.forward_features (SwinTransformerModule.py:821-837), inference mode.
+ * Matrices fp16 [out,in], vectors fp32.  Per block: attn_bias fp32 [heads,T,T] = relative_position_bias_table
+ * gathered through relative_position_index (:169-178); shift = 0 or window/2.  Per stage: window maps for the
+ * unshifted [0] and shifted [1] partition (null when the stage is a single window) and the region labels of
+ * create_attn_mask (:316-347) for the shifted partition; merge_* = PatchMerging (null on the last stage).
+ *   out_tokens fp32 [B,49,768] (x_region = patch_embedding), out_latent fp32 [B,768] (avg-pool, may be null),
+ *   out_xaug fp16 [B*49, ld_xaug] (may be null): MDN GEMM operand.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct vitad_swin_block {
+    const float *ln1_w, *ln1_b;
+    const void* qkv_w;
+    const float* qkv_b;
+    const float* attn_bias;
+    const void* proj_w;
+    const float* proj_b;
+    const float *ln2_w, *ln2_b;
+    const void* fc1_w;
+    const float* fc1_b;
+    const void* fc2_w;
+    const float* fc2_b;
+    int shift;
+} vitad_swin_block;
+
+typedef struct vitad_swin_stage {
+    int dim, heads, res, window, depth;
+    const vitad_swin_block* blocks; /* host array */
+    const int* tok2win[2];          /* int32 [res*res]: token -> window*T + pos */
+    const int* win2tok[2];          /* int32 [res*res]: window*T + pos -> token  */
+    const signed char* region;      /* int8 [windows*T], shifted partition */
+    const float *merge_ln_w, *merge_ln_b;
+    const void* merge_w;            /* fp16 [2*dim, 4*dim] or null */
+} vitad_swin_stage;
+
+typedef struct vitad_swin_weights {
+    int img, patch, embed, stages;
+    const void* patch_w;            /* fp16 [embed, 3*patch*patch] */
+    const float *patch_b, *patch_ln_w, *patch_ln_b;
+    const float *norm_w, *norm_b;
+    const vitad_swin_stage* stage;  /* host array */
+} vitad_swin_weights;
+
+size_t vitad_swin_workspace_bytes(const vitad_swin_weights* w, int batch);
+int vitad_swin_forward(const vitad_swin_weights* w, const float* images, int batch, void* workspace,
+                       size_t workspace_bytes, float* out_tokens, float* out_latent, void* out_xaug, int ld_xaug,
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------

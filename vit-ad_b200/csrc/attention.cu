@@ -1,10 +1,16 @@
-// Fused multi-head self-attention for short sequences (DeiT: 198 tokens, head dim 64):
-//   O = softmax(Q K^T) V      (Q is pre-scaled by hd^-0.5 in the QKV projection epilogue)
-// replaces timm Attention.forward's two bmm + softmax, which materialise [B,H,T,T] in HBM
-// (reference call site: src/classes/transformer/TransformerEncoder.py:150-165 via timm Block).
+// Fused multi-head self-attention for short sequences:
+//   O = softmax(Q K^T + bias + mask) V      (Q is pre-scaled by hd^-0.5 in the QKV projection epilogue)
+// DeiT (198 tokens, head dim 64): timm Attention.forward, called through
+//   src/classes/transformer/TransformerEncoder.py:150-165;
+// Swin / EsViT (windows of 196 or 49 tokens, head dim 32): WindowAttention.forward
+//   (src/classes/transformer/SwinTransformerModule.py:144-193) with the relative-position bias, the shifted-window
+//   mask of create_attn_mask (:316-347, value -100 between different regions) and window_reverse + the
+//   reverse cyclic shift (:392-408) folded into the output row address.
+// The reference materialises [B,H,T,T] scores in HBM (and rebuilds the shift mask on the CPU every forward).
 //
-// One CTA = one (image, head, 128-query tile); both GEMMs run on tcgen05 with accumulators in TMEM:
-//   S[128 x TKP] = Q[128 x 64] . K[TKP x 64]^T      (TMA-loaded, 128B-swizzled operands)
+// One CTA = one (window, head, 128-query tile); both GEMMs run on tcgen05 with accumulators in TMEM:
+//   S[128 x TKP] = Q[128 x 64] . K[TKP x 64]^T      (TMA-loaded, 128B-swizzled operands; head dim 32 is
+//                                                    zero-extended to 64 by the TMA box)
 //   softmax over the T valid keys: each thread owns one query row (one TMEM lane), two passes over
 //   TMEM (max, then exp/sum); P is written to shared memory as fp16 in the K-major swizzled layout
 //   tcgen05 expects, overlaying the (dead) Q/K tiles
@@ -26,34 +32,45 @@ struct AttnSmem {
     static constexpr int kPBytes = kKeyBlocks * 128 * 128;  // P: 128 rows x 64 keys x fp16 per block
     static constexpr int kQBytes = 128 * 128;
     static constexpr int kKBytes = TKP * 128;
-    static constexpr int kVtBlockBytes = 64 * 128;  // 64 (head dim) rows x 64 keys
+    static constexpr int kVtBlockBytes = 64 * 128;  // 64 rows x 64 keys
     static constexpr int kVtBytes = kKeyBlocks * kVtBlockBytes;
     static constexpr int kRegion0 = kPBytes > kQBytes + kKBytes ? kPBytes : kQBytes + kKBytes;
-    static constexpr int kTotal = kRegion0 + kVtBytes + 64 + 1024;
+    static constexpr int kTotal = kRegion0 + kVtBytes + 64 + 256 + 1024;  // + barriers + key region ids
+};
+
+struct AttnParams {
+    __half* out;
+    const float* bias;          // [H][T][T] or null
+    const signed char* region;  // [nW][T] or null
+    const int* win2tok;         // [nW*T] or null
+    int T, H, hd, nW, L;        // window tokens, heads, head dim, windows per image, tokens per image
 };
 
 template <int TKP>
 __global__ void __launch_bounds__(128, 2)
-attention_hd64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-                      const __grid_constant__ CUtensorMap tma_vt, __half* __restrict__ out, int T, int H) {
+attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                 const __grid_constant__ CUtensorMap tma_vt, const AttnParams p) {
     using S = AttnSmem<TKP>;
     static_assert(TKP % 16 == 0 && TKP <= 256, "key padding must be a legal UMMA N");
-    constexpr int HD = 64;
     constexpr uint32_t kTmemCols = 256;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint8_t* sP = smem;                 // overlays sQ|sK once S has been produced
+    uint8_t* sP = smem;  // overlays sQ|sK once S has been produced
     uint8_t* sQ = smem;
     uint8_t* sK = smem + S::kQBytes;
     uint8_t* sVt = smem + S::kRegion0;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sVt + S::kVtBytes);  // qk, v, s, o
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    signed char* s_region = reinterpret_cast<signed char*>(bars + 8);  // key region ids of this window
 
     const int warp = threadIdx.x >> 5;
-    const int bh = blockIdx.y;
+    const int bh = blockIdx.y;  // (batch*window, head)
     const int m0 = blockIdx.x * 128;
+    const int T = p.T;
+    const int bw = bh / p.H, h = bh - bw * p.H;
+    const int b = bw / p.nW, widx = bw - b * p.nW;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tma_q);
@@ -62,6 +79,8 @@ attention_hd64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
+    if (p.region != nullptr)
+        for (int i = threadIdx.x; i < T; i += 128) s_region[i] = p.region[widx * T + i];
     if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
@@ -70,18 +89,17 @@ attention_hd64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(&bars[0], S::kQBytes + S::kKBytes);
-        tma_load_3d(sQ, &tma_q, &bars[0], 0, m0, bh);  // rows >= T of this head: zero-filled
+        tma_load_3d(sQ, &tma_q, &bars[0], 0, m0, bh);  // rows >= T and columns >= hd: zero-filled
         tma_load_3d(sK, &tma_k, &bars[0], 0, 0, bh);
         mbar_arrive_expect_tx(&bars[1], S::kVtBytes);
         for (int kb = 0; kb < S::kKeyBlocks; ++kb)
-            tma_load_2d(sVt + kb * S::kVtBlockBytes, &tma_vt, &bars[1], kb * 64, bh * HD);
-        // S = Q K^T
+            tma_load_2d(sVt + kb * S::kVtBlockBytes, &tma_vt, &bars[1], kb * 64, bh * p.hd);
         mbar_wait(&bars[0], 0);
         tc_fence_after();
         constexpr uint32_t idesc_s = make_idesc_f16(128, TKP);
         const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
+        for (int k = 0; k < 4; ++k)
             umma_f16_ss(tmem, make_smem_desc_sw128(qa + k * 32), make_smem_desc_sw128(ka + k * 32), idesc_s, k != 0);
         umma_commit(&bars[2]);
     }
@@ -91,7 +109,19 @@ attention_hd64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     __syncwarp();
     tc_fence_after();
     const int r = threadIdx.x;
+    const int tq = m0 + r;
+    const bool qvalid = tq < T;
+    const float* brow = (p.bias != nullptr && qvalid) ? p.bias + (static_cast<size_t>(h) * T + tq) * T : nullptr;
+    const int qreg = (p.region != nullptr && qvalid) ? s_region[tq] : -1;
     const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+    auto score = [&](uint32_t raw, int c) -> float {
+        float s = __uint_as_float(raw);
+        if (brow != nullptr) s += __ldg(brow + c);
+        if (qreg >= 0 && s_region[c] != qreg) s -= 100.0f;
+        return s;
+    };
+
     float mx = -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < TKP; c += 16) {
@@ -100,7 +130,7 @@ attention_hd64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            if (c + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+            if (c + j < T) mx = fmaxf(mx, score(v[j], c + j));
     }
     const float mxl = mx * kLog2e;
     float sum = 0.f;
@@ -109,11 +139,11 @@ attention_hd64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         uint32_t v[16];
         tmem_ld_x16(trow + c, v);
         tmem_ld_wait();
-        float p[16];
+        float pv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            p[j] = (c + j < T) ? ex2f(fmaf(__uint_as_float(v[j]), kLog2e, -mxl)) : 0.f;
-            sum += p[j];
+            pv[j] = (c + j < T) ? ex2f(fmaf(score(v[j], c + j), kLog2e, -mxl)) : 0.f;
+            sum += pv[j];
         }
         // two 16-byte chunks (8 keys each) of row r in key block c/64, 128B-swizzled
         const int blk = c >> 6;
@@ -122,10 +152,10 @@ attention_hd64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
             uint4 u;
-            u.x = pack_h2(p[8 * h2 + 0], p[8 * h2 + 1]);
-            u.y = pack_h2(p[8 * h2 + 2], p[8 * h2 + 3]);
-            u.z = pack_h2(p[8 * h2 + 4], p[8 * h2 + 5]);
-            u.w = pack_h2(p[8 * h2 + 6], p[8 * h2 + 7]);
+            u.x = pack_h2(pv[8 * h2 + 0], pv[8 * h2 + 1]);
+            u.y = pack_h2(pv[8 * h2 + 2], pv[8 * h2 + 3]);
+            u.z = pack_h2(pv[8 * h2 + 4], pv[8 * h2 + 5]);
+            u.w = pack_h2(pv[8 * h2 + 6], pv[8 * h2 + 7]);
             *reinterpret_cast<uint4*>(rowp + (((chunk0 + h2) ^ (r & 7)) << 4)) = u;
         }
     }
@@ -138,7 +168,7 @@ attention_hd64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         tc_fence_after();
         mbar_wait(&bars[1], 0);
         tc_fence_after();
-        constexpr uint32_t idesc_o = make_idesc_f16(128, HD);
+        constexpr uint32_t idesc_o = make_idesc_f16(128, 64);
         const uint32_t pa = smem_u32(sP), va = smem_u32(sVt);
 #pragma unroll 1
         for (int kk = 0; kk < TKP / 16; ++kk) {
@@ -153,15 +183,14 @@ attention_hd64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     __syncwarp();
     tc_fence_after();
     const float inv = 1.0f / sum;
-    const int t = m0 + r;
-    const int b = bh / H, h = bh - b * H;
-    __half* orow = out + (static_cast<size_t>(b) * T + t) * (H * HD) + h * HD;
+    const int tok = qvalid ? (p.win2tok != nullptr ? __ldg(p.win2tok + widx * T + tq) : tq) : 0;
+    __half* orow = p.out + (static_cast<size_t>(b) * p.L + tok) * (p.H * p.hd) + h * p.hd;
 #pragma unroll
-    for (int c = 0; c < HD; c += 32) {
+    for (int c = 0; c < 64; c += 32) {
         uint32_t v[32];
         tmem_ld_x32(trow + c, v);
         tmem_ld_wait();
-        if (t < T) {
+        if (qvalid && c < p.hd) {
             uint4* o = reinterpret_cast<uint4*>(orow + c);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -186,37 +215,42 @@ attention_hd64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 
 using namespace vitad;
 
-// q, k: fp16 [B,H,T,64]; vt: fp16 [B,H,64,Tpad] (zero beyond T); out: fp16 [B*T, H*64].
-extern "C" int vitad_attention_f16(const void* q, const void* k, const void* vt, void* out, int batch, int heads,
-                                   int tokens, int tokens_pad, int head_dim, void* stream) {
+extern "C" int vitad_attention_f16(const vitad_attention_args* args, void* stream) {
     int rc = check_device_arch();
     if (rc) return rc;
-    VITAD_REQUIRE(q && k && vt && out, VITAD_ERR_ARG, "null pointer");
-    VITAD_REQUIRE(head_dim == 64, VITAD_ERR_SHAPE, "head_dim %d unsupported (64)", head_dim);
-    VITAD_REQUIRE(tokens > 0 && tokens <= 208, VITAD_ERR_SHAPE, "tokens=%d unsupported (1..208)", tokens);
-    VITAD_REQUIRE(tokens_pad >= 256 && tokens_pad % 8 == 0, VITAD_ERR_SHAPE,
-                  "tokens_pad=%d must be >= 256 and a multiple of 8", tokens_pad);
-    VITAD_REQUIRE(aligned16(out), VITAD_ERR_ALIGN, "output alignment");
+    VITAD_REQUIRE(args, VITAD_ERR_ARG, "null args");
+    const vitad_attention_args& a = *args;
+    VITAD_REQUIRE(a.q && a.k && a.vt && a.out, VITAD_ERR_ARG, "null pointer");
+    VITAD_REQUIRE(a.head_dim == 64 || a.head_dim == 32, VITAD_ERR_SHAPE, "head_dim %d unsupported (32, 64)", a.head_dim);
+    VITAD_REQUIRE(a.tokens > 0 && a.tokens <= 208, VITAD_ERR_SHAPE, "tokens=%d unsupported (1..208)", a.tokens);
+    VITAD_REQUIRE(a.tokens_pad >= 256 && a.tokens_pad % 8 == 0, VITAD_ERR_SHAPE,
+                  "tokens_pad=%d must be >= 256 and a multiple of 8", a.tokens_pad);
+    const int nW = a.windows > 0 ? a.windows : 1;
+    VITAD_REQUIRE(a.batch_windows > 0 && a.batch_windows % nW == 0 && a.heads > 0, VITAD_ERR_SHAPE, "batch/windows");
+    VITAD_REQUIRE(nW == 1 || a.win2tok, VITAD_ERR_ARG, "window attention needs the win2tok map");
+    VITAD_REQUIRE(aligned16(a.out), VITAD_ERR_ALIGN, "output alignment");
     constexpr int TKP = 208;
     using S = AttnSmem<TKP>;
-    const int BH = batch * heads;
+    const int BH = a.batch_windows * a.heads;
+    const uint64_t hd = a.head_dim;
     CUtensorMap tq, tk, tv;
-    rc = make_tmap_f16_3d(&tq, q, BH, tokens, 64, 64, static_cast<uint64_t>(tokens) * 64, 128);
+    rc = make_tmap_f16_3d(&tq, a.q, BH, a.tokens, hd, hd, static_cast<uint64_t>(a.tokens) * hd, 128);
     if (rc) return rc;
-    rc = make_tmap_f16_3d(&tk, k, BH, tokens, 64, 64, static_cast<uint64_t>(tokens) * 64, TKP);
+    rc = make_tmap_f16_3d(&tk, a.k, BH, a.tokens, hd, hd, static_cast<uint64_t>(a.tokens) * hd, TKP);
     if (rc) return rc;
-    rc = make_tmap_f16_2d(&tv, vt, static_cast<uint64_t>(BH) * 64, tokens_pad, tokens_pad, 64);
+    rc = make_tmap_f16_2d(&tv, a.vt, static_cast<uint64_t>(BH) * hd, a.tokens_pad, a.tokens_pad, 64);
     if (rc) return rc;
-    auto kern = attention_hd64_kernel<TKP>;
+    auto kern = attention_kernel<TKP>;
     static bool attr_set = false;
     if (!attr_set) {
         VITAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         attr_set = true;
     }
-    dim3 grid((tokens + 127) / 128, BH);
+    AttnParams p{static_cast<__half*>(a.out), a.bias, a.region, a.win2tok, a.tokens, a.heads, a.head_dim, nW,
+                 nW * a.tokens};
+    dim3 grid((a.tokens + 127) / 128, BH);
     ProfScope prof("attention", static_cast<cudaStream_t>(stream));
-    kern<<<grid, 128, S::kTotal, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, static_cast<__half*>(out), tokens,
-                                                                     heads);
+    kern<<<grid, 128, S::kTotal, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;

@@ -9,7 +9,6 @@ extern "C" int vitad_layernorm(const float*, const float*, const float*, void*, 
                                int, int, float, int, void*);
 extern "C" int vitad_patchify(const float*, void*, int, int, int, int, void*);
 extern "C" int vitad_prefix_tokens(const float*, const float*, float*, int, int, int, int, void*);
-extern "C" int vitad_attention_f16(const void*, const void*, const void*, void*, int, int, int, int, int, void*);
 
 namespace {
 constexpr int kTokPad = 256;  // key padding of the transposed-V buffer
@@ -97,7 +96,12 @@ extern "C" int vitad_deit_forward(const vitad_deit_weights* wp, const float* ima
         a.epilogue = VITAD_EPI_QKV, a.q = ws.q, a.kmat = ws.k, a.vt = ws.vt;
         a.tokens = T, a.tokens_pad = kTokPad, a.heads = w.heads, a.q_scale = 0.125f;
         if ((rc = vitad_linear_f16(&a, s))) return rc;
-        if ((rc = vitad_attention_f16(ws.q, ws.k, ws.vt, ws.h, batch, w.heads, T, kTokPad, C / w.heads, s))) return rc;
+        vitad_attention_args at;
+        memset(&at, 0, sizeof(at));
+        at.q = ws.q, at.k = ws.k, at.vt = ws.vt, at.out = ws.h;
+        at.batch_windows = batch, at.heads = w.heads, at.tokens = T, at.tokens_pad = kTokPad;
+        at.head_dim = C / w.heads, at.windows = 1;
+        if ((rc = vitad_attention_f16(&at, s))) return rc;
         memset(&a, 0, sizeof(a));
         a.a = ws.h, a.w = L.proj_w, a.bias = L.proj_b, a.m = rows, a.n = C, a.k = C, a.lda = C, a.ldw = C;
         a.epilogue = VITAD_EPI_RESIDUAL_F32, a.out = ws.x, a.resid = ws.x, a.ldo = C;

@@ -124,12 +124,13 @@ struct EpiResidualF32 {
     }
 };
 
-// Fused QKV projection epilogue (timm Attention.qkv + reshape/permute):
-//   row = b*T + t, col = which*C + h*64 + e
-//   q[b][h][t][e] = (acc+bias) * scale   (scale = hd^-0.5 folded in; exact power of two for hd=64)
-//   k[b][h][t][e] =  acc+bias
-//   vt[b][h][e][t] = acc+bias            (V stored transposed, token index contiguous, padded to Tpad,
-//                                         so P@V reads a K-major B operand)
+// Fused QKV projection epilogue (timm Attention.qkv / Swin WindowAttention.qkv + reshape/permute, and for Swin
+// the cyclic shift + window_partition of SwinTransformerModule.py:360-384 folded into the store address):
+//   row = b*L + t, col = which*C + h*hd + e;  (window, pos) = tok2win[t] (identity when tok2win is null)
+//   q [bw][h][pos][e] = (acc+bias) * scale   (scale = hd^-0.5 folded in)
+//   k [bw][h][pos][e] =  acc+bias
+//   vt[bw][h][e][pos] =  acc+bias            (V stored transposed, position index contiguous, padded to Tpad,
+//                                             so P@V reads a K-major B operand);   bw = b*nW + window
 template <int BLOCK_N>
 struct EpiQkv {
     static constexpr int W = EpiChunk<BLOCK_N>::kW;
@@ -138,34 +139,43 @@ struct EpiQkv {
     __half* q;
     __half* k;
     __half* vt;
-    int M, T, Tpad, H;  // tokens per image, padded token count, heads
+    const int* tok2win;       // [L] token -> window*T + pos, or null
+    int M, L, T, Tpad, H, hd, nW;  // rows, tokens per image, tokens per window, padded T, heads, head dim, windows
     float scale;
     __device__ __forceinline__ void tile_begin(int, int, int) const {}
     __device__ __forceinline__ void tile_end(int, int, int) const {}
     __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr, int c0, int c1) const {
-        const int C = H * 64;
+        const int C = H * hd;
         const int n0 = n_tile * BLOCK_N;
-        const int b = row / T;
-        const int t = row - b * T;
+        const int b = row / L;
+        const int t = row - b * L;
+        int widx = 0, pos = t;
+        if (tok2win != nullptr && row < M) {
+            const int wp = __ldg(tok2win + t);
+            widx = wp / T;
+            pos = wp - widx * T;
+        }
+        const size_t bw = static_cast<size_t>(b) * nW + widx;
         for_each_chunk<W>(taddr, c0, c1, [&](int c, float (&v)[W]) {
             const int col = n0 + c;
             if (row < M && col < 3 * C) {
                 float bb[W];
                 load_bias<W>(bias, col, bb);
                 const int which = col / C;
-                const int h = (col - which * C) >> 6;
-                const int e0 = col & 63;
-                const size_t bh = static_cast<size_t>(b) * H + h;
+                const int cc = col - which * C;
+                const int h = cc / hd;
+                const int e0 = cc - h * hd;
+                const size_t bh = bw * H + h;
                 if (which == 0) {
 #pragma unroll
                     for (int j = 0; j < W; ++j) v[j] = (v[j] + bb[j]) * scale;
-                    store_h<W>(q + (bh * T + t) * 64 + e0, v);
+                    store_h<W>(q + (bh * T + pos) * hd + e0, v);
                 } else if (which == 1) {
 #pragma unroll
                     for (int j = 0; j < W; ++j) v[j] = v[j] + bb[j];
-                    store_h<W>(k + (bh * T + t) * 64 + e0, v);
+                    store_h<W>(k + (bh * T + pos) * hd + e0, v);
                 } else {
-                    __half* dst = vt + (bh * 64 + e0) * Tpad + t;
+                    __half* dst = vt + (bh * hd + e0) * Tpad + pos;
 #pragma unroll
                     for (int j = 0; j < W; ++j) dst[static_cast<size_t>(j) * Tpad] = to_h(v[j] + bb[j]);
                 }

@@ -86,14 +86,21 @@ static int dispatch_epilogue(const vitad_linear_args& a, cudaStream_t stream) {
             return launch_gemm<BLOCK_N>(a, e, stream);
         }
         case VITAD_EPI_QKV: {
+            const int hd = a.head_dim > 0 ? a.head_dim : 64;
+            const int nw = a.windows > 0 ? a.windows : 1;
+            const int wt = a.win_tokens > 0 ? a.win_tokens : a.tokens;
             EpiQkv<BLOCK_N> e{a.bias,
                               static_cast<__half*>(a.q),
                               static_cast<__half*>(a.kmat),
                               static_cast<__half*>(a.vt),
+                              a.tok2win,
                               a.m,
                               a.tokens,
+                              wt,
                               a.tokens_pad,
                               a.heads,
+                              hd,
+                              nw,
                               a.q_scale};
             return launch_gemm<BLOCK_N>(a, e, stream);
         }
@@ -165,9 +172,13 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
         case VITAD_EPI_QKV:
             VITAD_REQUIRE(a.q && a.kmat && a.vt && aligned16(a.q) && aligned16(a.kmat), VITAD_ERR_ARG,
                           "q/k/vt missing or misaligned");
-            VITAD_REQUIRE(a.heads > 0 && a.n == 3 * a.heads * 64 && a.tokens > 0 && a.m % a.tokens == 0 &&
-                              a.tokens_pad >= a.tokens,
-                          VITAD_ERR_SHAPE, "QKV epilogue needs N = 3*H*64 and M = B*T");
+            VITAD_REQUIRE((a.head_dim == 0 || a.head_dim == 32 || a.head_dim == 64) && a.heads > 0 &&
+                              a.n == 3 * a.heads * (a.head_dim > 0 ? a.head_dim : 64) && a.tokens > 0 &&
+                              a.m % a.tokens == 0,
+                          VITAD_ERR_SHAPE, "QKV epilogue needs N = 3*H*hd (hd 32 or 64) and M = B*tokens");
+            VITAD_REQUIRE(a.tokens_pad >= (a.win_tokens > 0 ? a.win_tokens : a.tokens) &&
+                              (a.windows <= 1 || (a.tok2win && a.windows * a.win_tokens == a.tokens)),
+                          VITAD_ERR_SHAPE, "QKV epilogue window layout (windows*win_tokens == tokens, map given)");
             break;
         case VITAD_EPI_PATCH_EMBED:
             VITAD_REQUIRE(a.out && a.pos && aligned16(a.out) && aligned16(a.pos) && a.patches > 0 &&

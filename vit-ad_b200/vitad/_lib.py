@@ -65,6 +65,10 @@ class LinearArgs(C.Structure):
         ("pos", C.c_void_p),
         ("patches", C.c_int),
         ("prefix", C.c_int),
+        ("head_dim", C.c_int),
+        ("windows", C.c_int),
+        ("win_tokens", C.c_int),
+        ("tok2win", C.c_void_p),
     ]
 
 
@@ -89,7 +93,15 @@ lib.vitad_patchify.argtypes = [_vp, _vp, _i, _i, _i, _i, _vp]
 lib.vitad_patchify.restype = _i
 lib.vitad_prefix_tokens.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _vp]
 lib.vitad_prefix_tokens.restype = _i
-lib.vitad_attention_f16.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [("q", _vp), ("k", _vp), ("vt", _vp), ("out", _vp), ("batch_windows", _i), ("heads", _i),
+                ("tokens", _i), ("tokens_pad", _i), ("head_dim", _i), ("windows", _i), ("bias", _vp),
+                ("region", _vp), ("win2tok", _vp)]
+
+
+lib.vitad_attention_f16.argtypes = [C.POINTER(AttentionArgs), _vp]
 lib.vitad_attention_f16.restype = _i
 
 DEIT_MAX_DEPTH = 24
@@ -111,6 +123,29 @@ lib.vitad_deit_workspace_bytes.argtypes = [C.POINTER(DeitWeights), _i]
 lib.vitad_deit_workspace_bytes.restype = _sz
 lib.vitad_deit_forward.argtypes = [C.POINTER(DeitWeights), _vp, _i, _i, _vp, _sz, _vp, _vp, _vp, _i, _vp]
 lib.vitad_deit_forward.restype = _i
+
+# ------------------------------------------------------------------------------------ Swin / EsViT
+class SwinBlock(C.Structure):
+    _fields_ = [(n, _vp) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "attn_bias", "proj_w", "proj_b", "ln2_w",
+                                   "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")] + [("shift", _i)]
+
+
+class SwinStage(C.Structure):
+    _fields_ = [(n, _i) for n in ("dim", "heads", "res", "window", "depth")] + [
+        ("blocks", C.POINTER(SwinBlock)), ("tok2win", _vp * 2), ("win2tok", _vp * 2), ("region", _vp),
+        ("merge_ln_w", _vp), ("merge_ln_b", _vp), ("merge_w", _vp)]
+
+
+class SwinWeights(C.Structure):
+    _fields_ = [(n, _i) for n in ("img", "patch", "embed", "stages")] + [
+        ("patch_w", _vp), ("patch_b", _vp), ("patch_ln_w", _vp), ("patch_ln_b", _vp), ("norm_w", _vp),
+        ("norm_b", _vp), ("stage", C.POINTER(SwinStage))]
+
+
+lib.vitad_swin_workspace_bytes.argtypes = [C.POINTER(SwinWeights), _i]
+lib.vitad_swin_workspace_bytes.restype = _sz
+lib.vitad_swin_forward.argtypes = [C.POINTER(SwinWeights), _vp, _i, _vp, _sz, _vp, _vp, _vp, _i, _vp]
+lib.vitad_swin_forward.restype = _i
 
 # ---------------------------------------------------------------------------------------- GMM head
 lib.vitad_gmm_plan.argtypes = [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]

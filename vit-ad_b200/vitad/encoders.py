@@ -190,3 +190,230 @@ class EncoderDeit(TransformerEncoder):
                                      torch.cuda.current_stream().cuda_stream))
         tokens._vitad_xaug = xaug  # fp16 GEMM operand for the MDN head (saves one conversion pass)
         return TransformerEncoderOutput(patch_embedding=tokens, latent_space=cls)
+
+
+# --------------------------------------------------------------------------------------------------
+# EsViT Swin-T (window 14)
+# --------------------------------------------------------------------------------------------------
+SWIN_DEPTHS = (2, 2, 6, 2)
+SWIN_HEADS = (3, 6, 12, 24)
+SWIN_EMBED = 96
+SWIN_WINDOW = 14
+ESVIT_CHECKPOINT = "pretrained_vit_weights/esvit-T/checkpoint_best.pth"  # TransformerEncoder.py:243-246
+
+
+def _relative_position_index(ws: int) -> torch.Tensor:
+    coords = torch.stack(torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")).flatten(1)
+    rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += ws - 1
+    rel[:, :, 1] += ws - 1
+    rel[:, :, 0] *= 2 * ws - 1
+    return rel.sum(-1)
+
+
+class _WinAttn(nn.Module):
+    def __init__(self, dim, ws, heads):
+        super().__init__()
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws - 1) ** 2, heads))
+        self.register_buffer("relative_position_index", _relative_position_index(ws))
+        self.qkv = nn.Linear(dim, 3 * dim)
+        self.proj = nn.Linear(dim, dim)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+
+
+class _SwinBlock(nn.Module):
+    def __init__(self, dim, res, heads, window, shift):
+        super().__init__()
+        if res <= window:  # SwinTransformerModule.py:262-265
+            shift, window = 0, res
+        self.window_size, self.shift_size = window, shift
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = _WinAttn(dim, window, heads)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = _Mlp(dim, 4 * dim)
+
+
+class _PatchMerging(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = nn.LayerNorm(4 * dim)
+
+
+class _SwinLayer(nn.Module):
+    def __init__(self, dim, res, depth, heads, window, downsample):
+        super().__init__()
+        self.blocks = nn.ModuleList(
+            [_SwinBlock(dim, res, heads, window, 0 if i % 2 == 0 else window // 2) for i in range(depth)])
+        if downsample:
+            self.downsample = _PatchMerging(dim)
+        else:
+            self.downsample = None
+
+
+class _SwinPatchEmbed(nn.Module):
+    def __init__(self, embed):
+        super().__init__()
+        self.proj = nn.Conv2d(3, embed, kernel_size=4, stride=4)
+        self.norm = nn.LayerNorm(embed)
+
+
+class _SwinParams(nn.Module):
+    """Parameter tree of the vendored SwinTransformer as EncoderEsVit builds it (185 state_dict keys)."""
+
+    def __init__(self, img=224, num_classes=3):
+        super().__init__()
+        self.img = img
+        self.patch_embed = _SwinPatchEmbed(SWIN_EMBED)
+        res = img // 4
+        self.layers = nn.ModuleList()
+        for s, (depth, heads) in enumerate(zip(SWIN_DEPTHS, SWIN_HEADS)):
+            self.layers.append(_SwinLayer(SWIN_EMBED * 2**s, res, depth, heads, SWIN_WINDOW, s < 3))
+            if s < 3:
+                res //= 2
+        self.norm = nn.LayerNorm(SWIN_EMBED * 8)
+        self.head = nn.Linear(SWIN_EMBED * 8, num_classes)
+        for m in self.modules():  # SwinTransformer._init_weights (:800-808)
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+
+def _window_maps(H: int, ws: int, shift: int):
+    """token -> window*T + pos for the (cyclically shifted) window partition, its inverse, and the region label
+    of every window position (create_attn_mask, SwinTransformerModule.py:316-347)."""
+    T = ws * ws
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(H), indexing="ij")
+    y2, x2 = (ys - shift) % H, (xs - shift) % H  # torch.roll(x, -shift): token y lands at (y - shift) mod H
+    tok2win = ((y2 // ws) * (H // ws) + x2 // ws) * T + (y2 % ws) * ws + x2 % ws
+    tok2win = tok2win.reshape(-1).to(torch.int32)
+    win2tok = torch.empty_like(tok2win)
+    win2tok[tok2win.long()] = torch.arange(H * H, dtype=torch.int32)
+    region = None
+    if shift > 0:
+        def band(v):
+            return (v >= H - ws).long() + (v >= H - shift).long()
+        ids = (3 * band(y2) + band(x2)).reshape(-1)  # label per token (in shifted-frame coordinates)
+        region = torch.empty(H * H, dtype=torch.int8)
+        region[tok2win.long()] = ids.to(torch.int8)
+    return tok2win, win2tok, region
+
+
+class EncoderEsVit(TransformerEncoder):
+    """Drop-in for the reference EncoderEsVit (TransformerEncoder.py:211-273): vendored Swin-T, window 14.
+
+    `requires_grad=False` loads the EsViT student checkpoint from the reference's relative path when that file
+    exists with matching shapes (position-encoding interpolation, :276-350, is not implemented — DESIGN.md §8);
+    without the file the random init is kept and a notice is printed (the reference would raise).  Forward runs
+    in inference mode: the reference leaves DropPath(0.1) active during MDN/NF validation, which makes its
+    features random; that accident is deliberately not reproduced.
+    """
+
+    def __init__(self, img_size: int, requires_grad: bool = False) -> None:
+        super().__init__(img_size=img_size)
+        if img_size != 224:
+            raise ValueError("EncoderEsVit (vitad): image size has to be 224")
+        self.size_patch_embedding = 768
+        self.patch_size = 32
+        self.num_embedded_patches = self.calc_num_embedded_patches()
+        self.esvit = _SwinParams(img=img_size)
+        if not requires_grad:
+            import os
+
+            if os.path.exists(ESVIT_CHECKPOINT):
+                student = torch.load(ESVIT_CHECKPOINT, map_location="cpu")["student"]
+                weights = {k[7:]: v for k, v in student.items() if not k.startswith("module.head")}
+                delattr(self.esvit, "head")
+                self.esvit.load_state_dict(weights)
+            else:
+                print(f"EncoderEsVit (vitad): {ESVIT_CHECKPOINT} not found, keeping the random initialisation")
+        for p in self.esvit.parameters():
+            p.requires_grad = False
+        self._packed = None
+
+    def _apply(self, fn, recurse=True):
+        self._packed = None
+        return super()._apply(fn, recurse)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        self._packed = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def _pack(self, device):
+        e = self.esvit
+        keep = []
+
+        def dev(t, dtype):
+            t = t.detach().to(device=device, dtype=dtype).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        f32 = lambda t: dev(t, torch.float32)
+        f16 = lambda t: dev(t, torch.float16)
+        stages = (_lib.SwinStage * len(e.layers))()
+        block_arrays = []
+        res = self.img_size // 4
+        for s, layer in enumerate(e.layers):
+            st = stages[s]
+            dim = SWIN_EMBED * 2**s
+            ws = layer.blocks[0].window_size
+            st.dim, st.heads, st.res, st.window, st.depth = dim, SWIN_HEADS[s], res, ws, len(layer.blocks)
+            T = ws * ws
+            blocks = (_lib.SwinBlock * len(layer.blocks))()
+            block_arrays.append(blocks)
+            for i, blk in enumerate(layer.blocks):
+                B = blocks[i]
+                B.ln1_w, B.ln1_b = f32(blk.norm1.weight), f32(blk.norm1.bias)
+                B.qkv_w, B.qkv_b = f16(blk.attn.qkv.weight), f32(blk.attn.qkv.bias)
+                table, index = blk.attn.relative_position_bias_table.detach().float(), blk.attn.relative_position_index
+                B.attn_bias = f32(table[index.reshape(-1).long()].view(T, T, -1).permute(2, 0, 1))
+                B.proj_w, B.proj_b = f16(blk.attn.proj.weight), f32(blk.attn.proj.bias)
+                B.ln2_w, B.ln2_b = f32(blk.norm2.weight), f32(blk.norm2.bias)
+                B.fc1_w, B.fc1_b = f16(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias)
+                B.fc2_w, B.fc2_b = f16(blk.mlp.fc2.weight), f32(blk.mlp.fc2.bias)
+                B.shift = blk.shift_size
+            st.blocks = C.cast(blocks, C.POINTER(_lib.SwinBlock))
+            if res > ws:
+                t0, w0, _ = _window_maps(res, ws, 0)
+                st.tok2win[0], st.win2tok[0] = dev(t0, torch.int32), dev(w0, torch.int32)
+                shift = max(b.shift_size for b in layer.blocks)
+                if shift > 0:
+                    t1, w1, reg = _window_maps(res, ws, shift)
+                    st.tok2win[1], st.win2tok[1] = dev(t1, torch.int32), dev(w1, torch.int32)
+                    st.region = dev(reg, torch.int8)
+            if layer.downsample is not None:
+                st.merge_ln_w, st.merge_ln_b = f32(layer.downsample.norm.weight), f32(layer.downsample.norm.bias)
+                st.merge_w = f16(layer.downsample.reduction.weight)
+                res //= 2
+        w = _lib.SwinWeights()
+        w.img, w.patch, w.embed, w.stages = self.img_size, 4, SWIN_EMBED, len(e.layers)
+        w.patch_w = f16(e.patch_embed.proj.weight.reshape(SWIN_EMBED, -1))
+        w.patch_b = f32(e.patch_embed.proj.bias)
+        w.patch_ln_w, w.patch_ln_b = f32(e.patch_embed.norm.weight), f32(e.patch_embed.norm.bias)
+        w.norm_w, w.norm_b = f32(e.norm.weight), f32(e.norm.bias)
+        w.stage = C.cast(stages, C.POINTER(_lib.SwinStage))
+        self._packed = dict(w=w, stages=stages, blocks=block_arrays, keep=keep, device=device, ws=None, ws_batch=0)
+
+    def forward(self, x: torch.Tensor, block_index: int = 0) -> TransformerEncoderOutput:
+        if not x.is_cuda:
+            raise RuntimeError("EncoderEsVit (vitad): CUDA input required — this implementation has no CPU path")
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.img_size or x.shape[3] != self.img_size:
+            raise ValueError(f"expected [B,3,{self.img_size},{self.img_size}] input, got {tuple(x.shape)}")
+        if self._packed is None or self._packed["device"] != x.device:
+            self._pack(x.device)
+        pk = self._packed
+        x = x.to(torch.float32).contiguous()
+        B = x.shape[0]
+        P, Cdim = self.num_embedded_patches, self.size_patch_embedding
+        if pk["ws"] is None or pk["ws_batch"] < B:
+            nbytes = lib.vitad_swin_workspace_bytes(C.byref(pk["w"]), B)
+            pk["ws"], pk["ws_batch"] = torch.empty(nbytes, device=x.device, dtype=torch.uint8), B
+        tokens = torch.empty((B, P, Cdim), device=x.device, dtype=torch.float32)
+        latent = torch.empty((B, Cdim), device=x.device, dtype=torch.float32)
+        xaug = torch.empty((B * P, _lib.MDN_KA), device=x.device, dtype=torch.float16)
+        check(lib.vitad_swin_forward(C.byref(pk["w"]), x.data_ptr(), B, pk["ws"].data_ptr(), pk["ws"].numel(),
+                                     tokens.data_ptr(), latent.data_ptr(), xaug.data_ptr(), _lib.MDN_KA,
+                                     torch.cuda.current_stream().cuda_stream))
+        tokens._vitad_xaug = xaug
+        return TransformerEncoderOutput(latent_space=latent, patch_embedding=tokens)

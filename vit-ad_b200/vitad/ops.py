@@ -54,10 +54,12 @@ def linear(
 
 def linear_qkv(
     a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, batch: int, tokens: int, heads: int, tokens_pad: int,
-    q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, q_scale: float, block_n: int = 0,
+    q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, q_scale: float, block_n: int = 0, head_dim: int = 0,
+    windows: int = 0, win_tokens: int = 0, tok2win: torch.Tensor | None = None,
 ) -> None:
-    """Fused qkv projection writing q/k as [B,H,T,64] and v transposed as [B,H,64,Tpad] (fp16)."""
-    _need_cuda(a, w, bias, q, k, vt)
+    """Fused qkv projection writing q/k as [BW,H,T,hd] and v transposed as [BW,H,hd,Tpad] (fp16); with
+    `windows`/`tok2win` the rows are scattered into (shifted) attention windows."""
+    _need_cuda(a, w, bias, q, k, vt, tok2win)
     m, kk = a.shape
     assert m == batch * tokens
     args = _lib.LinearArgs()
@@ -67,6 +69,7 @@ def linear_qkv(
     args.epilogue, args.block_n = _lib.EPI_QKV, block_n
     args.q, args.kmat, args.vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
     args.tokens, args.tokens_pad, args.heads, args.q_scale = tokens, tokens_pad, heads, q_scale
+    args.head_dim, args.windows, args.win_tokens, args.tok2win = head_dim, windows, win_tokens, _ptr(tok2win)
     check(lib.vitad_linear_f16(C.byref(args), _stream()))
 
 
@@ -109,13 +112,17 @@ def patchify(images, patch):
     return out
 
 
-def attention(q, k, vt, tokens):
-    """q,k fp16 [B,H,T,64] (q pre-scaled); vt fp16 [B,H,64,Tpad] zero-padded -> fp16 [B*T, H*64]."""
-    _need_cuda(q, k, vt)
-    b, h, t, hd = q.shape
-    out = torch.empty((b * t, h * hd), device=q.device, dtype=torch.float16)
-    check(lib.vitad_attention_f16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), b, h, tokens,
-                                  vt.shape[-1], hd, _stream()))
+def attention(q, k, vt, tokens, windows=1, bias=None, region=None, win2tok=None):
+    """q,k fp16 [BW,H,T,hd] (q pre-scaled); vt fp16 [BW,H,hd,Tpad] zero-padded -> fp16 [BW*T, H*hd] in original
+    token order.  Swin: bias fp32 [H,T,T], region int8 [windows,T], win2tok int32 [windows*T]."""
+    _need_cuda(q, k, vt, bias, region, win2tok)
+    bw, h, t, hd = q.shape
+    out = torch.empty((bw * t, h * hd), device=q.device, dtype=torch.float16)
+    a = _lib.AttentionArgs()
+    a.q, a.k, a.vt, a.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
+    a.batch_windows, a.heads, a.tokens, a.tokens_pad, a.head_dim, a.windows = bw, h, tokens, vt.shape[-1], hd, windows
+    a.bias, a.region, a.win2tok = _ptr(bias), _ptr(region), _ptr(win2tok)
+    check(lib.vitad_attention_f16(C.byref(a), _stream()))
     return out
 
 
