@@ -119,7 +119,8 @@ int vitad_prefix_tokens(const float* tokens, const float* pos, float* x, int bat
  *         392-408).
  * q,k fp16 [BW,H,T,hd] (q pre-scaled), vt fp16 [BW,H,hd,tokens_pad] (zero beyond T), BW = batch*windows;
  * out fp16 [batch*windows*T, H*hd] in ORIGINAL token order: row = b*(windows*T) + win2tok[window*T + pos].
- * bias fp32 [H,T,T] (relative-position bias, dense) or null; region int8 [windows,T] region label per window
+ * bias fp32 [H,T_key,T_query] (dense relative-position bias, key-major so query lanes read contiguous memory)
+ * or null; region int8 [windows,T] region label per window
  * position (scores between different labels get -100) or null.  T <= 208, hd in {32, 64}. */
 typedef struct vitad_attention_args {
     const void *q, *k, *vt;
@@ -172,8 +173,9 @@ int vitad_deit_forward(const vitad_deit_weights* w, const float* images, int bat
 /* ------------------------------------------------------------------------------------------
  * Whole EsViT Swin-T encoder forward = EncoderEsVit.forward (TransformerEncoder.py:269-273) =
  * SwinTransformer.forward_features (SwinTransformerModule.py:821-837), inference mode.
- * Matrices fp16 [out,in], vectors fp32.  Per block: attn_bias fp32 [heads,T,T] = relative_position_bias_table
- * gathered through relative_position_index (:169-178); shift = 0 or window/2.  Per stage: window maps for the
+ * Matrices fp16 [out,in], vectors fp32.  Per block: attn_bias fp32 [heads,T_key,T_query] =
+ * relative_position_bias_table gathered through relative_position_index (:169-178), key-major; shift = 0 or
+ * window/2.  Per stage: window maps for the
  * unshifted [0] and shifted [1] partition (null when the stage is a single window) and the region labels of
  * create_attn_mask (:316-347) for the shifted partition; merge_* = PatchMerging (null on the last stage).
  *   out_tokens fp32 [B,49,768] (x_region = patch_embedding), out_latent fp32 [B,768] (avg-pool, may be null),

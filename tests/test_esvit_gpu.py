@@ -25,8 +25,8 @@ def test_window_attention_matches_torch():
     t2w, w2t, region = _window_maps(H, ws, shift)
     vt = torch.zeros(B * nW, heads, 32, 256, dtype=torch.float16)
     vt[..., :T] = v.transpose(-1, -2)
-    out = ops.attention(q.cuda(), k.cuda(), vt.cuda(), T, windows=nW, bias=bias.cuda(), region=region.cuda(),
-                        win2tok=w2t.cuda())
+    out = ops.attention(q.cuda(), k.cuda(), vt.cuda(), T, windows=nW, bias=bias.transpose(1, 2).contiguous().cuda(),
+                        region=region.cuda(), win2tok=w2t.cuda())  # bias is passed key-major [H, key, query]
     torch.cuda.synchronize()
     reg = region.view(nW, T).float()
     mask = (reg.unsqueeze(1) != reg.unsqueeze(2)).float() * -100.0  # [nW,T,T]

@@ -40,7 +40,7 @@ struct AttnSmem {
 
 struct AttnParams {
     __half* out;
-    const float* bias;          // [H][T][T] or null
+    const float* bias;          // [H][T key][T query] or null
     const signed char* region;  // [nW][T] or null
     const int* win2tok;         // [nW*T] or null
     int T, H, hd, nW, L;        // window tokens, heads, head dim, windows per image, tokens per image
@@ -111,38 +111,53 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     const int r = threadIdx.x;
     const int tq = m0 + r;
     const bool qvalid = tq < T;
-    const float* brow = (p.bias != nullptr && qvalid) ? p.bias + (static_cast<size_t>(h) * T + tq) * T : nullptr;
+    // bias is stored key-major ([H][key][query]) so that the 32 query lanes of a warp read contiguous memory
+    const float* brow = (p.bias != nullptr && qvalid) ? p.bias + static_cast<size_t>(h) * T * T + tq : nullptr;
     const int qreg = (p.region != nullptr && qvalid) ? s_region[tq] : -1;
     const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
 
-    auto score = [&](uint32_t raw, int c) -> float {
-        float s = __uint_as_float(raw);
-        if (brow != nullptr) s += __ldg(brow + c);
-        if (qreg >= 0 && s_region[c] != qreg) s -= 100.0f;
-        return s;
+    // scores of one 16-key chunk: accumulator + bias (16 independent loads issued before the TMEM wait so their
+    // latency overlaps; a load per element inside the compare chain serialised ~400 L2 round trips per thread)
+    // + region mask.  Key indices are clamped so the loads stay in bounds; invalid keys are masked by the caller.
+    auto load_chunk = [&](int c, float (&sc)[16]) {
+        uint32_t v[16];
+        tmem_ld_x16(trow + c, v);
+        float bv[16];
+        if (brow != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) bv[j] = __ldg(brow + static_cast<size_t>(min(c + j, T - 1)) * T);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) bv[j] = 0.f;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float s = __uint_as_float(v[j]) + bv[j];
+            if (qreg >= 0 && s_region[c + j] != qreg) s -= 100.0f;
+            sc[j] = s;
+        }
     };
 
     float mx = -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < TKP; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(trow + c, v);
-        tmem_ld_wait();
+        float sc[16];
+        load_chunk(c, sc);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            if (c + j < T) mx = fmaxf(mx, score(v[j], c + j));
+            if (c + j < T) mx = fmaxf(mx, sc[j]);
     }
     const float mxl = mx * kLog2e;
     float sum = 0.f;
 #pragma unroll 1
     for (int c = 0; c < TKP; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(trow + c, v);
-        tmem_ld_wait();
+        float sc[16];
+        load_chunk(c, sc);
         float pv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            pv[j] = (c + j < T) ? ex2f(fmaf(score(v[j], c + j), kLog2e, -mxl)) : 0.f;
+            pv[j] = (c + j < T) ? ex2f(fmaf(sc[j], kLog2e, -mxl)) : 0.f;
             sum += pv[j];
         }
         // two 16-byte chunks (8 keys each) of row r in key block c/64, 128B-swizzled
@@ -249,7 +264,10 @@ extern "C" int vitad_attention_f16(const vitad_attention_args* args, void* strea
     AttnParams p{static_cast<__half*>(a.out), a.bias, a.region, a.win2tok, a.tokens, a.heads, a.head_dim, nW,
                  nW * a.tokens};
     dim3 grid((a.tokens + 127) / 128, BH);
-    ProfScope prof("attention", static_cast<cudaStream_t>(stream));
+    char pname[64];
+    snprintf(pname, sizeof(pname), "attention_t%d_h%d_hd%d_bw%d%s", a.tokens, a.heads, a.head_dim, a.batch_windows,
+             a.region ? "_shift" : "");
+    ProfScope prof(pname, static_cast<cudaStream_t>(stream));
     kern<<<grid, 128, S::kTotal, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);

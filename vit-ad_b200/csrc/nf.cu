@@ -48,6 +48,14 @@ struct EpiNfCouple {
             uint32_t as[16], at[16];
             tmem_ld_x16(taddr + q, as);
             tmem_ld_x16(taddr + kNfHalf + q, at);
+            // issue all 32 stream loads of this chunk before touching the accumulators (latency overlap)
+            float x1a[16], x2a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int c = n_tile * kNfHalf + q + j;
+                x1a[j] = __ldg(xin + static_cast<size_t>(c) * ld + r);
+                x2a[j] = __ldg(xin + static_cast<size_t>(c_half + c) * ld + r);
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -55,8 +63,8 @@ struct EpiNfCouple {
                 const float a_s = __uint_as_float(as[j]) + __ldg(b2p + n_tile * kNfTile + q + j);
                 const float a_t = __uint_as_float(at[j]) + __ldg(b2p + n_tile * kNfTile + kNfHalf + q + j);
                 const float sv = clamp * tanhf(a_s);
-                const float x1v = xin[static_cast<size_t>(c) * ld + r];
-                const float x2v = xin[static_cast<size_t>(c_half + c) * ld + r];
+                const float x1v = x1a[j];
+                const float x2v = x2a[j];
                 const float y2 = x2v * expf(sv) + a_t;
                 if (valid) {
                     xout[static_cast<size_t>(__ldg(inv_perm + c)) * ld + row] = x1v * __ldg(scale + c) + __ldg(offset + c);

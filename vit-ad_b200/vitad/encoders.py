@@ -367,7 +367,8 @@ class EncoderEsVit(TransformerEncoder):
                 B.ln1_w, B.ln1_b = f32(blk.norm1.weight), f32(blk.norm1.bias)
                 B.qkv_w, B.qkv_b = f16(blk.attn.qkv.weight), f32(blk.attn.qkv.bias)
                 table, index = blk.attn.relative_position_bias_table.detach().float(), blk.attn.relative_position_index
-                B.attn_bias = f32(table[index.reshape(-1).long()].view(T, T, -1).permute(2, 0, 1))
+                # dense bias[h][key][query] (key-major: the kernel's query lanes read contiguous memory)
+                B.attn_bias = f32(table[index.reshape(-1).long()].view(T, T, -1).permute(2, 1, 0))
                 B.proj_w, B.proj_b = f16(blk.attn.proj.weight), f32(blk.attn.proj.bias)
                 B.ln2_w, B.ln2_b = f32(blk.norm2.weight), f32(blk.norm2.bias)
                 B.fc1_w, B.fc1_b = f16(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias)

@@ -114,7 +114,7 @@ def patchify(images, patch):
 
 def attention(q, k, vt, tokens, windows=1, bias=None, region=None, win2tok=None):
     """q,k fp16 [BW,H,T,hd] (q pre-scaled); vt fp16 [BW,H,hd,Tpad] zero-padded -> fp16 [BW*T, H*hd] in original
-    token order.  Swin: bias fp32 [H,T,T], region int8 [windows,T], win2tok int32 [windows*T]."""
+    token order.  Swin: bias fp32 [H,T_key,T_query] (key-major), region int8 [windows,T], win2tok int32 [windows*T]."""
     _need_cuda(q, k, vt, bias, region, win2tok)
     bw, h, t, hd = q.shape
     out = torch.empty((bw * t, h * hd), device=q.device, dtype=torch.float16)
