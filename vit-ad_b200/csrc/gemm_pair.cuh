@@ -38,7 +38,11 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        // default semantics: what is ordered here are this warp's TMEM reads (tcgen05.wait::ld +
+        // tcgen05.fence::before_thread_sync precede the arrive), not its global stores; a
+        // .release.cluster arrive costs MEMBAR + ERRBAR = a full drain of the epilogue's stores (15-20% of
+        // the epilogue warps' samples in ncu)
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(smem_u32(bar))
         : "memory");
 }
