@@ -18,14 +18,18 @@ def _ref(a, w, b):
     return a.float() @ w.float().t() + b
 
 
-@pytest.mark.parametrize("block_n", [96, 128, 256])
+@pytest.mark.parametrize("block_n", [0, 96, 128, 256])
 @pytest.mark.parametrize(
     "m,n,k",
-    [(128, 256, 64), (128, 256, 768), (6336, 768, 768), (6336, 2304, 768), (200, 3072, 784), (77, 512, 3072)],
+    [(128, 256, 64), (128, 256, 768), (6336, 768, 768), (6336, 2304, 768), (200, 3072, 784), (77, 512, 3072),
+     (6336, 800, 128), (1568, 96, 96), (3000, 1152, 384)],
 )
 def test_linear_bias_fp16(m, n, k, block_n):
+    """Covers the single-CTA kernel (M <= 128), the CTA-pair kernel's full-width tiles and its cut tail
+    (6336x768: 74 tiles of 256 columns + 8 pieces of 32; 6336x800: pieces of 128 with a ragged last column block)."""
     from vitad import _lib, ops
 
+    # block_n is a hint: 96 exists only in the single-CTA kernel (M <= 128), elsewhere the library picks
     a, w, b = _mk(m, n, k)
     out = ops.linear(a, w, b, _lib.EPI_BIAS_F16, block_n=block_n)
     torch.cuda.synchronize()
@@ -51,9 +55,10 @@ def test_linear_gelu_and_residual():
 
     a, w, b = _mk(6336, 3072, 768, seed=2)
     out = ops.linear(a, w, b, _lib.EPI_BIAS_GELU_F16)
-    ref = torch.nn.functional.gelu(_ref(a, w, b))
+    ref = torch.nn.functional.gelu(_ref(a, w, b))  # exact erf GELU (timm Mlp: nn.GELU())
     torch.cuda.synchronize()
-    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    # fp16 output rounding (2^-11 relative) + 3.5e-6 absolute from the sigmoid-polynomial GELU of the epilogue
+    assert ((out.float() - ref).abs() <= 6e-4 * ref.abs() + 1e-5).all()
 
     a, w, b = _mk(6336, 768, 3072, seed=3)
     resid = torch.randn(6336, 768, device="cuda")

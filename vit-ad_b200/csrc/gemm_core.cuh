@@ -42,6 +42,27 @@ struct GemmSmem {
     static_assert(kBBytes % 1024 == 0, "B stage must keep 1024-byte alignment (BLOCK_N % 8 == 0)");
 };
 
+// Optional in-kernel timeline (diagnostic builds only: `make TL=1` -> lib/libvitad_tl.so): clock64 stamps of the
+// role loops of every CTA into a [grid][64] buffer, read back by tools/gpu_timeline.py.
+#ifdef VITAD_TIMELINE
+static __device__ unsigned long long* g_timeline = nullptr;
+__device__ __forceinline__ void tl_stamp(int slot, bool global = false) {
+    if (g_timeline != nullptr && slot < 64) {
+        unsigned long long t;
+        if (global)
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        else
+            t = static_cast<unsigned long long>(clock64());
+        g_timeline[static_cast<size_t>(blockIdx.x) * 64 + slot] = t;
+    }
+}
+#define VITAD_TL(slot) ::vitad::tl_stamp(slot)
+#define VITAD_TLG(slot) ::vitad::tl_stamp(slot, true)
+#else
+#define VITAD_TL(slot)
+#define VITAD_TLG(slot)
+#endif
+
 __host__ __device__ constexpr uint32_t tmem_cols_pow2(int n) {
     return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u;
 }

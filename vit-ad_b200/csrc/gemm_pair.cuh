@@ -143,6 +143,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int num_kb = (num_k16 + 3) / 4;
 
     if (threadIdx.x == 0) {
+        VITAD_TL(0);
+        VITAD_TLG(1);
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         for (int i = 0; i < kStages; ++i) {
@@ -161,6 +163,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     cluster_sync_all();  // barriers of both CTAs initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    if (threadIdx.x == 0) VITAD_TL(2);
 
     if (warp == 0) {
         // TMA producer (both CTAs): warp-uniform loop, one elected lane issues.
@@ -178,6 +181,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                         if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
                         tma_load_2d_pair(smem_a + stage * S::kABytes, &tma_a, &full_bar[stage], kb * kBlockK, row0);
                         tma_load_2d_pair(smem_b + stage * S::kBBytes, &tma_b, &full_bar[stage], kb * kBlockK, n_row0);
+                        if (tile == cluster_id && sub == 0 && kb == 0) VITAD_TL(3);
+                        VITAD_TL(4);
                     }
                     __syncwarp();
                     if (++stage == kStages) {
@@ -197,14 +202,18 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            int tl_i = 0;
+            (void)tl_i;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 for (int sub = 0; sub < SUBTILES; ++sub) {
                     mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
+                    if (elect_one() && tl_i < 12) VITAD_TL(8 + 3 * tl_i);
                     const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                     for (int kb = 0; kb < num_kb; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
+                        if (kb == 0 && elect_one() && tl_i < 12) VITAD_TL(9 + 3 * tl_i);
                         const uint32_t a_lo = a_lo0 + stage * (S::kABytes >> 4);
                         const uint32_t b_lo = b_lo0 + stage * (S::kBBytes >> 4);
                         const int nk = num_k16 - kb * 4;
@@ -223,7 +232,11 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                             phase ^= 1;
                         }
                     }
-                    if (elect_one()) umma_commit_pair(&tmem_full[acc]);
+                    if (elect_one()) {
+                        umma_commit_pair(&tmem_full[acc]);
+                        if (tl_i < 12) VITAD_TL(10 + 3 * tl_i);
+                    }
+                    ++tl_i;
                     __syncwarp();
                     if (++acc == 2) {
                         acc = 0;
@@ -252,11 +265,13 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                     mbar_wait(&tmem_full[acc], (unit >> 1) & 1);
                     __syncwarp();
                     tc_fence_after();
+                    if (threadIdx.x == 64 && unit < 8) VITAD_TL(44 + 2 * unit);
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
                     epi.sub(sub, m_blk, n_tile, row, taddr, c0, c1);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+                    if (threadIdx.x == 64 && unit < 8) VITAD_TL(45 + 2 * unit);
                 }
             }
             if constexpr (kSplit) {
@@ -278,6 +293,10 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     tc_fence_before();
     __syncwarp();
     cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still signal or read it
+    if (threadIdx.x == 0) {
+        VITAD_TL(60);
+        VITAD_TLG(61);
+    }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, kTmemCols);

@@ -1,49 +1,103 @@
 // vitad_linear_f16: dispatch of the tcgen05 GEMM main loops with the encoder's fused epilogues.
 //
-// Tile choice.  The encoder's GEMMs are small (M = 6336 at batch 32, N in {768, 2304, 3072}), so the
-// persistent schedule is dominated by wave quantisation: with 256-row CTA-pair tiles there are 25 row
-// blocks, and N = 768 at BLOCK_N = 256 gives 75 tiles for 74 SM pairs (two waves, the second almost empty).
-// pick_block_n() minimises ceil(tiles / SM pairs) * BLOCK_N over the instantiated widths; BLOCK_N = 96
-// divides 768/2304/3072 and lands within 2-10% of the ideal split for all three.
+// Tile choice (M > 128: CTA-pair kernel of gemm_staged.cuh).  The encoder's GEMMs are small (M = 6336 at batch
+// 32, N in {768, 2304, 3072}): narrow tiles are bound by L2->SM operand traffic, wide tiles by wave quantisation
+// (N = 768 at BLOCK_N = 256: 75 tiles for 74 SM pairs).  make_sched() runs the full waves on 256 x BLOCK_N tiles
+// and cuts the tiles of the last, partial wave into 2/4/8 narrower ones so that wave is short and full;
+// pick_block_n() compares BLOCK_N = 128 and 256 under that schedule.  M <= 128 uses the single-CTA kernel.
 #include <atomic>
 
 #include "gemm_epilogues.cuh"
 #include "gemm_pair.cuh"
+#include "gemm_staged.cuh"
 #include "host_util.cuh"
 
 namespace vitad {
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_use_pair;
 
-// CTA-pair (cta_group::2) launch: 256-row tiles, cluster of two CTAs.
+// Full waves of 256 x bn tiles, then the remaining tiles cut into `split` pieces each (<= one wave of pieces).
+static TileSched make_sched(int m, int n, int bn, int clusters) {
+    TileSched s;
+    s.num_m = (m + 2 * kBlockM - 1) / (2 * kBlockM);
+    const int tiles = s.num_m * ((n + bn - 1) / bn);
+    const int rest = tiles % clusters;
+    s.big_tiles = tiles - rest;
+    s.tail_split = 1;
+    while (s.tail_split < 8 && rest * s.tail_split * 2 <= clusters && bn / (s.tail_split * 2) >= 32) s.tail_split *= 2;
+    s.tail_tiles = rest * s.tail_split;
+    s.tail_w = bn / s.tail_split;
+    return s;
+}
+// Relative cost of a schedule in units of "one 256 x 256 tile": a cut piece still streams the whole 256-row A block,
+// so a wave of pieces costs ~max(w/256, 0.55) of a full wave (measured: L2->SM delivery per SM, not MMA, bounds it).
+static double sched_cost(const TileSched& s, int bn, int clusters) {
+    const double full = static_cast<double>(s.big_tiles / clusters) * bn / 256.0;
+    if (s.tail_tiles == 0) return full;
+    const double piece = static_cast<double>(s.tail_w) / 256.0;
+    return full + (piece > 0.55 * bn / 256.0 ? piece : 0.55 * bn / 256.0);
+}
+
+// CTA-pair launch with the staged epilogue (gemm_staged.cuh).
 template <int BLOCK_N, class Epi>
-static int launch_gemm_pair(const vitad_linear_args& a, const Epi& epi, cudaStream_t stream) {
-    using S = PairSmem<BLOCK_N>;
-    CUtensorMap ta, tb;
+static int launch_gemm_staged(const vitad_linear_args& a, const Epi& epi, cudaStream_t stream) {
+    using S = StagedSmem<BLOCK_N>;
+    const int max_clusters = device_sm_count() / 2;
+    const TileSched sched = make_sched(a.m, a.n, BLOCK_N, max_clusters);
+    CUtensorMap ta, tb, tbt;
     int rc = make_tmap_f16_2d(&ta, a.a, a.m, a.k, a.lda, kBlockM);
     if (rc) return rc;
     rc = make_tmap_f16_2d(&tb, a.w, a.n, a.k, a.ldw, BLOCK_N / 2);
     if (rc) return rc;
-    auto kern = gemm2_tc_kernel<BLOCK_N, 1, Epi>;
+    rc = make_tmap_f16_2d(&tbt, a.w, a.n, a.k, a.ldw, sched.tail_w / 2);
+    if (rc) return rc;
+    auto kern = gemm3_tc_kernel<BLOCK_N, Epi>;
     static bool attr_set = false;
     if (!attr_set) {
         VITAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
         attr_set = true;
     }
-    const int num_m = (a.m + 2 * kBlockM - 1) / (2 * kBlockM);
-    const int num_n = (a.n + BLOCK_N - 1) / BLOCK_N;
-    const int tiles = num_m * num_n;
-    const int max_clusters = device_sm_count() / 2;
+    const int tiles = sched.big_tiles + sched.tail_tiles;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
-    kern<<<2 * clusters, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, a.m, num_n, a.k, epi);
+    kern<<<2 * clusters, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, tbt, sched, a.k, epi);
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;
 }
 
+template <int BLOCK_N>
+static int dispatch_staged(const vitad_linear_args& a, cudaStream_t stream) {
+    switch (a.epilogue) {
+        case VITAD_EPI_BIAS_F16:
+            return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<0>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n}, stream);
+        case VITAD_EPI_BIAS_GELU_F16:
+            return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<1>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n}, stream);
+        case VITAD_EPI_BIAS_RELU_F16:
+            return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<2>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n}, stream);
+        case VITAD_EPI_RESIDUAL_F32:
+            return launch_gemm_staged<BLOCK_N>(a, SEpiResidualF32{a.bias, a.resid, static_cast<float*>(a.out), a.ldo, a.m, a.n},
+                                               stream);
+        case VITAD_EPI_QKV: {
+            const int hd = a.head_dim > 0 ? a.head_dim : 64;
+            const int nw = a.windows > 0 ? a.windows : 1;
+            const int wt = a.win_tokens > 0 ? a.win_tokens : a.tokens;
+            SEpiQkv e{a.bias, static_cast<__half*>(a.q), static_cast<__half*>(a.kmat), static_cast<__half*>(a.vt),
+                      a.tok2win, a.m, a.tokens, wt, a.tokens_pad, a.heads, hd, nw, a.q_scale};
+            return launch_gemm_staged<BLOCK_N>(a, e, stream);
+        }
+        case VITAD_EPI_PATCH_EMBED:
+            return launch_gemm_staged<BLOCK_N>(
+                a, SEpiPatchEmbed{a.bias, a.pos, static_cast<float*>(a.out), a.m, a.patches, a.prefix, a.n}, stream);
+        case VITAD_EPI_F32:
+            return launch_gemm_staged<BLOCK_N>(a, SEpiBiasF32{a.bias, static_cast<float*>(a.out), a.ldo, a.m, a.n}, stream);
+        default:
+            set_error("unknown epilogue %d", a.epilogue);
+            return VITAD_ERR_ARG;
+    }
+}
+
 template <int BLOCK_N, class Epi>
 static int launch_gemm(const vitad_linear_args& a, const Epi& epi, cudaStream_t stream) {
-    if (g_use_pair.load() && a.m > kBlockM) return launch_gemm_pair<BLOCK_N>(a, epi, stream);
     using S = GemmSmem<BLOCK_N>;
     CUtensorMap ta, tb;
     int rc = make_tmap_f16_2d(&ta, a.a, a.m, a.k, a.lda, kBlockM);
@@ -118,12 +172,10 @@ static int dispatch_epilogue(const vitad_linear_args& a, cudaStream_t stream) {
     }
 }
 
-// Minimise (waves of the persistent schedule) x (tile width); ties go to the wider tile.
-static int pick_block_n(int m, int n) {
-    const bool pair = g_use_pair.load() && m > kBlockM;
-    const int rows = pair ? 2 * kBlockM : kBlockM;
-    const int workers = pair ? device_sm_count() / 2 : device_sm_count();
-    const int num_m = (m + rows - 1) / rows;
+// Single-CTA kernel (M <= 128 or pairs disabled): minimise (waves) x (tile width); ties go to the wider tile.
+static int pick_block_n_single(int m, int n) {
+    const int workers = device_sm_count();
+    const int num_m = (m + kBlockM - 1) / kBlockM;
     const int cand[3] = {256, 128, 96};
     int best = 256;
     long best_cost = -1;
@@ -137,8 +189,23 @@ static int pick_block_n(int m, int n) {
     }
     return best;
 }
+static int pick_block_n_pair(int m, int n) {
+    const int clusters = device_sm_count() / 2;
+    const double c256 = sched_cost(make_sched(m, n, 256, clusters), 256, clusters);
+    const double c128 = sched_cost(make_sched(m, n, 128, clusters), 128, clusters) * 1.25;  // 128-wide: more L2 traffic
+    return c128 < c256 ? 128 : 256;
+}
 
 }  // namespace vitad
+
+#ifdef VITAD_TIMELINE
+// Diagnostic builds only: point the CTA-pair GEMM's timeline stamps at a [grid][64] uint64 device buffer.
+extern "C" int vitad_debug_timeline(void* device_buffer) {
+    unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
+    VITAD_CUDA_OK(cudaMemcpyToSymbol(vitad::g_timeline, &p, sizeof(p)));
+    return VITAD_OK;
+}
+#endif
 
 extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
     using namespace vitad;
@@ -189,10 +256,17 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
             break;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int bn = a.block_n == 0 ? pick_block_n(a.m, a.n) : a.block_n;
+    const bool pair = g_use_pair.load() && a.m > kBlockM;
+    // block_n is a hint: widths the selected kernel does not instantiate fall back to the library's choice
+    const bool hint_ok = pair ? (a.block_n == 128 || a.block_n == 256) : (a.block_n == 96 || a.block_n == 128 || a.block_n == 256);
+    const int bn = hint_ok ? a.block_n : (pair ? pick_block_n_pair(a.m, a.n) : pick_block_n_single(a.m, a.n));
     char pname[64];
     snprintf(pname, sizeof(pname), "gemm_epi%d_n%d_k%d_bn%d", a.epilogue, a.n, a.k, bn);
     ProfScope prof(pname, s);
+    if (pair) {
+        if (bn == 256) return dispatch_staged<256>(a, s);
+        return dispatch_staged<128>(a, s);
+    }
     if (bn == 256) return dispatch_epilogue<256>(a, s);
     if (bn == 128) return dispatch_epilogue<128>(a, s);
     if (bn == 96) return dispatch_epilogue<96>(a, s);

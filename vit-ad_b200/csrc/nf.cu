@@ -292,7 +292,7 @@ extern "C" int vitad_nf_forward(const vitad_nf_weights* wp, const float* tokens,
         vitad_linear_args la;
         memset(&la, 0, sizeof(la));
         la.a = a1, la.w = st.w0p, la.bias = st.b0p, la.m = M, la.n = w.hidden_pad, la.k = k1, la.lda = k1, la.ldw = k1;
-        la.epilogue = VITAD_EPI_BIAS_RELU_F16, la.out = ws.h, la.ldo = w.hidden_pad, la.block_n = 96;
+        la.epilogue = VITAD_EPI_BIAS_RELU_F16, la.out = ws.h, la.ldo = w.hidden_pad;
         if ((rc = vitad_linear_f16(&la, s))) return rc;
         const void* a2 = ws.h;
         int k2 = w.hidden_pad;

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libvitad.so")
+# VITAD_LIB selects another build of the same library (diagnostic variants such as lib/libvitad_tl.so)
+LIB_PATH = os.environ.get("VITAD_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libvitad.so")
 
 
 class VitadError(RuntimeError):
