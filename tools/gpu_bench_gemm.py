@@ -44,9 +44,10 @@ for name, n, k in shapes:
     q = torch.empty(32, 12, 198, 64, dtype=torch.float16, device="cuda")
     kk = torch.empty_like(q)
     vt = torch.zeros(32, 12, 64, 256, dtype=torch.float16, device="cuda")
-    for bn in bns:
+    for bn, ew in [(b_, e_) for b_ in bns for e_ in (8, 16)]:
         if n % bn:
             continue
+        _lib.lib.vitad_set_epilogue_warps(ew)
         res = []
         for epi, label in ((_lib.EPI_BIAS_F16, "bias"), (_lib.EPI_BIAS_GELU_F16, "gelu"), (_lib.EPI_RESIDUAL_F32, "resid")):
             if epi == _lib.EPI_RESIDUAL_F32:
@@ -58,7 +59,8 @@ for name, n, k in shapes:
         if name == "qkv":
             t = timed_graph(lambda: ops.linear_qkv(a, w, b, 32, 198, 12, 256, q, kk, vt, 0.125, block_n=bn))
             res.append(f"qkv {t:6.1f} us {flops/t/1e6:6.1f}")
-        print(f"   bn{bn:3d}: " + " | ".join(res))
+        print(f"   bn{bn:3d} ew{ew:2d}: " + " | ".join(res))
+    _lib.lib.vitad_set_epilogue_warps(0)
 # fixed overhead: one k-block, one wave
 a = (torch.randn(M, 64) * 0.5).half().cuda(); w = (torch.randn(768, 64) * 0.05).half().cuda(); b = torch.zeros(768).cuda()
 o = torch.empty(M, 768, dtype=torch.float16, device="cuda")

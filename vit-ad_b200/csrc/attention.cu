@@ -18,6 +18,7 @@
 // Scores never touch HBM.  ~97 KB smem and 256 TMEM columns per CTA -> two CTAs per SM.
 #include <atomic>
 
+#include "gemm_core.cuh"
 #include "host_util.cuh"
 #include "ptx.cuh"
 
@@ -29,14 +30,19 @@ constexpr float kLog2e = 1.4426950408889634f;
 template <int TKP>
 struct AttnSmem {
     static constexpr int kKeyBlocks = (TKP + 63) / 64;
-    static constexpr int kPBytes = kKeyBlocks * 128 * 128;  // P: 128 rows x 64 keys x fp16 per block
     static constexpr int kQBytes = 128 * 128;
     static constexpr int kKBytes = TKP * 128;
     static constexpr int kVtBlockBytes = 64 * 128;  // 64 rows x 64 keys
     static constexpr int kVtBytes = kKeyBlocks * kVtBlockBytes;
-    static constexpr int kRegion0 = kPBytes > kQBytes + kKBytes ? kPBytes : kQBytes + kKBytes;
-    static constexpr int kTotal = kRegion0 + kVtBytes + 64 + 256 + 1024;  // + barriers + key region ids
+    static constexpr int kRegion0 = ((kQBytes + kKBytes + 1023) / 1024) * 1024;  // Q | K, later the output slabs
+    static constexpr int kTotal = kRegion0 + kVtBytes + 64 + 256 + 3072 + 1024;  // + barriers + key region ids + max/ref/sum exchange
+    static_assert(kRegion0 >= 8 * 2048, "output staging slabs overlay Q|K");
 };
+
+// TMEM columns of one CTA (256 allocated): S = Q.K^T in [0, TKP); P (fp16 pairs, 8 columns per 16 keys) is written
+// in place over the S columns its own thread has already consumed for the first key half ([0, 56)) and into the unused
+// tail [208, 256) for the second; O accumulates in [64, 128) (even key chunks) and [128, 192) (odd) once S is dead.
+constexpr uint32_t kPCol1 = 208, kOCol = 64;
 
 struct AttnParams {
     __half* out;
@@ -44,10 +50,22 @@ struct AttnParams {
     const signed char* region;  // [nW][T] or null
     const int* win2tok;         // [nW*T] or null
     int T, H, hd, nW, L;        // window tokens, heads, head dim, windows per image, tokens per image
+    // Read only by the MMA-issuing warp, straight from the constant bank, so that its loop counters and operand
+    // addresses stay in uniform registers (a value shared with per-thread code lives in a vector register and costs
+    // four R2UR round trips, ~190 cycles, per issued MMA).
+    int u_nch, u_h0;            // 16-key chunks with valid keys; chunks of the first key half
+    uint32_t u_idesc_s;         // instruction descriptor of S = Q.K^T (M 128, N 16*u_nch)
 };
 
-template <int TKP>
-__global__ void __launch_bounds__(128, 2)
+constexpr int kAttnThreads = 256;
+
+// 256 threads: warp w owns TMEM lane quarter (w & 3) = query rows 32*(w&3)..+31 of the tile and key half (w >> 2);
+// two threads share a query row and exchange its running max / partial sum through shared memory.  Warps whose
+// 32 rows are all beyond T (the second tile of 198 tokens has 70 valid rows, a 49-token window 49) skip the softmax.
+// kBias / kMask specialise the relative-position bias and shifted-window mask away for DeiT: predicated-off
+// instructions still issue, and the generic loop spent 20 instructions per score where 5 are needed.
+template <int TKP, bool kBias, bool kMask>
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                  const __grid_constant__ CUtensorMap tma_vt, const AttnParams p) {
     using S = AttnSmem<TKP>;
@@ -57,169 +75,314 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint8_t* sP = smem;  // overlays sQ|sK once S has been produced
     uint8_t* sQ = smem;
     uint8_t* sK = smem + S::kQBytes;
     uint8_t* sVt = smem + S::kRegion0;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sVt + S::kVtBytes);  // qk, v, s, o
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
     signed char* s_region = reinterpret_cast<signed char*>(bars + 8);  // key region ids of this window
+    float* s_xch = reinterpret_cast<float*>(s_region + 256);           // 3 x [2 halves][128 rows]: first-group max, reference, sum
 
     const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int quarter = warp & 3, half = warp >> 2;
     const int bh = blockIdx.y;  // (batch*window, head)
     const int m0 = blockIdx.x * 128;
     const int T = p.T;
     const int bw = bh / p.H, h = bh - bw * p.H;
     const int b = bw / p.nW, widx = bw - b * p.nW;
+    const int nch = (T + 15) >> 4;  // 16-key chunks that hold valid keys
 
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tma_q);
-        tma_prefetch_desc(&tma_k);
-        tma_prefetch_desc(&tma_vt);
-        for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
-        fence_barrier_init();
+    // Warp 0 drives TMA and the tensor core warp-uniformly (one elected lane issues; a loop under `if (lane == 0)`
+    // costs ~115 cycles per MMA in vector->uniform register moves, 1500 cycles for the 13 P.V MMAs).  The loads are
+    // issued before the TMEM allocation so their L2 latency overlaps it.
+    if (warp == 0) {
+        if (elect_one()) {
+            VITAD_TL(0);
+            VITAD_TLG(1);
+            tma_prefetch_desc(&tma_q);
+            tma_prefetch_desc(&tma_k);
+            tma_prefetch_desc(&tma_vt);
+            for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+            fence_barrier_init();
+            mbar_arrive_expect_tx(&bars[0], S::kQBytes + S::kKBytes);
+            tma_load_3d(sQ, &tma_q, &bars[0], 0, m0, bh);  // rows >= T and columns >= hd: zero-filled
+            tma_load_3d(sK, &tma_k, &bars[0], 0, 0, bh);
+            mbar_arrive_expect_tx(&bars[1], S::kVtBytes);
+            for (int kb = 0; kb < S::kKeyBlocks; ++kb)
+                tma_load_2d(sVt + kb * S::kVtBlockBytes, &tma_vt, &bars[1], kb * 64, bh * p.hd);
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, kTmemCols);
     }
-    if (p.region != nullptr)
-        for (int i = threadIdx.x; i < T; i += 128) s_region[i] = p.region[widx * T + i];
-    if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+    if constexpr (kMask)
+        for (int i = threadIdx.x; i < T; i += kAttnThreads) s_region[i] = p.region[widx * T + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(&bars[0], S::kQBytes + S::kKBytes);
-        tma_load_3d(sQ, &tma_q, &bars[0], 0, m0, bh);  // rows >= T and columns >= hd: zero-filled
-        tma_load_3d(sK, &tma_k, &bars[0], 0, 0, bh);
-        mbar_arrive_expect_tx(&bars[1], S::kVtBytes);
-        for (int kb = 0; kb < S::kKeyBlocks; ++kb)
-            tma_load_2d(sVt + kb * S::kVtBlockBytes, &tma_vt, &bars[1], kb * 64, bh * p.hd);
+    if (warp == 0) {
+        if (lane == 0) VITAD_TL(2);
         mbar_wait(&bars[0], 0);
         tc_fence_after();
-        constexpr uint32_t idesc_s = make_idesc_f16(128, TKP);
-        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+        if (lane == 0) VITAD_TL(3);
+        const uint32_t idesc_s = p.u_idesc_s;
+        const uint32_t q_lo = smem_desc_lo(smem_u32(sQ)), k_lo = smem_desc_lo(smem_u32(sK));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            umma_f16_ss(tmem, make_smem_desc_sw128(qa + k * 32), make_smem_desc_sw128(ka + k * 32), idesc_s, k != 0);
-        umma_commit(&bars[2]);
+            for (int k = 0; k < 4; ++k)
+                umma_f16_ss(tmem, smem_desc_join(q_lo + 2 * k), smem_desc_join(k_lo + 2 * k), idesc_s, k != 0);
+            umma_commit(&bars[2]);
+        }
+        __syncwarp();
     }
 
-    // ---- softmax: thread r owns query row m0 + r = TMEM lane r
+    // ---- softmax: threads (quarter, lane) of both halves own query row m0 + r = TMEM lane r
+    const int r = quarter * 32 + lane;
+    const int tq = m0 + r;
+    const bool qvalid = tq < T;
+    const bool warp_active = m0 + quarter * 32 < T;  // warp-uniform
+    const int c_begin = half == 0 ? 0 : ((nch + 1) >> 1) * 16;
+    const int c_end = half == 0 ? ((nch + 1) >> 1) * 16 : nch * 16;
+    // bias is stored key-major ([H][key][query]) so that the 32 query lanes of a warp read contiguous memory
+    const float* brow = (kBias && qvalid) ? p.bias + static_cast<size_t>(h) * T * T + tq : nullptr;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    float sum = 0.f;
+
     mbar_wait(&bars[2], 0);
     __syncwarp();
     tc_fence_after();
-    const int r = threadIdx.x;
-    const int tq = m0 + r;
-    const bool qvalid = tq < T;
-    // bias is stored key-major ([H][key][query]) so that the 32 query lanes of a warp read contiguous memory
-    const float* brow = (p.bias != nullptr && qvalid) ? p.bias + static_cast<size_t>(h) * T * T + tq : nullptr;
-    const int qreg = (p.region != nullptr && qvalid) ? s_region[tq] : -1;
-    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    if (threadIdx.x == 32) VITAD_TL(5);
+    const int qreg = (kMask && qvalid) ? s_region[tq] : -1;
 
-    // scores of one 16-key chunk: accumulator + bias (16 independent loads issued before the TMEM wait so their
-    // latency overlaps; a load per element inside the compare chain serialised ~400 L2 round trips per thread)
-    // + region mask.  Key indices are clamped so the loads stay in bounds; invalid keys are masked by the caller.
-    auto load_chunk = [&](int c, float (&sc)[16]) {
-        uint32_t v[16];
+    // scores of two 16-key chunks (the second only when c + 16 < c_end): accumulator + bias (independent loads
+    // issued before the single TMEM wait so their latency overlaps) + region mask.  Key indices are clamped so
+    // the loads stay in bounds; keys >= T are masked by the caller.
+    auto load_pair = [&](int c, bool two, float (&sc)[32]) {
+        uint32_t v[32];
         tmem_ld_x16(trow + c, v);
-        float bv[16];
-        if (brow != nullptr) {
+        if (two) tmem_ld_x16(trow + c + 16, v + 16);
+        float bv[32];
+        if constexpr (kBias) {
+            if (brow != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) bv[j] = __ldg(brow + static_cast<size_t>(min(c + j, T - 1)) * T);
-        } else {
+                for (int j = 0; j < 32; ++j) bv[j] = __ldg(brow + static_cast<size_t>(min(c + j, T - 1)) * T);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) bv[j] = 0.f;
+                for (int j = 0; j < 32; ++j) bv[j] = 0.f;
+            }
         }
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float s = __uint_as_float(v[j]) + bv[j];
-            if (qreg >= 0 && s_region[c + j] != qreg) s -= 100.0f;
-            sc[j] = s;
+        for (int j = 0; j < 32; ++j) {
+            float sv = __uint_as_float(v[j]);
+            if constexpr (kBias) sv += bv[j];
+            if constexpr (kMask) {
+                if (qreg >= 0 && s_region[min(c + j, T - 1)] != qreg) sv -= 100.0f;
+            }
+            sc[j] = sv;
+        }
+    };
+    // max over the valid keys of a pair; `full` (warp-uniform): both chunks present and all 32 keys < T
+    auto pair_max = [&](int c, bool two, const float (&sc)[32]) {
+        float gm = -INFINITY;
+        if (two && c + 32 <= T) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gm = fmaxf(gm, sc[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if ((j < 16 || two) && c + j < T) gm = fmaxf(gm, sc[j]);
+        }
+        return gm;
+    };
+
+    // Single pass over the scores (TMEM reads, 64 B/clk per SM, bound this kernel: a max pass + an exp pass cost
+    // 2 x 106 KB per tile).  The two threads of a row agree on a reference m = max over their first 32 keys each
+    // (one exchange), then write P = 2^(s' - m') with the reference only raised when a later group exceeds it by
+    // more than 2^8 (P <= 256 stays far inside fp16): the rare raise, and a final mismatch between the two halves,
+    // rescale the thread's own P entries in shared memory.  Normalisation by the fp32 row sum happens on O.
+    constexpr float kTau = 8.0f;
+    float m2 = -INFINITY;  // reference in the log2 domain (m * log2 e)
+    float sc0[32];
+    const bool have0 = warp_active && c_begin < c_end;
+    const bool two0 = c_begin + 16 < c_end;
+    float g0 = -INFINITY;
+    if (have0) {
+        load_pair(c_begin, two0, sc0);
+        g0 = pair_max(c_begin, two0, sc0);
+    }
+    if (warp_active) s_xch[half * 128 + r] = g0;
+    __syncthreads();
+    if (threadIdx.x == 32) VITAD_TL(6);
+
+    // TMEM address of this thread's P entries for the 16-key chunk starting at key cc
+    auto p_addr = [&](int cc) { return trow + (half == 0 ? (cc >> 1) : kPCol1 + ((cc - c_begin) >> 1)); };
+    // multiply the warp's P entries of key chunks [c_begin, c_done) by the per-row factor f (warp-collective)
+    auto rescale_p = [&](int c_done, float f) {
+        const __half2 f2 = __float2half2_rn(f);
+        for (int cc = c_begin; cc < c_done; cc += 16) {
+            uint32_t u[8];
+            tmem_ld_x8(p_addr(cc), u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                __half2 hv = *reinterpret_cast<__half2*>(&u[e]);
+                hv = __hmul2(hv, f2);
+                u[e] = *reinterpret_cast<uint32_t*>(&hv);
+            }
+            tmem_st_x8(p_addr(cc), u);
+        }
+    };
+    auto emit_group = [&](int c, bool two, float gmax, const float (&sc)[32]) {
+        const float g2 = gmax * kLog2e;
+        const bool raise = g2 > m2 + kTau;
+        if (__any_sync(0xffffffffu, raise)) {  // rare: raise the reference, rescale what the warp has written so far
+            const float f = raise ? ex2f(m2 - g2) : 1.0f;
+            rescale_p(c, f);
+            sum *= f;
+            if (raise) m2 = g2;
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            if (g == 1 && !two) break;
+            const int cc = c + 16 * g;
+            float pv[16];
+            if (cc + 16 <= T) {  // warp-uniform: no per-key validity test
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pv[j] = ex2f(fmaf(sc[16 * g + j], kLog2e, -m2));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pv[j] = (cc + j < T) ? ex2f(fmaf(sc[16 * g + j], kLog2e, -m2)) : 0.f;
+            }
+            float ps = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) ps += (pv[j] + pv[j + 1]) + (pv[j + 2] + pv[j + 3]);
+            sum += ps;
+            uint32_t u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = pack_h2(pv[2 * j], pv[2 * j + 1]);
+            tmem_st_x8(p_addr(cc), u);
         }
     };
 
-    float mx = -INFINITY;
+    float* s_m2 = s_xch + 256;   // final references of both halves
+    float* s_sum = s_xch + 512;  // partial row sums of both halves
+    if (warp_active) {
+        m2 = fmaxf(g0, s_xch[(half ^ 1) * 128 + r]) * kLog2e;  // key 0 is always valid: finite for valid rows
+        if (!qvalid) m2 = 0.f;
+        if (have0) emit_group(c_begin, two0, g0, sc0);
 #pragma unroll 1
-    for (int c = 0; c < TKP; c += 16) {
-        float sc[16];
-        load_chunk(c, sc);
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (c + j < T) mx = fmaxf(mx, sc[j]);
-    }
-    const float mxl = mx * kLog2e;
-    float sum = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < TKP; c += 16) {
-        float sc[16];
-        load_chunk(c, sc);
-        float pv[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            pv[j] = (c + j < T) ? ex2f(fmaf(sc[j], kLog2e, -mxl)) : 0.f;
-            sum += pv[j];
+        for (int c = c_begin + 32; c < c_end; c += 32) {
+            const bool two = c + 16 < c_end;
+            float sc[32];
+            load_pair(c, two, sc);
+            emit_group(c, two, pair_max(c, two, sc), sc);
         }
-        // two 16-byte chunks (8 keys each) of row r in key block c/64, 128B-swizzled
-        const int blk = c >> 6;
-        const int chunk0 = (c & 63) >> 3;
-        uint8_t* rowp = sP + blk * (128 * 128) + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            uint4 u;
-            u.x = pack_h2(pv[8 * h2 + 0], pv[8 * h2 + 1]);
-            u.y = pack_h2(pv[8 * h2 + 2], pv[8 * h2 + 3]);
-            u.z = pack_h2(pv[8 * h2 + 4], pv[8 * h2 + 5]);
-            u.w = pack_h2(pv[8 * h2 + 6], pv[8 * h2 + 7]);
-            *reinterpret_cast<uint4*>(rowp + (((chunk0 + h2) ^ (r & 7)) << 4)) = u;
-        }
+        s_m2[half * 128 + r] = m2;
+        s_sum[half * 128 + r] = sum;
     }
-    // P (generic-proxy stores) must be visible to the tensor core (async proxy); S reads must be done.
-    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp_active) {
+        const float mp = s_m2[(half ^ 1) * 128 + r];
+        const float sp = s_sum[(half ^ 1) * 128 + r];
+        const float mm = fmaxf(m2, mp);
+        if (__any_sync(0xffffffffu, mp > m2))  // rare: the other half raised its reference
+            rescale_p(c_end, mp > m2 ? ex2f(m2 - mp) : 1.0f);
+        sum = sum * ex2f(m2 - mm) + sp * ex2f(mp - mm);
+        tmem_st_wait();
+    }
+    // P (tcgen05.st) complete and ordered before the MMA that reads it; all S reads done.
+    if (threadIdx.x == 32) VITAD_TL(7);
     tc_fence_before();
     __syncthreads();
 
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+        if (lane == 0) VITAD_TL(8);
         tc_fence_after();
         mbar_wait(&bars[1], 0);
         tc_fence_after();
         constexpr uint32_t idesc_o = make_idesc_f16(128, 64);
-        const uint32_t pa = smem_u32(sP), va = smem_u32(sVt);
-#pragma unroll 1
-        for (int kk = 0; kk < TKP / 16; ++kk) {
-            const int blk = kk >> 2, w = kk & 3;
-            umma_f16_ss(tmem, make_smem_desc_sw128(pa + blk * (128 * 128) + w * 32),
-                        make_smem_desc_sw128(va + blk * S::kVtBlockBytes + w * 32), idesc_o, kk != 0);
+        const uint32_t v_lo = smem_desc_lo(smem_u32(sVt));
+        // fully unrolled inside one elected region: every operand is (uniform base + constant), so the
+        // vector->uniform moves are hoisted and pipelined instead of serialising each MMA of a rolled loop
+        const int h0 = p.u_h0, nch_u = p.u_nch;
+        const uint32_t p1_base = tmem + kPCol1 - 8 * h0;  // second key half: chunk kk at p1_base + 8*kk
+        if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < TKP / 16; ++kk) {
+                if (kk < nch_u) {
+                    const uint32_t a_tmem = kk < h0 ? tmem + kk * 8 : p1_base + kk * 8;  // A = P from TMEM
+                    const uint32_t b_lo = v_lo + (kk >> 2) * (S::kVtBlockBytes >> 4) + 2 * (kk & 3);
+                    // two accumulators (even / odd key chunks): consecutive MMAs do not depend on each other
+                    umma_f16_ts(tmem + kOCol + (kk & 1) * 64, a_tmem, smem_desc_join(b_lo), idesc_o, kk >= 2);
+                }
+            }
         }
-        umma_commit(&bars[3]);
+        __syncwarp();
+        if (elect_one()) umma_commit(&bars[3]);
+        __syncwarp();
+        if (lane == 0) VITAD_TL(13);
     }
 
     mbar_wait(&bars[3], 0);
     __syncwarp();
     tc_fence_after();
-    const float inv = 1.0f / sum;
-    const int tok = qvalid ? (p.win2tok != nullptr ? __ldg(p.win2tok + widx * T + tq) : tq) : 0;
-    __half* orow = p.out + (static_cast<size_t>(b) * p.L + tok) * (p.H * p.hd) + h * p.hd;
-#pragma unroll
-    for (int c = 0; c < 64; c += 32) {
+    if (threadIdx.x == 32) VITAD_TL(9);
+    // warp (quarter, half) owns output columns [32*half, 32*half + 32) of its 32 rows.  Each thread holds one row
+    // (64 bytes as fp16); the warp transposes through a private 2 KB slab of the dead Q|K region so that a store
+    // instruction covers 8 rows x 64 contiguous bytes (full sectors) instead of 32 rows x 16 bytes.
+    if (warp_active && half * 32 < p.hd) {
+        const float inv = 1.0f / sum;
+        const int tok = qvalid ? (kBias && p.win2tok != nullptr ? __ldg(p.win2tok + widx * T + tq) : tq) : -1;
         uint32_t v[32];
-        tmem_ld_x32(trow + c, v);
-        tmem_ld_wait();
-        if (qvalid && c < p.hd) {
-            uint4* o = reinterpret_cast<uint4*>(orow + c);
+        if (threadIdx.x == 32) VITAD_TL(11);
+        tmem_ld_x32(trow + kOCol + half * 32, v);
+        if (nch >= 2) {  // second accumulator (odd key chunks)
+            uint32_t v2[32];
+            tmem_ld_x32(trow + kOCol + 64 + half * 32, v2);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint4 u;
-                u.x = pack_h2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
-                u.y = pack_h2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
-                u.z = pack_h2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
-                u.w = pack_h2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
-                o[j] = u;
-            }
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        }
+        tmem_ld_wait();
+        if (threadIdx.x == 32) VITAD_TL(12);
+        const uint32_t slab = smem_u32(sQ) + warp * 2048;  // Q|K are dead since S was produced
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t x0 = pack_h2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
+            const uint32_t x1 = pack_h2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
+            const uint32_t x2 = pack_h2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
+            const uint32_t x3 = pack_h2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
+            // row = lane (64 bytes), 16-byte chunk j rotated by the row so the 8 lanes of a phase hit distinct banks
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + lane * 64 + (((j + (lane >> 1)) & 3) << 4)),
+                         "r"(x0), "r"(x1), "r"(x2), "r"(x3)
+                         : "memory");
+        }
+        __syncwarp();
+        const int sub = lane >> 2, ch = lane & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + sub;
+            const int rtok = __shfl_sync(0xffffffffu, tok, rr);
+            uint4 u;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                         : "r"(slab + rr * 64 + (((ch + (rr >> 1)) & 3) << 4))
+                         : "memory");
+            if (rtok >= 0)
+                *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b) * p.L + rtok) * (p.H * p.hd) + h * p.hd +
+                                          half * 32 + ch * 8) = u;
         }
     }
+    if (threadIdx.x == 32) VITAD_TL(10);
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) {
+        VITAD_TL(60);
+        VITAD_TLG(61);
+    }
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem, kTmemCols);
@@ -229,6 +392,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 }  // namespace vitad
 
 using namespace vitad;
+
+#ifdef VITAD_TIMELINE
+// Diagnostic builds only: timeline stamps of the attention kernel into a [grid.y * grid.x][64] uint64 device buffer.
+extern "C" int vitad_debug_timeline_attention(void* device_buffer) {
+    unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
+    VITAD_CUDA_OK(cudaMemcpyToSymbol(vitad::g_timeline, &p, sizeof(p)));
+    return VITAD_OK;
+}
+#endif
 
 extern "C" int vitad_attention_f16(const vitad_attention_args* args, void* stream) {
     int rc = check_device_arch();
@@ -255,20 +427,25 @@ extern "C" int vitad_attention_f16(const vitad_attention_args* args, void* strea
     if (rc) return rc;
     rc = make_tmap_f16_2d(&tv, a.vt, static_cast<uint64_t>(BH) * hd, a.tokens_pad, a.tokens_pad, 64);
     if (rc) return rc;
-    auto kern = attention_kernel<TKP>;
+    VITAD_REQUIRE(!a.region || a.bias, VITAD_ERR_ARG, "a region mask is only supported together with a bias");
+    auto kern = a.region ? attention_kernel<TKP, true, true>
+                         : (a.bias ? attention_kernel<TKP, true, false> : attention_kernel<TKP, false, false>);
     static bool attr_set = false;
     if (!attr_set) {
-        VITAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        VITAD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<TKP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        VITAD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<TKP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        VITAD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<TKP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         attr_set = true;
     }
+    const int nch = (a.tokens + 15) / 16;
     AttnParams p{static_cast<__half*>(a.out), a.bias, a.region, a.win2tok, a.tokens, a.heads, a.head_dim, nW,
-                 nW * a.tokens};
+                 nW * a.tokens, nch, (nch + 1) / 2, make_idesc_f16(128, nch * 16)};
     dim3 grid((a.tokens + 127) / 128, BH);
     char pname[64];
     snprintf(pname, sizeof(pname), "attention_t%d_h%d_hd%d_bw%d%s", a.tokens, a.heads, a.head_dim, a.batch_windows,
              a.region ? "_shift" : "");
     ProfScope prof(pname, static_cast<cudaStream_t>(stream));
-    kern<<<grid, 128, S::kTotal, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+    kern<<<grid, kAttnThreads, S::kTotal, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;

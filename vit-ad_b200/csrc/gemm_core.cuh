@@ -53,7 +53,7 @@ __device__ __forceinline__ void tl_stamp(int slot, bool global = false) {
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         else
             t = static_cast<unsigned long long>(clock64());
-        g_timeline[static_cast<size_t>(blockIdx.x) * 64 + slot] = t;
+        g_timeline[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 64 + slot] = t;
     }
 }
 #define VITAD_TL(slot) ::vitad::tl_stamp(slot)

@@ -25,14 +25,14 @@ struct TileSched {
     int tail_w;      // BLOCK_N / tail_split (multiple of 32)
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI_WARPS>
 struct StagedSmem {
     static constexpr int kABytes = kBlockM * kBlockK * 2;
     static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarrierBytes = 512;
     static constexpr int kSlabBytes = 32 * 128;          // one epilogue warp: 32 rows x 32 fp32
-    static constexpr int kEpiBytes = 8 * kSlabBytes;
+    static constexpr int kEpiBytes = EPI_WARPS * kSlabBytes;
     static constexpr int kAvail = kSmemBudget - 1024 - kBarrierBytes - kEpiBytes;
     static constexpr int kStages = kAvail / kStageBytes > 10 ? 10 : kAvail / kStageBytes;
     static constexpr int kTotalBytes = kStages * kStageBytes + kBarrierBytes + kEpiBytes + 1024;
@@ -127,12 +127,17 @@ __device__ __forceinline__ void epilogue_unit(const Epi& epi, int row_base, int 
     __syncwarp();
 }
 
-template <int BLOCK_N, class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+// EPI_WARPS = 8 or 16 epilogue warps (2 or 4 per scheduler).  A warp may only touch TMEM lane quarter warp % 4,
+// so the EPI_WARPS / 4 warps of a quarter take the tile's 32-column units round-robin.  16 warps hide the
+// TMEM -> slab -> global latency chain of math-heavy epilogues (GELU: 2 MUFU + 12 FP32 ops per element) that 8
+// warps leave exposed; their register budget is 112 per thread.
+template <int BLOCK_N, int EPI_WARPS, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm3_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                 const __grid_constant__ CUtensorMap tma_b_tail, const TileSched sched, int K, Epi epi) {
-    using S = StagedSmem<BLOCK_N>;
+    using S = StagedSmem<BLOCK_N, EPI_WARPS>;
     constexpr int kStages = S::kStages;
+    static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "8 or 16 epilogue warps");
     static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N 128 or 256");
     constexpr uint32_t kTmemCols = tmem_cols_pow2(2 * BLOCK_N);
     constexpr int kPairM = 2 * kBlockM;
@@ -170,7 +175,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 16);  // 8 epilogue warps of both CTAs
+            mbar_init(&tmem_empty[i], 2 * EPI_WARPS);  // epilogue warps of both CTAs
         }
         fence_barrier_init();
     }
@@ -255,7 +260,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
     } else {
         const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-        const int group = (warp - 2) >> 2;  // the two groups alternate over the tile's 32-column units
+        const int group = (warp - 2) >> 2;  // the warps of a quarter alternate over the tile's 32-column units
         const uint32_t slab = smem_u32(epi_slabs + (warp - 2) * S::kSlabBytes);
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
@@ -270,7 +275,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             if (threadIdx.x == 64 && it < 8) VITAD_TL(44 + 2 * it);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-            for (int c = group * 32; c < t.w; c += 64)
+            for (int c = group * 32; c < t.w; c += 8 * EPI_WARPS)
                 epilogue_unit(epi, row_base, lane, my_ctx, t.n0 + c, taddr + c, slab);
             tc_fence_before();
             __syncwarp();
@@ -315,6 +320,7 @@ struct NoPre {};
 template <int ACT>
 struct SEpiBiasH {
     static constexpr bool kRowCtx = false;
+    static constexpr int kDefaultEpiWarps = ACT == 1 ? 16 : 8;
     using Pre = NoPre;
     using ColC = float4;
     const float* bias;
@@ -344,6 +350,7 @@ struct SEpiBiasH {
 // every element is read and written by the same thread)
 struct SEpiResidualF32 {
     static constexpr bool kRowCtx = false;
+    static constexpr int kDefaultEpiWarps = 8;
     using Pre = float4;
     using ColC = float4;
     const float* bias;
@@ -379,6 +386,7 @@ struct SEpiResidualF32 {
 //   vt[bw][h][e][pos] =  acc+bias   (V transposed, position contiguous, padded to Tpad: K-major B operand of P@V)
 struct SEpiQkv {
     static constexpr bool kRowCtx = true;
+    static constexpr int kDefaultEpiWarps = 8;
     using Pre = NoPre;
     struct ColC {
         float4 bias;
@@ -456,6 +464,7 @@ struct SEpiQkv {
 //   row = b*P + p  ->  x[b][prefix + p][col] = acc + bias[col] + pos[prefix + p][col]
 struct SEpiPatchEmbed {
     static constexpr bool kRowCtx = true;
+    static constexpr int kDefaultEpiWarps = 8;
     using Pre = float4;
     using ColC = float4;
     const float* bias;
@@ -493,6 +502,7 @@ struct SEpiPatchEmbed {
 // Plain fp32 output (+ optional bias), any N and pitch: used by tests and small projections.
 struct SEpiBiasF32 {
     static constexpr bool kRowCtx = false;
+    static constexpr int kDefaultEpiWarps = 8;
     using Pre = NoPre;
     using ColC = float4;
     const float* bias;  // may be null

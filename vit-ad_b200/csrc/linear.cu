@@ -15,6 +15,7 @@
 namespace vitad {
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_use_pair;
+std::atomic<int> g_epi_warps{0};  // 0 = per-epilogue default, 8 / 16 = forced (diagnostics)
 
 // Full waves of 256 x bn tiles, then the remaining tiles cut into `split` pieces each (<= one wave of pieces).
 static TileSched make_sched(int m, int n, int bn, int clusters) {
@@ -39,9 +40,9 @@ static double sched_cost(const TileSched& s, int bn, int clusters) {
 }
 
 // CTA-pair launch with the staged epilogue (gemm_staged.cuh).
-template <int BLOCK_N, class Epi>
-static int launch_gemm_staged(const vitad_linear_args& a, const Epi& epi, cudaStream_t stream) {
-    using S = StagedSmem<BLOCK_N>;
+template <int BLOCK_N, int EPI_WARPS, class Epi>
+static int launch_gemm_staged_w(const vitad_linear_args& a, const Epi& epi, cudaStream_t stream) {
+    using S = StagedSmem<BLOCK_N, EPI_WARPS>;
     const int max_clusters = device_sm_count() / 2;
     const TileSched sched = make_sched(a.m, a.n, BLOCK_N, max_clusters);
     CUtensorMap ta, tb, tbt;
@@ -51,7 +52,7 @@ static int launch_gemm_staged(const vitad_linear_args& a, const Epi& epi, cudaSt
     if (rc) return rc;
     rc = make_tmap_f16_2d(&tbt, a.w, a.n, a.k, a.ldw, sched.tail_w / 2);
     if (rc) return rc;
-    auto kern = gemm3_tc_kernel<BLOCK_N, Epi>;
+    auto kern = gemm3_tc_kernel<BLOCK_N, EPI_WARPS, Epi>;
     static bool attr_set = false;
     if (!attr_set) {
         VITAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
@@ -59,10 +60,18 @@ static int launch_gemm_staged(const vitad_linear_args& a, const Epi& epi, cudaSt
     }
     const int tiles = sched.big_tiles + sched.tail_tiles;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
-    kern<<<2 * clusters, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, tbt, sched, a.k, epi);
+    kern<<<2 * clusters, 64 + 32 * EPI_WARPS, S::kTotalBytes, stream>>>(ta, tb, tbt, sched, a.k, epi);
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;
+}
+
+template <int BLOCK_N, class Epi>
+static int launch_gemm_staged(const vitad_linear_args& a, const Epi& epi, cudaStream_t stream) {
+    const int forced = g_epi_warps.load();
+    const int warps = forced == 8 || forced == 16 ? forced : Epi::kDefaultEpiWarps;
+    if (warps == 16) return launch_gemm_staged_w<BLOCK_N, 16>(a, epi, stream);
+    return launch_gemm_staged_w<BLOCK_N, 8>(a, epi, stream);
 }
 
 template <int BLOCK_N>
@@ -197,6 +206,9 @@ static int pick_block_n_pair(int m, int n) {
 }
 
 }  // namespace vitad
+
+// Diagnostics: force 8 or 16 epilogue warps in the CTA-pair GEMM (0 = per-epilogue default).
+extern "C" void vitad_set_epilogue_warps(int warps) { vitad::g_epi_warps.store(warps); }
 
 #ifdef VITAD_TIMELINE
 // Diagnostic builds only: point the CTA-pair GEMM's timeline stamps at a [grid][64] uint64 device buffer.

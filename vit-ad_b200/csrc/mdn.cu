@@ -29,13 +29,6 @@ constexpr float kLog2SigmaFloor = -49.82892142331043f;  // log2(1e-15): sigma = 
 constexpr float kPadLogPi = -1e30f;
 constexpr int kMdnKA = 784;  // 768 + 16: K extent of the packed operands
 
-__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-
 // Epilogue of the fused projection: per thread one token row, per tile one feature d.
 template <int KC>
 struct EpiMdn {
@@ -196,8 +189,11 @@ __global__ void __launch_bounds__(256) gmm_logpi_kernel(const float* __restrict_
                                                         const float* __restrict__ wpi, const float* __restrict__ bpi,
                                                         const float* __restrict__ gumbel, float* __restrict__ lp2,
                                                         int M, int D, int K, int n_kc, int KC, int KCV) {
-    __shared__ float xs[kPiBM][kPiBK + 1];
-    __shared__ float wsh[kPiMaxK][kPiBK + 1];
+    // k is the contiguous index of both staging arrays and is read four at a time (LDS.128): 9 shared loads per
+    // 80 FMAs.  Row pitch 36 floats: 16-byte aligned, and the 8 lanes of a quarter-warp land on 8 distinct bank groups.
+    constexpr int kPitch = kPiBK + 4;
+    __shared__ __align__(16) float xs[kPiBM][kPitch];
+    __shared__ __align__(16) float wsh[kPiMaxK][kPitch];
     __shared__ float logit[kPiBM][kPiMaxK + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int m0 = blockIdx.x * kPiBM;
@@ -206,27 +202,44 @@ __global__ void __launch_bounds__(256) gmm_logpi_kernel(const float* __restrict_
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 5; ++j) acc[i][j] = 0.f;
+    // global -> register prefetch of the next k-block overlaps the FMAs of the current one (one float4 of x and
+    // five of Wpi per thread per k-block)
+    constexpr int kQ = kPiBK / 4;  // float4 per staged row
+    const int xr = threadIdx.x / kQ, xc = (threadIdx.x % kQ) * 4;
+    float4 px, pw[5];
+    auto fetch = [&](int k0) {
+        px = (m0 + xr < M) ? *reinterpret_cast<const float4*>(x + static_cast<size_t>(m0 + xr) * ldx + k0 + xc)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int r = xr + 32 * j;  // 160 rows = 5 x 32
+            pw[j] = (r < K) ? __ldg(reinterpret_cast<const float4*>(wpi + static_cast<size_t>(r) * D + k0 + xc))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    fetch(0);
     for (int k0 = 0; k0 < D; k0 += kPiBK) {
-        for (int i = threadIdx.x; i < kPiBM * kPiBK; i += 256) {
-            const int r = i / kPiBK, c = i % kPiBK;
-            xs[r][c] = (m0 + r < M) ? x[static_cast<size_t>(m0 + r) * ldx + k0 + c] : 0.f;
-        }
-        for (int i = threadIdx.x; i < kPiMaxK * kPiBK; i += 256) {
-            const int r = i / kPiBK, c = i % kPiBK;
-            wsh[r][c] = (r < K) ? wpi[static_cast<size_t>(r) * D + k0 + c] : 0.f;
-        }
+        *reinterpret_cast<float4*>(&xs[xr][xc]) = px;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) *reinterpret_cast<float4*>(&wsh[xr + 32 * j][xc]) = pw[j];
         __syncthreads();
-#pragma unroll 8
-        for (int k = 0; k < kPiBK; ++k) {
-            float xv[4], wv[5];
+        if (k0 + kPiBK < D) fetch(k0 + kPiBK);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) xv[i] = xs[ty * 4 + i][k];
+        for (int k = 0; k < kPiBK; k += 4) {
+            float4 xv[4], wv[5];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) wv[j] = wsh[tx + 32 * j][k];
+            for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(&xs[ty * 4 + i][k]);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) wv[j] = *reinterpret_cast<const float4*>(&wsh[tx + 32 * j][k]);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 5; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+                for (int j = 0; j < 5; ++j) {
+                    acc[i][j] = fmaf(xv[i].x, wv[j].x, acc[i][j]);
+                    acc[i][j] = fmaf(xv[i].y, wv[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(xv[i].z, wv[j].z, acc[i][j]);
+                    acc[i][j] = fmaf(xv[i].w, wv[j].w, acc[i][j]);
+                }
         }
         __syncthreads();
     }
@@ -278,20 +291,31 @@ __global__ void __launch_bounds__(256) gmm_logpi_kernel(const float* __restrict_
 
 // ------------------------------------------------------------------------------- score tail
 // L[t] = mean_d LL[d][t]   (torch.mean over features, MixtureDensityNetwork.py:86-88); fixed summation order.
-__global__ void __launch_bounds__(256) gmm_mean_kernel(const float* __restrict__ ll, int ldl, float* __restrict__ L,
-                                                       int M, int D) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= M) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int d = 0;
-    for (; d + 3 < D; d += 4) {
-        s0 += ll[static_cast<size_t>(d) * ldl + t];
-        s1 += ll[static_cast<size_t>(d + 1) * ldl + t];
-        s2 += ll[static_cast<size_t>(d + 2) * ldl + t];
-        s3 += ll[static_cast<size_t>(d + 3) * ldl + t];
+// CTA = 32 tokens x 32 feature groups (1024 threads): a warp reads 128 contiguous bytes of one feature row, group g
+// sums features g, g+32, ... with 8 loads in flight, the 32 partial sums are added in group order -> bit-reproducible.
+constexpr int kMeanGroups = 32;
+__global__ void __launch_bounds__(32 * kMeanGroups) gmm_mean_kernel(const float* __restrict__ ll, int ldl,
+                                                                    float* __restrict__ L, int M, int D) {
+    __shared__ float part[kMeanGroups][33];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (t < M) {
+        int d = g;
+        for (; d + 7 * kMeanGroups < D; d += 8 * kMeanGroups) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] += ll[static_cast<size_t>(d + i * kMeanGroups) * ldl + t];
+        }
+        for (; d < D; d += kMeanGroups) s[0] += ll[static_cast<size_t>(d) * ldl + t];
     }
-    for (; d < D; ++d) s0 += ll[static_cast<size_t>(d) * ldl + t];
-    L[t] = ((s0 + s1) + (s2 + s3)) / D;
+    part[g][lane] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    __syncthreads();
+    if (g == 0 && t < M) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMeanGroups; ++i) a += part[i][lane];
+        L[t] = a / D;
+    }
 }
 
 // One CTA: batch-global max (MixtureDensityNetwork.py:90-92), prob = exp(L - max) (:93-95),
@@ -433,6 +457,8 @@ extern "C" int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, cons
     if (rc) return rc;
     VITAD_REQUIRE(x && pi_w && pi_b && gumbel && lp2, VITAD_ERR_ARG, "null pointer");
     VITAD_REQUIRE(dim % kPiBK == 0 && tokens > 0, VITAD_ERR_SHAPE, "dim %% 32 != 0 or no tokens");
+    VITAD_REQUIRE(ldx % 4 == 0 && aligned16(x) && aligned16(pi_w), VITAD_ERR_ALIGN,
+                  "log_pi: x / pi_w must be 16-byte aligned with ldx %% 4 == 0");
     int n_kc, kc, kcv;
     rc = vitad_gmm_plan(num_gaussians, &n_kc, &kc, &kcv);
     if (rc) return rc;
@@ -468,7 +494,7 @@ extern "C" int vitad_gmm_patch_loglik(const void* xaug, const void* packed, cons
     }
     if (rc) return rc;
     ProfScope prof2("gmm_mean", s);
-    gmm_mean_kernel<<<(tokens + 255) / 256, 256, 0, s>>>(ll_ws, ld_ws, L, tokens, dim);
+    gmm_mean_kernel<<<(tokens + 31) / 32, 32 * kMeanGroups, 0, s>>>(ll_ws, ld_ws, L, tokens, dim);
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;
