@@ -47,7 +47,88 @@ class _BatchSharding:
         return batch_index % self.world_size == self.rank
 
 
-class ValidatorMdn:
+class _Pipelined:
+    """Three-stream batch pipeline shared by the validators: the H2D copy of batch k+1 (copy-in stream) and the D2H
+    copy of batch k-1's scores/maps into pinned buffers (copy-out stream) overlap the kernels of batch k (current
+    stream).  The reference moves one batch at a time and synchronises 33 times per batch (ValidatorMDN.py:123-168).
+    Host tensors should be pinned (DataLoader(pin_memory=True)); pageable input still works, its copy just blocks."""
+
+    DEPTH = 2  # batches in flight
+
+    def _stream_batches(self, batches: Iterable, compute: Callable):
+        """`batches` yields (batch_index, host_or_device_images, extra).  `compute(images_dev, batch_index)` returns a
+        tuple of device tensors.  Yields (batch_index, tuple of host numpy arrays, extra) in input order."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._pinned = {}
+        s_in, s_out = self._s_in, self._s_out
+        inflight = []  # (batch_index, extra, [pinned host tensors], done event)
+
+        def stage_in(item):
+            bi, images, extra = item
+            if torch.is_tensor(images) and images.device == dev:
+                return bi, images, extra, None
+            with torch.cuda.stream(s_in):  # allocated from the copy stream's pool; record_stream() guards its reuse
+                d = torch.as_tensor(images).to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            d.record_stream(main)
+            return bi, d, extra, ev
+
+        def drain(n_keep):
+            while len(inflight) > n_keep:
+                bi, extra, host, ev, slot = inflight.pop(0)
+                ev.synchronize()
+                yield bi, tuple(h.numpy().copy() for h in host), extra
+                self._free_slots.append(slot)
+
+        self._free_slots = list(range(self.DEPTH + 1))
+        it = iter(batches)
+        nxt = next(it, None)
+        staged = stage_in(nxt) if nxt is not None else None
+        while staged is not None:
+            bi, d_img, extra, ev_in = staged
+            if ev_in is not None:
+                main.wait_event(ev_in)
+            outs = compute(d_img, bi)
+            ev_c = torch.cuda.Event()
+            ev_c.record(main)
+            nxt = next(it, None)  # enqueue the next batch's H2D while this batch computes
+            staged = stage_in(nxt) if nxt is not None else None
+            slot = self._free_slots.pop(0)
+            s_out.wait_event(ev_c)
+            host = []
+            with torch.cuda.stream(s_out):
+                for j, o in enumerate(outs):
+                    key = (slot, j, tuple(o.shape), o.dtype)
+                    buf = self._pinned.get(key)
+                    if buf is None:
+                        buf = self._pinned[key] = torch.empty(o.shape, dtype=o.dtype).pin_memory()
+                    buf.copy_(o, non_blocking=True)
+                    o.record_stream(s_out)
+                    host.append(buf)
+                ev_o = torch.cuda.Event()
+                ev_o.record(s_out)
+            inflight.append((bi, extra, host, ev_o, slot))
+            yield from drain(self.DEPTH - 1)
+        yield from drain(0)
+
+    def iter_scores(self, dataloader: Iterable):
+        """Streaming form of the valid loops: yields (batch_index, image_scores [B], pixel_scores [B,1,S,S]) as fp32
+        numpy per batch of `dataloader` ((images, pixel_labels, image_labels) tuples), pipelined as above."""
+        def mine():
+            for bi, (images, _pl, _il) in enumerate(dataloader):
+                if self.shard.mine(bi):
+                    yield bi, images, None
+
+        with torch.no_grad():
+            for bi, out, _ in self._stream_batches(mine(), self.score_batch):
+                yield bi, out[0], out[1]
+
+
+class ValidatorMdn(_Pipelined):
     """Drop-in for src/pipeline/ValidatorMDN.py:27-183 (transformer encoders)."""
 
     def __init__(self, gmm_model: list, feature_extractor, dataloader, props: dict, weights_object: list | None = None,
@@ -82,32 +163,12 @@ class ValidatorMdn:
                                           post_one_minus=True)
         return image_scores, pixel_scores
 
-    def valid_loop_transformer(self, dataloader: Iterable) -> dict:
-        model = self.gmm_model[0]
-        model.to(self.device).eval()
+    def valid_loop_transformer(self, dataloader: Iterable, keep_origs: bool = True) -> dict:
+        """ValidatorMDN.py:104-183.  `keep_origs=False` drops the copy of the input images from the result (the
+        reference returns them for its plots)."""
+        self.gmm_model[0].to(self.device).eval()
         self.feature_extractor.to(self.device).eval()
-        out_s, out_p, lab_i, lab_p, origs, index, sizes = [], [], [], [], [], [], []
-        with torch.no_grad():
-            for bi, (images, pixel_labels, image_labels) in enumerate(dataloader):
-                if not self.shard.mine(bi):
-                    continue
-                s, p = self.score_batch(images, bi)
-                out_s.append(s.cpu().numpy())
-                out_p.append(p.cpu().numpy())
-                lab_i.append(np.asarray(image_labels))
-                lab_p.append(np.asarray(pixel_labels))
-                origs.append(np.asarray(images.cpu() if torch.is_tensor(images) else images))
-                index.append(bi)
-                sizes.append(int(s.shape[0]))
-        return {
-            "image_scores": np.concatenate(out_s, axis=0),
-            "pixel_scores": np.concatenate(out_p, axis=0),
-            "image_labels": np.concatenate(lab_i, axis=0),
-            "pixel_labels": np.concatenate(lab_p, axis=0),
-            "origs": np.concatenate(origs, axis=0),
-            "batch_index": np.asarray(index),
-            "batch_sizes": np.asarray(sizes),
-        }
+        return _collect(self, self.score_batch, dataloader, self.shard, keep_origs=keep_origs)
 
     def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
         """ValidatorMDN.py:71-102 without the W&B / matplotlib side effects: returns the metric dict."""
@@ -118,22 +179,27 @@ class ValidatorMdn:
         return calc_all_metrics(result, fp_thres=self.props.get("fp_thres", 0.3), dataset_name=self.dataset_name)
 
 
-def _collect(loop_body, dataloader, shard, with_recons=False):
-    """Shared batch loop: `loop_body(images, batch_index)` → (scores, maps[, recons]) device tensors."""
+def _collect(validator, loop_body, dataloader, shard, with_recons=False, keep_origs=True):
+    """Shared batch loop: `loop_body(images, batch_index)` → (scores, maps[, recons]) device tensors, run through the
+    validator's copy/compute pipeline; returns the reference's result dictionary (fp32 numpy)."""
     acc = {k: [] for k in ("image_scores", "pixel_scores", "image_labels", "pixel_labels", "origs", "recons")}
     index, sizes = [], []
-    with torch.no_grad():
+
+    def mine():
         for bi, (images, pixel_labels, image_labels) in enumerate(dataloader):
-            if not shard.mine(bi):
-                continue
-            out = loop_body(images, bi)
-            acc["image_scores"].append(out[0].cpu().numpy())
-            acc["pixel_scores"].append(out[1].cpu().numpy())
+            if shard.mine(bi):
+                yield bi, images, (images if keep_origs else None, pixel_labels, image_labels)
+
+    with torch.no_grad():
+        for bi, out, (images, pixel_labels, image_labels) in validator._stream_batches(mine(), loop_body):
+            acc["image_scores"].append(out[0])
+            acc["pixel_scores"].append(out[1])
             if with_recons:
-                acc["recons"].append(out[2].cpu().numpy())
+                acc["recons"].append(out[2])
             acc["image_labels"].append(np.asarray(image_labels))
             acc["pixel_labels"].append(np.asarray(pixel_labels))
-            acc["origs"].append(np.asarray(images.cpu() if torch.is_tensor(images) else images))
+            if keep_origs:
+                acc["origs"].append(np.asarray(images.cpu() if torch.is_tensor(images) else images))
             index.append(bi)
             sizes.append(int(out[0].shape[0]))
     res = {k: np.concatenate(v, axis=0) for k, v in acc.items() if v}
@@ -144,7 +210,7 @@ def _collect(loop_body, dataloader, shard, with_recons=False):
 BLOCK_INDEX_DEIT = 0  # src/pipeline/ValidatorNF.py:23
 
 
-class ValidatorNF:
+class ValidatorNF(_Pipelined):
     """Drop-in for src/pipeline/ValidatorNF.py:26-164 (transformer encoders)."""
 
     def __init__(self, nf_model: list, feature_extractor, dataloader, props: dict, weights_object: list | None = None,
@@ -169,7 +235,7 @@ class ValidatorNF:
     def valid_loop_transformer_nf(self, dataloader: Iterable) -> dict:
         self.nf_model[0].to(self.device).eval()
         self.feature_extractor.to(self.device).eval()
-        return _collect(self.score_batch, dataloader, self.shard)
+        return _collect(self, self.score_batch, dataloader, self.shard)
 
     def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
         from .metrics import calc_all_metrics
@@ -178,7 +244,7 @@ class ValidatorNF:
         return calc_all_metrics(result, fp_thres=self.props.get("fp_thres", 0.3), dataset_name=self.dataset_name)
 
 
-class ValidatorRecon:
+class ValidatorRecon(_Pipelined):
     """Drop-in for src/pipeline/ValidatorRecon.py:21-136: reconstruction → per-pixel L2 map → amax."""
 
     def __init__(self, model, dataloader, props: dict, weights_object: dict | None = None,
@@ -205,7 +271,7 @@ class ValidatorRecon:
 
     def valid_loop_mse(self, dataloader: Iterable) -> dict:
         self.model.to(self.device).eval()
-        return _collect(self.score_batch, dataloader, self.shard, with_recons=True)
+        return _collect(self, self.score_batch, dataloader, self.shard, with_recons=True)
 
     def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
         from .metrics import calc_all_metrics
