@@ -41,6 +41,8 @@ uint64_t vitad_launch_count(void);
 /* GEMM-class kernels run on CTA pairs (tcgen05 cta_group::2, 256-row tiles) by default; 0 selects the
  * single-CTA 128-row kernels (kept for A/B measurements and for problems of <= 128 rows). */
 void vitad_set_cta_pair(int enable);
+/* Programmatic dependent launch between the kernels of the scoring chain (default on; 0 = plain stream order). */
+void vitad_set_pdl(int enable);
 /* Diagnostics: force 8 or 16 epilogue warps in the CTA-pair GEMM kernels (0 = per-epilogue default). */
 void vitad_set_epilogue_warps(int warps);
 /* Optional in-library profiler: CUDA events around every launch site of this library.

@@ -93,6 +93,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     const int b = bw / p.nW, widx = bw - b * p.nW;
     const int nch = (T + 15) >> 4;  // 16-key chunks that hold valid keys
 
+    griddep_launch_dependents();
+    griddep_wait();  // q/k/vt come from the preceding QKV projection; everything below may touch global memory
     // Warp 0 drives TMA and the tensor core warp-uniformly (one elected lane issues; a loop under `if (lane == 0)`
     // costs ~115 cycles per MMA in vector->uniform register moves, 1500 cycles for the 13 P.V MMAs).  The loads are
     // issued before the TMEM allocation so their L2 latency overlaps it.
@@ -445,7 +447,7 @@ extern "C" int vitad_attention_f16(const vitad_attention_args* args, void* strea
     snprintf(pname, sizeof(pname), "attention_t%d_h%d_hd%d_bw%d%s", a.tokens, a.heads, a.head_dim, a.batch_windows,
              a.region ? "_shift" : "");
     ProfScope prof(pname, static_cast<cudaStream_t>(stream));
-    kern<<<grid, kAttnThreads, S::kTotal, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+    VITAD_CUDA_OK(launch_pdl(kern, grid, dim3(kAttnThreads), S::kTotal, static_cast<cudaStream_t>(stream), tq, tk, tv, p));
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;

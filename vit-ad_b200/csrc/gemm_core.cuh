@@ -111,6 +111,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int num_k16 = K / 16;
     const int num_kb = (num_k16 + 3) / 4;
 
+    griddep_launch_dependents();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
@@ -129,6 +130,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    griddep_wait();
 
     if (warp == 0) {
         // TMA producer: warp-uniform loop, one elected lane issues.

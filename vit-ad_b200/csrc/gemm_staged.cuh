@@ -163,6 +163,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int num_k16 = K / 16;
     const int num_kb = (num_k16 + 3) / 4;
 
+    griddep_launch_dependents();
     if (threadIdx.x == 0) {
         VITAD_TL(0);
         VITAD_TLG(1);
@@ -185,6 +186,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    griddep_wait();  // operands, residuals and outputs belong to the preceding kernels up to here
     if (threadIdx.x == 0) VITAD_TL(2);
 
     if (warp == 0) {

@@ -10,6 +10,8 @@ namespace vitad {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_use_pair{1};
+std::atomic<int> g_use_pdl{1};
+bool pdl_enabled() { return g_use_pdl.load() != 0; }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -101,6 +103,7 @@ extern "C" const char* vitad_last_error(void) { return vitad::g_err; }
 extern "C" int vitad_abi_version(void) { return 1; }
 extern "C" uint64_t vitad_launch_count(void) { return vitad::g_launches.load(); }
 extern "C" void vitad_set_cta_pair(int enable) { vitad::g_use_pair.store(enable ? 1 : 0); }
+extern "C" void vitad_set_pdl(int enable) { vitad::g_use_pdl.store(enable ? 1 : 0); }
 
 // ------------------------------------------------------------------------------------ profiler
 #include <map>

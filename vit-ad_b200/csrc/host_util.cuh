@@ -42,6 +42,25 @@ int make_tmap_f16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 int make_tmap_f16_3d(CUtensorMap* map, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint64_t ld2, uint32_t box_rows, uint32_t box_cols = 64);
 
+// Launch with programmatic stream serialization (see ptx.cuh: griddep_*).  Only for kernels that call griddep_wait()
+// before touching global memory.  vitad_set_pdl(0) turns the attribute off (plain stream order).
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int device_sm_count();
 int check_device_arch();  // VITAD_OK only on compute capability 10.x
 

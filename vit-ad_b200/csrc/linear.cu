@@ -60,7 +60,8 @@ static int launch_gemm_staged_w(const vitad_linear_args& a, const Epi& epi, cuda
     }
     const int tiles = sched.big_tiles + sched.tail_tiles;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
-    kern<<<2 * clusters, 64 + 32 * EPI_WARPS, S::kTotalBytes, stream>>>(ta, tb, tbt, sched, a.k, epi);
+    VITAD_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(64 + 32 * EPI_WARPS), S::kTotalBytes, stream, ta, tb, tbt, sched,
+                             a.k, epi));
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;
@@ -123,7 +124,7 @@ static int launch_gemm(const vitad_linear_args& a, const Epi& epi, cudaStream_t 
     const int num_n = (a.n + BLOCK_N - 1) / BLOCK_N;
     const int tiles = num_m * num_n;
     const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-    kern<<<grid, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, a.m, num_n, a.k, epi);
+    VITAD_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), S::kTotalBytes, stream, ta, tb, a.m, num_n, a.k, epi));
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;

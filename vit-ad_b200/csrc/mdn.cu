@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(256) gmm_logpi_kernel(const float* __restrict_
                                                         const float* __restrict__ wpi, const float* __restrict__ bpi,
                                                         const float* __restrict__ gumbel, float* __restrict__ lp2,
                                                         int M, int D, int K, int n_kc, int KC, int KCV) {
+    griddep_launch_dependents();
+    griddep_wait();
     // k is the contiguous index of both staging arrays and is read four at a time (LDS.128): 9 shared loads per
     // 80 FMAs.  Row pitch 36 floats: 16-byte aligned, and the 8 lanes of a quarter-warp land on 8 distinct bank groups.
     constexpr int kPitch = kPiBK + 4;
@@ -296,6 +298,8 @@ __global__ void __launch_bounds__(256) gmm_logpi_kernel(const float* __restrict_
 constexpr int kMeanGroups = 32;
 __global__ void __launch_bounds__(32 * kMeanGroups) gmm_mean_kernel(const float* __restrict__ ll, int ldl,
                                                                     float* __restrict__ L, int M, int D) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ float part[kMeanGroups][33];
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int t = blockIdx.x * 32 + lane;
@@ -322,6 +326,8 @@ __global__ void __launch_bounds__(32 * kMeanGroups) gmm_mean_kernel(const float*
 // image score = 1 - min_p prob (ValidatorMDN.py:133,170).
 __global__ void __launch_bounds__(1024) gmm_finish_kernel(const float* __restrict__ L, float* __restrict__ prob,
                                                           float* __restrict__ scores, int B, int P) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ float red[32];
     __shared__ float gmax;
     const int M = B * P;
@@ -378,7 +384,7 @@ static int launch_mdn(const void* xaug, const void* wpk, const float* lp2, const
         const int tiles2 = num_m2 * D;
         const int max_clusters = device_sm_count() / 2;
         const int clusters = tiles2 < max_clusters ? tiles2 : max_clusters;
-        kern2<<<2 * clusters, kGemmThreads, SP::kTotalBytes, stream>>>(ta, tb, M, D, kMdnKA, epi);
+        VITAD_CUDA_OK(launch_pdl(kern2, dim3(2 * clusters), dim3(kGemmThreads), SP::kTotalBytes, stream, ta, tb, M, D, kMdnKA, epi));
         VITAD_CUDA_OK(cudaGetLastError());
         g_launches.fetch_add(1);
         return VITAD_OK;
@@ -392,7 +398,7 @@ static int launch_mdn(const void* xaug, const void* wpk, const float* lp2, const
     const int num_m = (M + kBlockM - 1) / kBlockM;
     const int tiles = num_m * D;
     const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-    kern<<<grid, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, M, D, kMdnKA, epi);
+    VITAD_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), S::kTotalBytes, stream, ta, tb, M, D, kMdnKA, epi));
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;
@@ -463,8 +469,9 @@ extern "C" int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, cons
     rc = vitad_gmm_plan(num_gaussians, &n_kc, &kc, &kcv);
     if (rc) return rc;
     ProfScope prof("gmm_logpi", static_cast<cudaStream_t>(stream));
-    gmm_logpi_kernel<<<(tokens + kPiBM - 1) / kPiBM, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, num_gaussians, n_kc, kc, kcv);
+    VITAD_CUDA_OK(launch_pdl(gmm_logpi_kernel, dim3((tokens + kPiBM - 1) / kPiBM), dim3(256), 0,
+                             static_cast<cudaStream_t>(stream), x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, num_gaussians,
+                             n_kc, kc, kcv));
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;
@@ -494,7 +501,7 @@ extern "C" int vitad_gmm_patch_loglik(const void* xaug, const void* packed, cons
     }
     if (rc) return rc;
     ProfScope prof2("gmm_mean", s);
-    gmm_mean_kernel<<<(tokens + 31) / 32, 32 * kMeanGroups, 0, s>>>(ll_ws, ld_ws, L, tokens, dim);
+    VITAD_CUDA_OK(launch_pdl(gmm_mean_kernel, dim3((tokens + 31) / 32), dim3(32 * kMeanGroups), 0, s, ll_ws, ld_ws, L, tokens, dim));
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;
@@ -505,7 +512,8 @@ extern "C" int vitad_gmm_finish(const float* L, float* prob, float* scores, int 
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(L && prob && scores && batch > 0 && patches > 0, VITAD_ERR_ARG, "gmm_finish args");
-    gmm_finish_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(L, prob, scores, batch, patches);
+    VITAD_CUDA_OK(launch_pdl(gmm_finish_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(stream), L, prob, scores, batch,
+                             patches));
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;

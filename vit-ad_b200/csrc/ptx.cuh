@@ -206,6 +206,14 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------- programmatic dependent launch
+// Kernels of the scoring chain are launched with programmatic stream serialization (host_util.cuh: launch_pdl):
+// every CTA calls griddep_launch_dependents() first, so the next kernel's CTAs may become resident (and run their
+// prologue: barrier init, TMEM allocation, tensor-map prefetch) while this grid drains, and griddep_wait() before
+// its first access to global memory, which returns once the preceding grid has completed and flushed.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- fast math
 __device__ __forceinline__ float ex2f(float x) {
     float y;

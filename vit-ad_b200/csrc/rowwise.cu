@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         float* __restrict__ out_f, int rows, int C, int ldx, int ldh,
                                                         int ldf, int in_tokens, int out_tokens, int skip, float eps,
                                                         int aug_ones) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -87,6 +89,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // One thread moves 8 consecutive j (two float4 loads, one 16-byte store).
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, __half* __restrict__ out, int B,
                                                        int Cin, int S, int P, size_t total8) {
+    griddep_launch_dependents();
+    griddep_wait();
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= total8) return;
     const int g = S / P;
@@ -114,6 +118,8 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
 // x[b][t][:] = tok[t][:] + pos[t][:] for the `prefix` leading tokens (cls, dist) of every image.
 __global__ void prefix_tokens_kernel(const float* __restrict__ tok, const float* __restrict__ pos,
                                      float* __restrict__ x, int B, int prefix, int T, int C) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = B * prefix * C;
     if (idx >= total) return;
@@ -146,11 +152,13 @@ extern "C" int vitad_layernorm(const float* x, const float* weight, const float*
     const int blocks = (rows + 7) / 8;
     ProfScope prof("layernorm", s);
     if (c <= 768)
-        layernorm_kernel<6><<<blocks, 256, 0, s>>>(x, weight, bias, static_cast<__half*>(out_f16), out_f32, rows, c,
-                                                  ldx, ld_f16, ld_f32, in_tokens, out_tokens, skip, eps, aug_ones);
+        VITAD_CUDA_OK(launch_pdl(layernorm_kernel<6>, dim3(blocks), dim3(256), 0, s, x, weight, bias,
+                                 static_cast<__half*>(out_f16), out_f32, rows, c, ldx, ld_f16, ld_f32, in_tokens, out_tokens,
+                                 skip, eps, aug_ones));
     else
-        layernorm_kernel<12><<<blocks, 256, 0, s>>>(x, weight, bias, static_cast<__half*>(out_f16), out_f32, rows, c,
-                                                   ldx, ld_f16, ld_f32, in_tokens, out_tokens, skip, eps, aug_ones);
+        VITAD_CUDA_OK(launch_pdl(layernorm_kernel<12>, dim3(blocks), dim3(256), 0, s, x, weight, bias,
+                                 static_cast<__half*>(out_f16), out_f32, rows, c, ldx, ld_f16, ld_f32, in_tokens, out_tokens,
+                                 skip, eps, aug_ones));
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;
@@ -167,8 +175,8 @@ extern "C" int vitad_patchify(const float* images, void* out_f16, int batch, int
     const int g = size / patch;
     const size_t total8 = static_cast<size_t>(batch) * g * g * channels * patch * patch / 8;
     const unsigned blocks = static_cast<unsigned>((total8 + 255) / 256);
-    patchify_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(images, static_cast<__half*>(out_f16), batch,
-                                                                         channels, size, patch, total8);
+    VITAD_CUDA_OK(launch_pdl(patchify_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), images,
+                             static_cast<__half*>(out_f16), batch, channels, size, patch, total8));
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;
@@ -180,8 +188,8 @@ extern "C" int vitad_prefix_tokens(const float* tokens, const float* pos, float*
     if (rc) return rc;
     VITAD_REQUIRE(tokens && pos && x && batch > 0 && prefix > 0 && prefix <= t, VITAD_ERR_ARG, "prefix tokens args");
     const int total = batch * prefix * c;
-    prefix_tokens_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(tokens, pos, x, batch,
-                                                                                            prefix, t, c);
+    VITAD_CUDA_OK(launch_pdl(prefix_tokens_kernel, dim3((total + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                             tokens, pos, x, batch, prefix, t, c));
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;

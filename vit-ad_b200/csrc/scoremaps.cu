@@ -27,6 +27,8 @@ __device__ __forceinline__ void src_index(int o, int in_size, float scale, bool 
 __global__ void __launch_bounds__(256) bilinear_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                        unsigned int* __restrict__ img_max, int N, int g, int S,
                                                        int align, int pre_one_minus, int post_one_minus) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int per_img = S * S / 4;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = blockIdx.y;
@@ -99,8 +101,8 @@ extern "C" int vitad_bilinear_up(const float* in, float* out, float* image_max, 
     if (image_max) VITAD_CUDA_OK(cudaMemsetAsync(image_max, 0, sizeof(float) * n, s));
     const int per_img = size_out * size_out / 4;
     dim3 grid((per_img + 255) / 256, n);
-    bilinear_kernel<<<grid, 256, 0, s>>>(in, out, reinterpret_cast<unsigned int*>(image_max), n, grid_in, size_out,
-                                         align_corners, pre_one_minus, post_one_minus);
+    VITAD_CUDA_OK(launch_pdl(bilinear_kernel, grid, dim3(256), 0, s, in, out, reinterpret_cast<unsigned int*>(image_max), n,
+                             grid_in, size_out, align_corners, pre_one_minus, post_one_minus));
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;

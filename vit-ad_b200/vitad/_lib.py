@@ -32,6 +32,12 @@ lib.vitad_abi_version.restype = C.c_int
 lib.vitad_launch_count.restype = C.c_uint64
 lib.vitad_set_cta_pair.argtypes = [C.c_int]
 lib.vitad_set_cta_pair.restype = None
+lib.vitad_set_pdl.argtypes = [C.c_int]
+lib.vitad_set_pdl.restype = None
+lib.vitad_set_epilogue_warps.argtypes = [C.c_int]
+lib.vitad_set_epilogue_warps.restype = None
+if os.environ.get("VITAD_PDL") == "0":  # diagnostics: plain stream order between kernels
+    lib.vitad_set_pdl(0)
 
 EPI_BIAS_F16 = 0
 EPI_BIAS_GELU_F16 = 1
