@@ -39,7 +39,8 @@ def load_peaks():
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples SM clock and throttle reasons through NVML from the benchmark thread while the GPU is busy."""
+    """Samples SM clock and throttle reasons through NVML while the GPU is busy, from a background thread: an NVML
+    query can take milliseconds, and from the launching thread it would let the GPU's queue run dry mid-measurement."""
 
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown"}
@@ -75,6 +76,25 @@ class ClockSampler:
                     self.reasons.add(name)
         except Exception:
             pass
+
+    def start(self, period_s: float = 0.02):
+        import threading
+
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                self.sample()
+                self._stop.wait(period_s)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        if getattr(self, "_thread", None) is not None:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
 
     def summary(self):
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -206,16 +226,15 @@ def run_ours(args):
         clocks = ClockSampler(local)
         launches0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        every = max(1, args.steps // 16)
         barrier()
         torch.cuda.synchronize()
+        clocks.start()
         e0.record()
         for i in range(args.steps):
             step_device(i, timed=True)
-            if i % every == every - 1:
-                clocks.sample()
         e1.record()
         torch.cuda.synchronize()
+        clocks.stop()
         barrier()
         launches = _lib.launch_count() - launches0
         ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -232,6 +251,22 @@ def run_ours(args):
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
+        # per-launch-site device times of 3 more steps through the library's event profiler (CUDA events on the launch
+        # stream around every launch site; they break programmatic-dependent-launch overlap, so these times are an
+        # upper bound of what the kernels cost inside the timed region above)
+        import ctypes as C
+        _lib.lib.vitad_profile_enable.argtypes = [C.c_int]
+        _lib.lib.vitad_profile_report.argtypes = [C.c_char_p, C.c_int]
+        _lib.lib.vitad_profile_report.restype = C.c_int
+        PSTEPS = 3
+        _lib.lib.vitad_profile_enable(1)
+        for i in range(PSTEPS):
+            step_device(i)
+        buf = C.create_string_buffer(1 << 16)
+        _lib.lib.vitad_profile_report(buf, len(buf))
+        _lib.lib.vitad_profile_enable(0)
+        sites = [ln.split() for ln in buf.value.decode().strip().split("\n") if ln and not ln.startswith("__span__")]
+
     if rank != 0:
         return
     peaks, peak_src = load_peaks()
@@ -246,6 +281,39 @@ def run_ours(args):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("gmm_fused_bytes_per_launch")
+    hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
+    rows_tok = B * 198
+
+    def site_work(name):
+        """(bound, algorithmic work per launch, unit) of a launch site; unpadded logical sizes."""
+        if name.startswith("gemm_epi"):
+            n, k = int(name.split("_n")[1].split("_")[0]), int(name.split("_k")[1].split("_")[0])
+            m = B * 196 if name.startswith("gemm_epi4") else rows_tok
+            return "tensor", 2.0 * m * n * k / 1e12, "TFLOP/s"
+        if name.startswith("attention"):
+            return "tensor", 4.0 * B * 12 * 198 * 198 * 64 / 1e12, "TFLOP/s"
+        if name == "gmm_fused":
+            return "tensor", mdn_flops / 1e12, "TFLOP/s"
+        if name == "layernorm":
+            return "hbm", rows_tok * 768 * (4 + 2) / 1e9, "GB/s"
+        if name == "gmm_mean":
+            return "hbm", (768 * B * 196 + B * 196) * 4 / 1e9, "GB/s"
+        if name == "gmm_logpi":
+            return "fp32", 2.0 * B * 196 * 768 * K / 1e12, "TFLOP/s"
+        return None, 0.0, ""
+
+    kernels = []
+    for name, cnt, us_total in sites:
+        cnt, us_total = int(cnt), float(us_total)
+        bound, work, unit = site_work(name)
+        us = us_total / cnt
+        ent = {"site": name, "launches_per_step": cnt / PSTEPS, "us_per_launch": round(us, 2)}
+        if bound:
+            ach = work / (us * 1e-6)
+            pk = peak if bound == "tensor" else (hbm_peak if bound == "hbm" else None)
+            ent.update({"bound": bound, "achieved": round(ach, 1), "unit": unit, "frac": round(ach / pk, 3) if pk else None})
+        kernels.append(ent)
+    kernels.sort(key=lambda e: -e["us_per_launch"] * e["launches_per_step"])
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -258,11 +326,12 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4 + B * 224 * 224 * 4},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "gmm fused sigma/mu projection + logsumexp (gemm_tc_kernel<224,1,EpiMdn<112>>) + feature mean",
+        "roofline": {"kernel": "gmm fused sigma/mu projection + logsumexp (gemm2_tc_kernel<208,1,EpiMdn<104>>) + feature mean",
                      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src + ", sustained bf16/fp16 dense",
                      "flops_per_launch": mdn_flops, "ms_per_launch": mdn_ms,
                      "encoder_tflops": ENC_GFLOP_PER_IMG * B * 1e9 / ((ms_step - mdn_ms) * 1e-3) / 1e12},
+        "kernels": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:
         sample = 8

@@ -37,7 +37,7 @@ def test_gmm_head_k130_matches_reference_golden(tag, stress):
     assert np.abs(prob - g[f"{tag}_prob"]).max() <= 1e-3
 
 
-@pytest.mark.parametrize("K", [100, 130, 37])
+@pytest.mark.parametrize("K", [100, 130, 37, 110])
 @pytest.mark.parametrize("B,P", [(2, 196), (1, 49), (5, 196)])
 def test_gmm_patch_loglik_matches_oracle(K, B, P):
     from oracle import vitad_oracle as O

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(_lib.lib, n), f"{n} declared in include/vitad.h but not exported"
     assert _lib.lib.vitad_abi_version() == 1
-    assert _lib.gmm_plan(100) == (1, 112, 100) and _lib.gmm_plan(130) == (2, 72, 65)
+    assert _lib.gmm_plan(100) == (1, 104, 100) and _lib.gmm_plan(110) == (1, 112, 110) and _lib.gmm_plan(130) == (2, 72, 65)
     with pytest.raises(_lib.VitadError):
         _lib.gmm_plan(500)
 

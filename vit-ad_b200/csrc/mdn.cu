@@ -412,7 +412,9 @@ extern "C" int vitad_gmm_plan(int num_gaussians, int* n_kc, int* kc, int* kcv) {
     VITAD_REQUIRE(n_kc && kc && kcv, VITAD_ERR_ARG, "null pointer");
     VITAD_REQUIRE(num_gaussians >= 1 && num_gaussians <= 144, VITAD_ERR_SHAPE,
                   "num_gaussians=%d unsupported (1..144)", num_gaussians);
-    if (num_gaussians <= 112) {
+    if (num_gaussians <= 104) {  // K = 100: 104 slots (4% padding); the tile is 256 tokens x (104 sigma | 104 mu)
+        *n_kc = 1, *kc = 104, *kcv = num_gaussians;
+    } else if (num_gaussians <= 112) {
         *n_kc = 1, *kc = 112, *kcv = num_gaussians;
     } else {
         *n_kc = 2, *kc = 72, *kcv = (num_gaussians + 1) / 2;
@@ -494,7 +496,9 @@ extern "C" int vitad_gmm_patch_loglik(const void* xaug, const void* packed, cons
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     {
         ProfScope prof("gmm_fused", s);
-        if (n_kc == 1)
+        if (n_kc == 1 && kc == 104)
+            rc = launch_mdn<104, 1>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
+        else if (n_kc == 1)
             rc = launch_mdn<112, 1>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
         else
             rc = launch_mdn<72, 2>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);

@@ -21,6 +21,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // norm can drop the prefix tokens (x[:, 2:, :], TransformerEncoder.py:168) while normalising.
 // out_h: fp16 [rows, ldh]; columns [C, C+aug_ones) are set to 1 and [C+aug_ones, ldh) to 0 when
 // aug_ones > 0 (the MDN GEMM folds its biases into two extra K columns).  out_f: fp32 [rows, ldf].
+// One warp normalises kRows rows at once: all their loads are issued before the first reduction (the kernel is
+// latency-bound: one row per warp left each SM with ~3 KB per warp in flight and needed 1.07 waves of blocks),
+// and the affine parameters are fetched once per warp.
+constexpr int kLnRows = 2;
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, __half* __restrict__ out_h,
@@ -31,32 +35,44 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     griddep_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= rows) return;
-    const int bi = warp / out_tokens;
-    const int in_row = bi * in_tokens + skip + (warp - bi * out_tokens);
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(in_row) * ldx);
+    const int row0 = warp * kLnRows;
+    if (row0 >= rows) return;
     const int nv = C >> 2;
-    float4 v[MAXV];
-    float s = 0.f;
+    float4 v[kLnRows][MAXV];
+    float s[kLnRows];
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-        const int i = lane + 32 * j;
-        if (i < nv) {
-            v[j] = xr[i];
-            s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    for (int r = 0; r < kLnRows; ++r) {
+        const int row = min(row0 + r, rows - 1);  // a clamped duplicate row is computed and not stored
+        const int bi = row / out_tokens;
+        const int in_row = bi * in_tokens + skip + (row - bi * out_tokens);
+        const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(in_row) * ldx);
+        s[r] = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int i = lane + 32 * j;
+            if (i < nv) {
+                v[r][j] = xr[i];
+                s[r] += (v[r][j].x + v[r][j].y) + (v[r][j].z + v[r][j].w);
+            }
         }
     }
-    const float mean = warp_sum(s) / C;
-    float q = 0.f;
+    float mean[kLnRows], rstd[kLnRows];
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-        const int i = lane + 32 * j;
-        if (i < nv) {
-            const float a = v[j].x - mean, bb = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
-            q += (a * a + bb * bb) + (c * c + d * d);
+    for (int r = 0; r < kLnRows; ++r) mean[r] = warp_sum(s[r]) / C;
+#pragma unroll
+    for (int r = 0; r < kLnRows; ++r) {
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int i = lane + 32 * j;
+            if (i < nv) {
+                const float a = v[r][j].x - mean[r], bb = v[r][j].y - mean[r], c = v[r][j].z - mean[r],
+                            d = v[r][j].w - mean[r];
+                q += (a * a + bb * bb) + (c * c + d * d);
+            }
         }
+        rstd[r] = rsqrtf(warp_sum(q) / C + eps);
     }
-    const float rstd = rsqrtf(warp_sum(q) / C + eps);
     const float4* wr = reinterpret_cast<const float4*>(w);
     const float4* br = reinterpret_cast<const float4*>(b);
 #pragma unroll
@@ -64,23 +80,33 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         const int i = lane + 32 * j;
         if (i < nv) {
             const float4 ww = __ldg(wr + i), bb = __ldg(br + i);
-            float4 y;
-            y.x = (v[j].x - mean) * rstd * ww.x + bb.x;
-            y.y = (v[j].y - mean) * rstd * ww.y + bb.y;
-            y.z = (v[j].z - mean) * rstd * ww.z + bb.z;
-            y.w = (v[j].w - mean) * rstd * ww.w + bb.w;
-            if (out_f) reinterpret_cast<float4*>(out_f + static_cast<size_t>(warp) * ldf)[i] = y;
-            if (out_h) {
-                uint2 u;
-                u.x = pack_h2(y.x, y.y);
-                u.y = pack_h2(y.z, y.w);
-                reinterpret_cast<uint2*>(out_h + static_cast<size_t>(warp) * ldh)[i] = u;
+#pragma unroll
+            for (int r = 0; r < kLnRows; ++r) {
+                const int row = row0 + r;
+                if (row >= rows) break;
+                float4 y;
+                y.x = (v[r][j].x - mean[r]) * rstd[r] * ww.x + bb.x;
+                y.y = (v[r][j].y - mean[r]) * rstd[r] * ww.y + bb.y;
+                y.z = (v[r][j].z - mean[r]) * rstd[r] * ww.z + bb.z;
+                y.w = (v[r][j].w - mean[r]) * rstd[r] * ww.w + bb.w;
+                if (out_f) reinterpret_cast<float4*>(out_f + static_cast<size_t>(row) * ldf)[i] = y;
+                if (out_h) {
+                    uint2 u;
+                    u.x = pack_h2(y.x, y.y);
+                    u.y = pack_h2(y.z, y.w);
+                    reinterpret_cast<uint2*>(out_h + static_cast<size_t>(row) * ldh)[i] = u;
+                }
             }
         }
     }
     if (out_h && aug_ones > 0) {
-        for (int c = C + lane; c < ldh; c += 32)
-            out_h[static_cast<size_t>(warp) * ldh + c] = to_h(c < C + aug_ones ? 1.0f : 0.0f);
+#pragma unroll
+        for (int r = 0; r < kLnRows; ++r) {
+            const int row = row0 + r;
+            if (row >= rows) break;
+            for (int c = C + lane; c < ldh; c += 32)
+                out_h[static_cast<size_t>(row) * ldh + c] = to_h(c < C + aug_ones ? 1.0f : 0.0f);
+        }
     }
 }
 
@@ -149,7 +175,7 @@ extern "C" int vitad_layernorm(const float* x, const float* weight, const float*
     VITAD_REQUIRE(in_tokens > 0 && out_tokens > 0 && skip >= 0 && skip + out_tokens <= in_tokens, VITAD_ERR_SHAPE,
                   "token remap");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int blocks = (rows + 7) / 8;
+    const int blocks = (rows + 8 * kLnRows - 1) / (8 * kLnRows);
     ProfScope prof("layernorm", s);
     if (c <= 768)
         VITAD_CUDA_OK(launch_pdl(layernorm_kernel<6>, dim3(blocks), dim3(256), 0, s, x, weight, bias,
