@@ -102,13 +102,16 @@ class _Pipelined:
             host = []
             with torch.cuda.stream(s_out):
                 for j, o in enumerate(outs):
-                    key = (slot, j, tuple(o.shape), o.dtype)
+                    # one pinned buffer per (slot, output), grown to the largest batch seen: a short last batch
+                    # (the reference's loaders do not drop it) reuses a view instead of a fresh cudaHostAlloc
+                    key = (slot, j, tuple(o.shape[1:]), o.dtype)
                     buf = self._pinned.get(key)
-                    if buf is None:
+                    if buf is None or buf.shape[0] < o.shape[0]:
                         buf = self._pinned[key] = torch.empty(o.shape, dtype=o.dtype).pin_memory()
-                    buf.copy_(o, non_blocking=True)
+                    view = buf[: o.shape[0]]
+                    view.copy_(o, non_blocking=True)
                     o.record_stream(s_out)
-                    host.append(buf)
+                    host.append(view)
                 ev_o = torch.cuda.Event()
                 ev_o.record(s_out)
             inflight.append((bi, extra, host, ev_o, slot))
@@ -232,10 +235,10 @@ class ValidatorNF(_Pipelined):
         result = self.nf_model[0].forward_tokens(embedding)
         return result.image_max, result.anomaly_score_map
 
-    def valid_loop_transformer_nf(self, dataloader: Iterable) -> dict:
+    def valid_loop_transformer_nf(self, dataloader: Iterable, keep_origs: bool = True) -> dict:
         self.nf_model[0].to(self.device).eval()
         self.feature_extractor.to(self.device).eval()
-        return _collect(self, self.score_batch, dataloader, self.shard)
+        return _collect(self, self.score_batch, dataloader, self.shard, keep_origs=keep_origs)
 
     def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
         from .metrics import calc_all_metrics
@@ -269,9 +272,9 @@ class ValidatorRecon(_Pipelined):
         amap, score = self.model.anomaly_map_and_score(output.reconstruction, images)
         return score, amap, output.reconstruction
 
-    def valid_loop_mse(self, dataloader: Iterable) -> dict:
+    def valid_loop_mse(self, dataloader: Iterable, keep_origs: bool = True) -> dict:
         self.model.to(self.device).eval()
-        return _collect(self, self.score_batch, dataloader, self.shard, with_recons=True)
+        return _collect(self, self.score_batch, dataloader, self.shard, with_recons=True, keep_origs=keep_origs)
 
     def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
         from .metrics import calc_all_metrics
