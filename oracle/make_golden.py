@@ -92,6 +92,24 @@ def case_deit():
     save("deit_b2", **out)
 
 
+def case_vit():
+    """EncoderVit.forward (timm vit_base_patch16_224, one prefix token), default and stress weights, B=2."""
+    from src.classes.transformer.TransformerEncoder import EncoderVit
+
+    out = {}
+    for tag, stress in (("default", False), ("stress", True)):
+        enc = EncoderVit(img_size=224, requires_grad=True)
+        enc.load_state_dict(W.make_vit_state_dict(seed=13, stress=stress), strict=True)
+        enc.eval()
+        x = W.synthetic_images(seed=4, batch=2)
+        with torch.no_grad():
+            o = enc(x)
+        out[f"{tag}_tokens_sub"] = sub_tokens(o.patch_embedding)
+        out[f"{tag}_token_sum"] = o.patch_embedding.sum(-1).numpy()
+        out[f"{tag}_cls"] = o.latent_space.numpy()
+    save("vit_b2", **out)
+
+
 class ListLoader:
     """Stands in for GeneralDataLoader: get_dataloader() returns an iterable of batches."""
 
@@ -223,6 +241,7 @@ def case_recon_validator():
 
 CASES = {
     "deit": case_deit,
+    "vit": case_vit,
     "gmm_validator": case_gmm_validator,
     "gmm_head_k130": case_gmm_head_k130,
     "nf_validator": case_nf_validator,

@@ -69,7 +69,11 @@ def deit_forward(sd: dict, images: Tensor, block_index: int = 0, prefix: str = "
     # non-overlapping conv == per-patch GEMM; column order (c, i, j) as in the conv weight
     patches = images.reshape(B, 3, g, ps, g, ps).permute(0, 2, 4, 1, 3, 5).reshape(B, g * g, 3 * ps * ps)
     x = patches @ w.reshape(w.shape[0], -1).t() + sd[p + "patch_embed.proj.bias"]
-    x = torch.cat((sd[p + "cls_token"].expand(B, -1, -1), sd[p + "dist_token"].expand(B, -1, -1), x), dim=1)
+    n_prefix = 2 if (p + "dist_token") in sd else 1  # DeiT distilled: cls + dist; plain ViT (EncoderVit): cls
+    if n_prefix == 2:
+        x = torch.cat((sd[p + "cls_token"].expand(B, -1, -1), sd[p + "dist_token"].expand(B, -1, -1), x), dim=1)
+    else:
+        x = torch.cat((sd[p + "cls_token"].expand(B, -1, -1), x), dim=1)
     x = x + sd[p + "pos_embed"]
     if block_index != 0:
         for i in range(block_index + 1):
@@ -79,7 +83,13 @@ def deit_forward(sd: dict, images: Tensor, block_index: int = 0, prefix: str = "
         for i in range(depth):
             x = deit_block(sd, f"{p}blocks.{i}.", x)
         x = layer_norm(x, sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6)
-    return x[:, 2:, :], x[:, 0, :]
+    return x[:, n_prefix:, :], x[:, 0, :]
+
+
+def vit_forward(sd: dict, images: Tensor):
+    """EncoderVit.forward (TransformerEncoder.py:196-208): timm vit_base_patch16_224 forward_features, cls token
+    dropped → (patch_embedding [B,196,768], cls [B,768]).  block_index is ignored by the reference class."""
+    return deit_forward(sd, images, block_index=0, prefix="vit.")
 
 
 # ----------------------------------------------------------------------------------------------

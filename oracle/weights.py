@@ -35,14 +35,17 @@ def _xavier_normal(g, shape):
     return torch.randn(shape, generator=g) * std
 
 
-def make_deit_state_dict(seed: int = 0, stress: bool = False, depth: int = 12, prefix: str = "deit.") -> dict:
-    """timm deit_base_distilled_patch16_224(pretrained=False) init (TransformerEncoder.py:134-136)."""
+def make_deit_state_dict(seed: int = 0, stress: bool = False, depth: int = 12, prefix: str = "deit.",
+                         distilled: bool = True) -> dict:
+    """timm deit_base_distilled_patch16_224(pretrained=False) init (TransformerEncoder.py:134-136); with
+    distilled=False the same for vit_base_patch16_224 (EncoderVit, :193): one prefix token, no dist_token/head_dist."""
     g = torch.Generator().manual_seed(seed)
     C, H = 768, 3072
     sd = {}
     sd["cls_token"] = torch.randn(1, 1, C, generator=g) * (0.02 if stress else 1e-6)
-    sd["pos_embed"] = _tn(g, (1, 198, C), 0.02)
-    sd["dist_token"] = _tn(g, (1, 1, C), 0.02)
+    sd["pos_embed"] = _tn(g, (1, 198 if distilled else 197, C), 0.02)
+    if distilled:
+        sd["dist_token"] = _tn(g, (1, 1, C), 0.02)
     sd["patch_embed.proj.weight"] = _kaiming_uniform(g, (C, 3, 16, 16), 3 * 256)
     sd["patch_embed.proj.bias"] = _kaiming_uniform(g, (C,), 3 * 256)
 
@@ -70,8 +73,14 @@ def make_deit_state_dict(seed: int = 0, stress: bool = False, depth: int = 12, p
         lin(b + "mlp.fc2", C, H)
     ln("norm")
     lin("head", 1000, C)
-    lin("head_dist", 1000, C)
+    if distilled:
+        lin("head_dist", 1000, C)
     return {prefix + k: v for k, v in sd.items()}
+
+
+def make_vit_state_dict(seed: int = 0, stress: bool = False) -> dict:
+    """EncoderVit's state_dict (keys `vit.*`, timm vit_base_patch16_224)."""
+    return make_deit_state_dict(seed=seed, stress=stress, prefix="vit.", distilled=False)
 
 
 def make_esvit_state_dict(seed: int = 0, stress: bool = False, prefix: str = "esvit.") -> dict:

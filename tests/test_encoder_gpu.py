@@ -102,6 +102,32 @@ def test_deit_forward_matches_reference_golden(tag, stress, block_index):
     assert (xaug[:, 768:770] == 1).all() and (xaug[:, 770:] == 0).all()
 
 
+@pytest.mark.parametrize("tag,stress", [("default", False), ("stress", True)])
+def test_vit_forward_matches_reference_golden(tag, stress):
+    """EncoderVit (197 tokens, one prefix token) through the same CUDA forward; block_index is ignored as in the
+    reference (TransformerEncoder.py:196-208); state_dict keys vit.* load strictly."""
+    from oracle import weights as W
+    from vitad.encoders import EncoderVit
+    from vitad.model_helper import get_model
+
+    g = golden("vit_b2")
+    enc = get_model("enc_vit", 224, requires_grad=True)
+    assert isinstance(enc, EncoderVit) and enc.num_embedded_patches == 196 and enc.size_patch_embedding == 768
+    enc.load_state_dict(W.make_vit_state_dict(seed=13, stress=stress), strict=True)
+    enc = enc.cuda().eval()
+    x = W.synthetic_images(seed=4, batch=2).cuda()
+    with torch.no_grad():
+        o = enc(x)
+        o7 = enc(x, block_index=7)
+    torch.cuda.synchronize()
+    tok, cls = o.patch_embedding.cpu(), o.latent_space.cpu()
+    assert tok.shape == (2, 196, 768) and cls.shape == (2, 768)
+    assert np.abs(tok[:, ::14].numpy() - g[f"{tag}_tokens_sub"]).max() <= 1.5e-2
+    assert np.sqrt(np.mean((tok[:, ::14].numpy() - g[f"{tag}_tokens_sub"]) ** 2)) <= 2.5e-3
+    assert np.abs(cls.numpy() - g[f"{tag}_cls"]).max() <= 1.5e-2
+    assert torch.equal(o7.patch_embedding.cpu(), tok)
+
+
 def test_deit_forward_matches_oracle_batch_sizes():
     """Ragged batch sizes (the reference loader has no drop_last): B=1 and B=5 against the CPU oracle."""
     from oracle import vitad_oracle as O

@@ -16,6 +16,18 @@ def deit_stress():
 
 
 @pytest.mark.parametrize("tag,stress", [("default", False), ("stress", True)])
+def test_vit_oracle_matches_reference_golden(tag, stress):
+    """EncoderVit (timm vit_base_patch16_224, one prefix token) — fixture from the reference class, oracle/make_golden.py."""
+    g = golden("vit_b2")
+    sd = W.make_vit_state_dict(seed=13, stress=stress)
+    with torch.no_grad():
+        tok, cls = O.vit_forward(sd, W.synthetic_images(seed=4, batch=2))
+    np.testing.assert_allclose(tok[:, ::14].numpy(), g[f"{tag}_tokens_sub"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(tok.sum(-1).numpy(), g[f"{tag}_token_sum"], rtol=0, atol=5e-3)
+    np.testing.assert_allclose(cls.numpy(), g[f"{tag}_cls"], rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize("tag,stress", [("default", False), ("stress", True)])
 @pytest.mark.parametrize("block_index", [0, 7])
 def test_deit_oracle_matches_reference_golden(tag, stress, block_index):
     g = golden("deit_b2")

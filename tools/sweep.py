@@ -59,7 +59,7 @@ def main():
     data = {k: (t[0].pin_memory(),) + tuple(t[1:]) for k, t in data.items()}
     # warm-up (packs weights, builds workspaces)
     name0 = cats[0][0]
-    wb = batches(*data[name0])[:1]
+    wb = batches(*data[name0])  # one whole category: full and short batches, workspaces, pinned buffers
     v_gmm.shard.world_size, v_nf.shard.world_size = 1, 1
     v_gmm.shard.rank, v_nf.shard.rank = 0, 0
     v_gmm.valid_loop_transformer(wb), v_nf.valid_loop_transformer_nf(wb)
@@ -72,11 +72,16 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    per_cat = {}
+    per_cat, loop_ms = {}, []
     for name, n in cats:
         bl = batches(*data[name])
-        per_cat[name] = (v_gmm.valid_loop_transformer(bl, keep_origs=False),
-                         v_nf.valid_loop_transformer_nf(bl, keep_origs=False), len(bl))
+        t0 = time.perf_counter()
+        rg = v_gmm.valid_loop_transformer(bl, keep_origs=False)
+        t1 = time.perf_counter()
+        rn = v_nf.valid_loop_transformer_nf(bl, keep_origs=False)
+        t2 = time.perf_counter()
+        loop_ms.append((name, n, round((t1 - t0) * 1e3, 1), round((t2 - t1) * 1e3, 1)))
+        per_cat[name] = (rg, rn, len(bl))
         n_images += n
     e1.record()
     torch.cuda.synchronize()
@@ -102,7 +107,7 @@ def main():
             "workload": "15-category MVTecAD-sized synthetic validation sweep, DeiT + GMM(100) and DeiT + NF(20 steps), batch 32",
             "n_gpus": world, "images": n_images, "heads_per_image": 2,
             "ms_scoring": float(ms.item()), "images_per_s": 2 * n_images / (float(ms.item()) * 1e-3),
-            "gather_s": t_gather, "metrics": metrics}))
+            "gather_s": t_gather, "loop_ms_gmm_nf": loop_ms, "metrics": metrics}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -74,20 +74,24 @@ class _PatchEmbed(nn.Module):
 class _DeitParams(nn.Module):
     """Parameters of timm's deit_base_distilled_patch16_224 with its random init (pretrained=False)."""
 
-    def __init__(self, img=224, patch=16, dim=768, depth=12, heads=12, hidden=3072, num_classes=1000):
+    def __init__(self, img=224, patch=16, dim=768, depth=12, heads=12, hidden=3072, num_classes=1000,
+                 distilled=True):
         super().__init__()
         self.geometry = dict(img=img, patch=patch, dim=dim, depth=depth, heads=heads, hidden=hidden)
         n_patches = (img // patch) ** 2
+        self.num_prefix = 2 if distilled else 1
         self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
-        self.pos_embed = nn.Parameter(torch.zeros(1, n_patches + 2, dim))
-        self.dist_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, n_patches + self.num_prefix, dim))
+        if distilled:
+            self.dist_token = nn.Parameter(torch.zeros(1, 1, dim))
         self.patch_embed = _PatchEmbed(dim, patch)
         self.blocks = nn.ModuleList([_Block(dim, hidden) for _ in range(depth)])
         self.norm = nn.LayerNorm(dim, eps=1e-6)
         self.head = nn.Linear(dim, num_classes)
-        self.head_dist = nn.Linear(dim, num_classes)
+        if distilled:
+            self.head_dist = nn.Linear(dim, num_classes)
+            nn.init.trunc_normal_(self.dist_token, std=0.02)
         nn.init.trunc_normal_(self.pos_embed, std=0.02)
-        nn.init.trunc_normal_(self.dist_token, std=0.02)
         nn.init.normal_(self.cls_token, std=1e-6)
         for m in self.modules():
             if isinstance(m, nn.Linear):
@@ -95,26 +99,27 @@ class _DeitParams(nn.Module):
                 nn.init.zeros_(m.bias)
 
 
-class EncoderDeit(TransformerEncoder):
-    """Drop-in for the reference EncoderDeit (TransformerEncoder.py:116-173).
+class _TimmVitEncoder(TransformerEncoder):
+    """Shared body of EncoderDeit / EncoderVit: timm's 16/224 base transformer with 2 or 1 prefix tokens, parameters
+    under the attribute the reference uses (``deit`` / ``vit``), forward = one C-ABI call (vitad_deit_forward)."""
 
-    ``requires_grad=False`` in the reference downloads ImageNet weights through timm; there is no network
-    here, so both settings start from timm's random init and the caller loads a checkpoint with
-    ``load_state_dict`` (keys ``deit.*`` as in the reference).  Parameters are always frozen: this class
-    implements the inference/scoring path only.
-    """
+    _ATTR = "deit"
+    _DISTILLED = True
 
     def __init__(self, img_size: int, requires_grad: bool = False) -> None:
         super().__init__(img_size=img_size)
         if img_size != 224:
-            raise ValueError("EncoderDeit: image size has to be 224 (position embedding), as in the reference")
-        self.deit = _DeitParams(img=img_size)
+            raise ValueError(f"{type(self).__name__}: image size has to be 224 (position embedding), as in the reference")
+        setattr(self, self._ATTR, _DeitParams(img=img_size, distilled=self._DISTILLED))
         self.size_patch_embedding = 768
         self.patch_size = 16
         self.num_embedded_patches = self.calc_num_embedded_patches()
-        for p in self.deit.parameters():
+        for p in self._params().parameters():
             p.requires_grad = False
         self._packed = None  # device-side fp16 copies + C structs, rebuilt when parameters change
+
+    def _params(self) -> _DeitParams:
+        return getattr(self, self._ATTR)
 
     # -- parameter packing -------------------------------------------------------------------------
     def _apply(self, fn, recurse=True):
@@ -126,7 +131,7 @@ class EncoderDeit(TransformerEncoder):
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def _pack(self, device):
-        d = self.deit
+        d = self._params()
         geo = d.geometry
         keep = []  # keep device tensors alive
 
@@ -152,10 +157,11 @@ class EncoderDeit(TransformerEncoder):
         w = _lib.DeitWeights()
         w.img, w.patch, w.dim, w.heads = geo["img"], geo["patch"], geo["dim"], geo["heads"]
         w.hidden, w.depth = geo["hidden"], geo["depth"]
-        w.tokens, w.prefix = d.pos_embed.shape[1], 2
+        w.tokens, w.prefix = d.pos_embed.shape[1], d.num_prefix
         w.patch_w = f16(d.patch_embed.proj.weight.reshape(geo["dim"], -1))
         w.patch_b = f32(d.patch_embed.proj.bias)
-        w.prefix_tokens = f32(torch.cat((d.cls_token, d.dist_token), dim=1).reshape(2, geo["dim"]))
+        prefix = (d.cls_token, d.dist_token) if d.num_prefix == 2 else (d.cls_token,)
+        w.prefix_tokens = f32(torch.cat(prefix, dim=1).reshape(d.num_prefix, geo["dim"]))
         w.pos = f32(d.pos_embed.reshape(-1, geo["dim"]))
         w.norm_w, w.norm_b = f32(d.norm.weight), f32(d.norm.bias)
         w.layers = C.cast(layers, C.POINTER(_lib.DeitLayer))
@@ -172,7 +178,8 @@ class EncoderDeit(TransformerEncoder):
     # -- forward -----------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, block_index: int = 0) -> TransformerEncoderOutput:
         if not x.is_cuda:
-            raise RuntimeError("EncoderDeit (vitad): CUDA input required — this implementation has no CPU path")
+            raise RuntimeError(f"{type(self).__name__} (vitad): CUDA input required — this implementation has no CPU path")
+        block_index = self._block_index(int(block_index))
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.img_size or x.shape[3] != self.img_size:
             raise ValueError(f"expected [B,3,{self.img_size},{self.img_size}] input, got {tuple(x.shape)}")
         if self._packed is None or self._packed["device"] != x.device:
@@ -190,6 +197,34 @@ class EncoderDeit(TransformerEncoder):
                                      torch.cuda.current_stream().cuda_stream))
         tokens._vitad_xaug = xaug  # fp16 GEMM operand for the MDN head (saves one conversion pass)
         return TransformerEncoderOutput(patch_embedding=tokens, latent_space=cls)
+
+
+    def _block_index(self, block_index: int) -> int:
+        return block_index
+
+
+class EncoderDeit(_TimmVitEncoder):
+    """Drop-in for the reference EncoderDeit (TransformerEncoder.py:116-173).
+
+    ``requires_grad=False`` in the reference downloads ImageNet weights through timm; there is no network
+    here, so both settings start from timm's random init and the caller loads a checkpoint with
+    ``load_state_dict`` (keys ``deit.*`` as in the reference).  Parameters are always frozen: this class
+    implements the inference/scoring path only.
+    """
+
+    _ATTR = "deit"
+    _DISTILLED = True
+
+
+class EncoderVit(_TimmVitEncoder):
+    """Drop-in for the reference EncoderVit (TransformerEncoder.py:176-208): timm vit_base_patch16_224, one prefix
+    token (197 tokens), keys ``vit.*``.  The reference's forward ignores ``block_index`` (:196-208); so does this."""
+
+    _ATTR = "vit"
+    _DISTILLED = False
+
+    def _block_index(self, block_index: int) -> int:
+        return 0
 
 
 # --------------------------------------------------------------------------------------------------

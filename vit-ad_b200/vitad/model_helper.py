@@ -7,6 +7,7 @@ from . import encoders
 
 MODEL_DICT = {
     "enc_deit": encoders.EncoderDeit,
+    "enc_vit": encoders.EncoderVit,
 }
 
 

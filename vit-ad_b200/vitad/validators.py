@@ -35,6 +35,15 @@ def _load_weights(models, weights_object, weights_base_path, weights_name):
             model.load_state_dict(torch.load(path, map_location=torch.device("cpu")))
 
 
+def _place(module, device):
+    """module.to(device).eval() without touching a module that already lives there: nn.Module.to() always walks
+    _apply(), which drops the packed fp16 weight copies the CUDA modules keep (and re-packing costs ms per call)."""
+    p = next(module.parameters(), None)
+    if p is None or p.device != device:
+        module.to(device)
+    return module.eval()
+
+
 class _BatchSharding:
     """Batch-granular round-robin sharding: batch i belongs to rank i % world_size."""
 
@@ -169,8 +178,8 @@ class ValidatorMdn(_Pipelined):
     def valid_loop_transformer(self, dataloader: Iterable, keep_origs: bool = True) -> dict:
         """ValidatorMDN.py:104-183.  `keep_origs=False` drops the copy of the input images from the result (the
         reference returns them for its plots)."""
-        self.gmm_model[0].to(self.device).eval()
-        self.feature_extractor.to(self.device).eval()
+        _place(self.gmm_model[0], self.device)
+        _place(self.feature_extractor, self.device)
         return _collect(self, self.score_batch, dataloader, self.shard, keep_origs=keep_origs)
 
     def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
@@ -236,8 +245,8 @@ class ValidatorNF(_Pipelined):
         return result.image_max, result.anomaly_score_map
 
     def valid_loop_transformer_nf(self, dataloader: Iterable, keep_origs: bool = True) -> dict:
-        self.nf_model[0].to(self.device).eval()
-        self.feature_extractor.to(self.device).eval()
+        _place(self.nf_model[0], self.device)
+        _place(self.feature_extractor, self.device)
         return _collect(self, self.score_batch, dataloader, self.shard, keep_origs=keep_origs)
 
     def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
@@ -273,7 +282,7 @@ class ValidatorRecon(_Pipelined):
         return score, amap, output.reconstruction
 
     def valid_loop_mse(self, dataloader: Iterable, keep_origs: bool = True) -> dict:
-        self.model.to(self.device).eval()
+        _place(self.model, self.device)
         return _collect(self, self.score_batch, dataloader, self.shard, with_recons=True, keep_origs=keep_origs)
 
     def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
