@@ -62,3 +62,25 @@ def test_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
     pix_ref = roc_auc_score(masks.numpy().ravel() > 0.5, ref_maps.numpy().ravel())
     pix = roc_auc_score(res["pixel_labels"].ravel() > 0.5, res["pixel_scores"].ravel())
     assert abs(pix - pix_ref) <= 5e-4, (pix, pix_ref)
+
+
+def test_device_metrics_equal_sklearn_on_validator_output():
+    """calc_all_metrics on the GPU (sort + cumulative counts) equals the reference's sklearn calls
+    (ValidationHelper.py:131-211) to 4 decimals on pixel-level data with ties (1.2 M pixels, thresholded maps)."""
+    from vitad.gpu_metrics import calc_all_metrics_device
+    from vitad.metrics import calc_all_metrics
+    from vitad.synthetic import make_category
+
+    n = 24
+    _images, labels, masks = make_category("cable", n, seed=78)
+    rng = np.random.default_rng(5)
+    maps = rng.random((n, 1, 224, 224), dtype=np.float32) * 0.5 + 0.5 * masks.numpy() * rng.random((n, 1, 224, 224), dtype=np.float32)
+    maps = np.round(maps * 512) / 512  # ties
+    scores = maps.reshape(n, -1).max(1)
+    result = {"image_scores": scores, "image_labels": labels.numpy(), "pixel_scores": maps, "pixel_labels": masks.numpy()}
+    ref = calc_all_metrics(result, fp_thres=0.3, dataset_name="x")
+    got = calc_all_metrics_device(result, fp_thres=0.3, dataset_name="x")
+    for k, v in ref.items():
+        if isinstance(v, float):
+            assert round(got[k], 4) == round(v, 4), (k, got[k], v)
+    assert set(got) == set(ref)

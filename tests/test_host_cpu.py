@@ -118,3 +118,30 @@ def test_batch_sharded_gather_world_size_2_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("seed,n,ties", [(0, 500, False), (1, 4000, True), (2, 37, True), (3, 20000, True)])
+def test_device_metrics_equal_sklearn(seed, n, ties):
+    """vitad.gpu_metrics (sort + cumulative counts, torch ops — run on the CPU here) against the sklearn calls of
+    ValidationHelper.calc_all_metrics: AUROC, PR-AUC, the FPR-limited threshold and the thresholded 'PRO' AUROC,
+    with heavy ties (quantised scores, as a thresholded anomaly map has)."""
+    import torch
+    from sklearn import metrics as skm
+
+    from vitad import gpu_metrics as G
+    from vitad.metrics import calc_threshold as sk_threshold
+
+    rng = np.random.default_rng(seed)
+    y = (rng.random(n) < 0.3).astype(np.float32)
+    s = (rng.normal(size=n) + 0.8 * y).astype(np.float32)
+    if ties:
+        s = np.round(s * 4) / 4
+    ts, ty = torch.from_numpy(s), torch.from_numpy(y)
+    assert abs(G.roc_auc_score(ts, ty) - skm.roc_auc_score(y, s)) < 1e-9
+    p, r, _ = skm.precision_recall_curve(y, s)
+    assert abs(G.pr_auc_score(ts, ty) - skm.auc(r, p)) < 1e-9
+    for fpr_t in (0.05, 0.3, 0.9):
+        thr = sk_threshold(s, y, fpr_t)
+        assert G.calc_threshold(ts, ty, fpr_t) == pytest.approx(thr, abs=0), (fpr_t, thr)
+        an = np.where(s > thr, s, 0)
+        assert abs(G.roc_auc_score(torch.from_numpy(an), ty) - skm.roc_auc_score(y, an)) < 1e-9

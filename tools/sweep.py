@@ -25,6 +25,7 @@ import torch.distributed as dist  # noqa: E402
 from oracle import weights as W  # noqa: E402  (seeded synthetic weights only)
 from vitad.encoders import EncoderDeit  # noqa: E402
 from vitad.mdn import GaussianMixtureDensityNetwork  # noqa: E402
+from vitad.gpu_metrics import calc_all_metrics_device  # noqa: E402
 from vitad.metrics import calc_all_metrics  # noqa: E402
 from vitad.nf import NormalizingFlow  # noqa: E402
 from vitad.parallel import gather_results, init_from_env  # noqa: E402
@@ -35,7 +36,8 @@ from vitad.validators import ValidatorMdn, ValidatorNF  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--categories", type=int, default=len(MVTEC_TEST_SIZES))
-    ap.add_argument("--pixel-metrics", action="store_true", help="also pixel AUROC / PRO (sklearn over all pixels, slow)")
+    ap.add_argument("--pixel-metrics", action="store_true", help="also pixel AUROC / PRO over all pixels")
+    ap.add_argument("--sklearn", action="store_true", help="metrics through sklearn on the host instead of vitad.gpu_metrics")
     args = ap.parse_args()
     rank, world, local = init_from_env()
     torch.cuda.set_device(local)
@@ -95,19 +97,21 @@ def main():
         dist.barrier()
     t_gather = time.perf_counter() - t0
     if rank == 0:
+        t_m0 = time.perf_counter()
         metrics = {}
         for name, (rg, rn) in results.items():
             for tag, r in (("gmm", rg), ("nf", rn)):
                 if not args.pixel_metrics:
                     r = {k: v for k, v in r.items() if not k.startswith("pixel")}
                     r["pixel_labels"], r["pixel_scores"] = np.zeros(1), np.zeros(1)
-                m = calc_all_metrics(r, fp_thres=0.3, dataset_name=name)
+                m = (calc_all_metrics if args.sklearn else calc_all_metrics_device)(r, fp_thres=0.3, dataset_name=name)
                 metrics[f"{name}/{tag}"] = {k: round(v, 4) for k, v in m.items() if isinstance(v, float)}
         print(json.dumps({
             "workload": "15-category MVTecAD-sized synthetic validation sweep, DeiT + GMM(100) and DeiT + NF(20 steps), batch 32",
             "n_gpus": world, "images": n_images, "heads_per_image": 2,
             "ms_scoring": float(ms.item()), "images_per_s": 2 * n_images / (float(ms.item()) * 1e-3),
-            "gather_s": t_gather, "loop_ms_gmm_nf": loop_ms, "metrics": metrics}))
+            "gather_s": t_gather, "metrics_s": time.perf_counter() - t_m0,
+            "metrics_impl": "sklearn" if args.sklearn else "vitad.gpu_metrics", "loop_ms_gmm_nf": loop_ms, "metrics": metrics}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -44,6 +44,16 @@ def _place(module, device):
     return module.eval()
 
 
+def _metrics(result: dict, fp_thres: float, dataset_name: str, on_device: bool) -> dict:
+    if on_device:
+        from .gpu_metrics import calc_all_metrics_device
+
+        return calc_all_metrics_device(result, fp_thres=fp_thres, dataset_name=dataset_name)
+    from .metrics import calc_all_metrics
+
+    return calc_all_metrics(result, fp_thres=fp_thres, dataset_name=dataset_name)
+
+
 class _BatchSharding:
     """Batch-granular round-robin sharding: batch i belongs to rank i % world_size."""
 
@@ -182,13 +192,12 @@ class ValidatorMdn(_Pipelined):
         _place(self.feature_extractor, self.device)
         return _collect(self, self.score_batch, dataloader, self.shard, keep_origs=keep_origs)
 
-    def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
-        """ValidatorMDN.py:71-102 without the W&B / matplotlib side effects: returns the metric dict."""
-        from .metrics import calc_all_metrics
-
+    def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True, on_device: bool = True) -> dict:
+        """ValidatorMDN.py:71-102 without the W&B / matplotlib side effects: returns the metric dict
+        (`on_device`: sort-based metrics on the GPU, vitad.gpu_metrics; False: the reference's sklearn calls)."""
         loader = self.dataloader.get_dataloader(centering=centering)
         result = self.valid_loop_transformer(loader)
-        return calc_all_metrics(result, fp_thres=self.props.get("fp_thres", 0.3), dataset_name=self.dataset_name)
+        return _metrics(result, self.props.get("fp_thres", 0.3), self.dataset_name, on_device)
 
 
 def _collect(validator, loop_body, dataloader, shard, with_recons=False, keep_origs=True):
@@ -249,11 +258,9 @@ class ValidatorNF(_Pipelined):
         _place(self.feature_extractor, self.device)
         return _collect(self, self.score_batch, dataloader, self.shard, keep_origs=keep_origs)
 
-    def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
-        from .metrics import calc_all_metrics
-
+    def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True, on_device: bool = True) -> dict:
         result = self.valid_loop_transformer_nf(self.dataloader.get_dataloader(centering=centering))
-        return calc_all_metrics(result, fp_thres=self.props.get("fp_thres", 0.3), dataset_name=self.dataset_name)
+        return _metrics(result, self.props.get("fp_thres", 0.3), self.dataset_name, on_device)
 
 
 class ValidatorRecon(_Pipelined):
@@ -285,8 +292,6 @@ class ValidatorRecon(_Pipelined):
         _place(self.model, self.device)
         return _collect(self, self.score_batch, dataloader, self.shard, with_recons=True, keep_origs=keep_origs)
 
-    def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True) -> dict:
-        from .metrics import calc_all_metrics
-
+    def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True, on_device: bool = True) -> dict:
         result = self.valid_loop_mse(self.dataloader.get_dataloader(centering=centering))
-        return calc_all_metrics(result, fp_thres=self.props.get("fp_thres", 0.3), dataset_name=self.dataset_name)
+        return _metrics(result, self.props.get("fp_thres", 0.3), self.dataset_name, on_device)
