@@ -110,6 +110,20 @@ def case_vit():
     save("vit_b2", **out)
 
 
+def case_esvit_interpolate():
+    """interpolate_position_encoding of the reference on a window-7 checkpoint loaded into the window-14 model."""
+    from src.classes.transformer.SwinTransformerModule import SwinTransformer
+    from src.classes.transformer.TransformerEncoder import interpolate_position_encoding
+
+    model = SwinTransformer(patch_size=4, img_size=224, num_classes=3, window_size=14, use_dense_prediction=True)
+    delattr(model, "head")
+    out = interpolate_position_encoding(weights=W.synthetic_esvit_checkpoint(), model=model)
+    keep = {k.replace(".", "__"): v.float().numpy() for k, v in out.items()
+            if ("relative_position" in k and (k.startswith("layers.0.blocks.1") or k.startswith("layers.2.blocks.0")
+                                              or k.startswith("layers.3.blocks.1")))}
+    save("esvit_interpolate", **keep)
+
+
 class ListLoader:
     """Stands in for GeneralDataLoader: get_dataloader() returns an iterable of batches."""
 
@@ -242,6 +256,7 @@ def case_recon_validator():
 CASES = {
     "deit": case_deit,
     "vit": case_vit,
+    "esvit_interpolate": case_esvit_interpolate,
     "gmm_validator": case_gmm_validator,
     "gmm_head_k130": case_gmm_head_k130,
     "nf_validator": case_nf_validator,

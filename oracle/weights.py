@@ -214,3 +214,18 @@ def synthetic_images(seed: int, batch: int, size: int = 224) -> torch.Tensor:
     """fp32 NCHW in [0,1] — the loader's ToTensor contract (GeneralDataset.py:38-59)."""
     g = torch.Generator().manual_seed(1000 + seed)
     return torch.rand(batch, 3, size, size, generator=g)
+
+
+def synthetic_esvit_checkpoint(seed: int = 61):
+    """A `student` state dict as an EsViT checkpoint trained with window 7 would hold it (tables 169 x nH, index
+    49 x 49 in the first three stages): the case interpolate_position_encoding (TransformerEncoder.py:276-350) exists for."""
+    sd = {k[len("esvit."):]: v.clone() for k, v in make_esvit_state_dict(seed=seed, stress=True).items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    from oracle.vitad_oracle import swin_relative_position_index
+
+    for k in list(sd):
+        if k.endswith("relative_position_bias_table") and sd[k].shape[0] == 729:
+            sd[k] = torch.randn(169, sd[k].shape[1], generator=g) * 0.02
+        if k.endswith("relative_position_index") and sd[k].shape[0] == 196:
+            sd[k] = swin_relative_position_index(7)
+    return {k: v for k, v in sd.items() if not k.startswith("head")}

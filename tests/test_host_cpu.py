@@ -145,3 +145,26 @@ def test_device_metrics_equal_sklearn(seed, n, ties):
         assert G.calc_threshold(ts, ty, fpr_t) == pytest.approx(thr, abs=0), (fpr_t, thr)
         an = np.where(s > thr, s, 0)
         assert abs(G.roc_auc_score(torch.from_numpy(an), ty) - skm.roc_auc_score(y, an)) < 1e-9
+
+
+def test_esvit_checkpoint_position_encoding_interpolation():
+    """EncoderEsVit.load_student_weights = the reference's checkpoint path
+    (TransformerEncoder.py:248-263, interpolate_position_encoding :276-350).  A window-7 'student' checkpoint is
+    loaded into the window-14 model; the resized tables / indices equal the reference function's output
+    (fixture from oracle/make_golden.py case esvit_interpolate)."""
+    from oracle import weights as W
+    from vitad.encoders import EncoderEsVit, interpolate_position_encoding
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "esvit_interpolate.npz"))
+    enc = EncoderEsVit(224, requires_grad=True)
+    delattr(enc.esvit, "head")
+    ckpt = W.synthetic_esvit_checkpoint()
+    out = interpolate_position_encoding(weights=ckpt, model=enc.esvit)
+    assert len(g.files) >= 6
+    for key in g.files:
+        k = key.replace("__", ".")
+        np.testing.assert_allclose(out[k].float().numpy(), g[key], rtol=0, atol=1e-6, err_msg=k)
+    enc.load_student_weights(ckpt)  # strict load succeeds with the adapted shapes
+    sd = enc.esvit.state_dict()
+    assert sd["layers.0.blocks.0.attn.relative_position_bias_table"].shape == (729, 3)
+    assert sd["layers.0.blocks.0.attn.relative_position_index"].dtype == torch.int64

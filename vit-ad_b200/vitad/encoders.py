@@ -246,6 +246,40 @@ def _relative_position_index(ws: int) -> torch.Tensor:
     return rel.sum(-1)
 
 
+def interpolate_position_encoding(weights: dict, model: nn.Module) -> dict:
+    """TransformerEncoder.py:276-350 (from microsoft/esvit): adapt a checkpoint whose window / image size differs
+    from the model's — relative-position bias tables are resized bicubically over their (2w-1)x(2w-1) grid, the
+    relative-position index buffers by nearest neighbour, an absolute position embedding bicubically over its
+    token grid.  Entries with matching shapes (and everything else) pass through; a head-count mismatch is
+    reported and passed through unchanged, as in the reference."""
+    model_dict = model.state_dict()
+    out = {}
+    for k, v in weights.items():
+        cur = model_dict.get(k)
+        if cur is not None and v.size() != cur.size():
+            if "relative_position_bias_table" in k:
+                (l1, nh1), (l2, nh2) = v.size(), cur.size()
+                if nh1 != nh2:
+                    print(f"Error in loading {k}, passing")
+                elif l1 != l2:
+                    s1, s2 = int(l1 ** 0.5), int(l2 ** 0.5)
+                    r = torch.nn.functional.interpolate(v.permute(1, 0).view(1, nh1, s1, s1), size=(s2, s2), mode="bicubic")
+                    v = r.view(nh2, l2).permute(1, 0)
+            elif "relative_position_index" in k:
+                (l1, h1), (l2, h2) = v.size(), cur.size()
+                v = torch.nn.functional.interpolate(v.view(1, 1, l1, h1).float(), size=(l2, h2), mode="nearest").view(l2, h2)
+            elif "absolute_pos_embed" in k:
+                (_, l1, c1), (_, l2, c2) = v.size(), cur.size()
+                if c1 != c2:
+                    print(f"Error in loading {k}, passing")
+                elif l1 != l2:
+                    s1, s2 = int(l1 ** 0.5), int(l2 ** 0.5)
+                    r = torch.nn.functional.interpolate(v.reshape(-1, s1, s1, c1).permute(0, 3, 1, 2), size=(s2, s2), mode="bicubic")
+                    v = r.permute(0, 2, 3, 1).flatten(1, 2)
+        out[k] = v
+    return out
+
+
 class _WinAttn(nn.Module):
     def __init__(self, dim, ws, heads):
         super().__init__()
@@ -339,8 +373,8 @@ class EncoderEsVit(TransformerEncoder):
     """Drop-in for the reference EncoderEsVit (TransformerEncoder.py:211-273): vendored Swin-T, window 14.
 
     `requires_grad=False` loads the EsViT student checkpoint from the reference's relative path when that file
-    exists with matching shapes (position-encoding interpolation, :276-350, is not implemented — DESIGN.md §8);
-    without the file the random init is kept and a notice is printed (the reference would raise).  Forward runs
+    exists, through `interpolate_position_encoding` (:276-350) like the reference; without the file the random
+    init is kept and a notice is printed (the reference would raise).  Forward runs
     in inference mode: the reference leaves DropPath(0.1) active during MDN/NF validation, which makes its
     features random; that accident is deliberately not reproduced.
     """
@@ -360,7 +394,7 @@ class EncoderEsVit(TransformerEncoder):
                 student = torch.load(ESVIT_CHECKPOINT, map_location="cpu")["student"]
                 weights = {k[7:]: v for k, v in student.items() if not k.startswith("module.head")}
                 delattr(self.esvit, "head")
-                self.esvit.load_state_dict(weights)
+                self.load_student_weights(weights)
             else:
                 print(f"EncoderEsVit (vitad): {ESVIT_CHECKPOINT} not found, keeping the random initialisation")
         for p in self.esvit.parameters():
@@ -370,6 +404,16 @@ class EncoderEsVit(TransformerEncoder):
     def _apply(self, fn, recurse=True):
         self._packed = None
         return super()._apply(fn, recurse)
+
+    def load_student_weights(self, weights: dict) -> None:
+        """The reference's checkpoint path (TransformerEncoder.py:248-263): `student` weights with the `module.`
+        prefix stripped and the head dropped, adapted by interpolate_position_encoding, loaded into `self.esvit`."""
+        adapted = interpolate_position_encoding(weights=weights, model=self.esvit)
+        fixed = {}
+        for k, v in adapted.items():  # the nearest-neighbour resize yields float indices; buffers are int64
+            fixed[k] = v.long() if "relative_position_index" in k else v
+        self.esvit.load_state_dict(fixed)
+        self._packed = None
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         self._packed = None
