@@ -114,6 +114,8 @@ int vitad_layernorm(const float* x, const float* weight, const float* bias, void
                     int rows, int c, int ldx, int ld_f16, int ld_f32, int in_tokens, int out_tokens, int skip,
                     float eps, int aug_ones, void* stream);
 int vitad_patchify(const float* images, void* out_f16, int batch, int channels, int size, int patch, void* stream);
+/* Same from uint8 pixels: value = u / 255 (torchvision ToTensor, GeneralDataset.py:46-53) before the fp16 rounding. */
+int vitad_patchify_u8(const uint8_t* images, void* out_f16, int batch, int channels, int size, int patch, void* stream);
 int vitad_prefix_tokens(const float* tokens, const float* pos, float* x, int batch, int prefix, int t, int c,
                         void* stream);
 
@@ -173,6 +175,10 @@ size_t vitad_deit_workspace_bytes(const vitad_deit_weights* w, int batch);
 int vitad_deit_forward(const vitad_deit_weights* w, const float* images, int batch, int block_index, void* workspace,
                        size_t workspace_bytes, float* out_tokens, float* out_cls, void* out_xaug, int ld_xaug,
                        void* stream);
+/* Same forward from uint8 images [B,3,S,S] (the /255 of ToTensor is folded into the patch gather). */
+int vitad_deit_forward_u8(const vitad_deit_weights* w, const uint8_t* images, int batch, int block_index, void* workspace,
+                          size_t workspace_bytes, float* out_tokens, float* out_cls, void* out_xaug, int ld_xaug,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Whole EsViT Swin-T encoder forward = EncoderEsVit.forward (TransformerEncoder.py:269-273) =

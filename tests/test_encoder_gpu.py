@@ -128,6 +128,23 @@ def test_vit_forward_matches_reference_golden(tag, stress):
     assert torch.equal(o7.patch_embedding.cpu(), tok)
 
 
+def test_deit_forward_from_uint8_images_equals_float_path():
+    """uint8 pixels in, /255 (ToTensor, GeneralDataset.py:46-53) folded into the patch gather — the
+    result is bit-identical to feeding the fp32 tensor ToTensor would have produced."""
+    from oracle import weights as W
+    from vitad.encoders import EncoderDeit
+
+    enc = EncoderDeit(224)
+    enc.load_state_dict(W.make_deit_state_dict(seed=11, stress=True))
+    enc = enc.cuda().eval()
+    u8 = torch.randint(0, 256, (3, 3, 224, 224), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        a = enc(u8.cuda())
+        b = enc((u8.float() / 255.0).cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(a.patch_embedding, b.patch_embedding) and torch.equal(a.latent_space, b.latent_space)
+
+
 def test_deit_forward_matches_oracle_batch_sizes():
     """Ragged batch sizes (the reference loader has no drop_last): B=1 and B=5 against the CPU oracle."""
     from oracle import vitad_oracle as O

@@ -8,6 +8,7 @@
 extern "C" int vitad_layernorm(const float*, const float*, const float*, void*, float*, int, int, int, int, int, int,
                                int, int, float, int, void*);
 extern "C" int vitad_patchify(const float*, void*, int, int, int, int, void*);
+extern "C" int vitad_patchify_u8(const uint8_t*, void*, int, int, int, int, void*);
 extern "C" int vitad_prefix_tokens(const float*, const float*, float*, int, int, int, int, void*);
 
 namespace {
@@ -52,9 +53,27 @@ extern "C" size_t vitad_deit_workspace_bytes(const vitad_deit_weights* w, int ba
     return carve_ws(*w, batch, nullptr).total;
 }
 
+static int deit_forward_impl(const vitad_deit_weights* wp, const void* images, bool images_u8, int batch, int block_index,
+                             void* workspace, size_t workspace_bytes, float* out_tokens, float* out_cls, void* out_xaug,
+                             int ld_xaug, void* stream);
+
 extern "C" int vitad_deit_forward(const vitad_deit_weights* wp, const float* images, int batch, int block_index,
                                   void* workspace, size_t workspace_bytes, float* out_tokens, float* out_cls,
                                   void* out_xaug, int ld_xaug, void* stream) {
+    return deit_forward_impl(wp, images, false, batch, block_index, workspace, workspace_bytes, out_tokens, out_cls,
+                             out_xaug, ld_xaug, stream);
+}
+
+extern "C" int vitad_deit_forward_u8(const vitad_deit_weights* wp, const uint8_t* images, int batch, int block_index,
+                                     void* workspace, size_t workspace_bytes, float* out_tokens, float* out_cls,
+                                     void* out_xaug, int ld_xaug, void* stream) {
+    return deit_forward_impl(wp, images, true, batch, block_index, workspace, workspace_bytes, out_tokens, out_cls,
+                             out_xaug, ld_xaug, stream);
+}
+
+static int deit_forward_impl(const vitad_deit_weights* wp, const void* images, bool images_u8, int batch, int block_index,
+                             void* workspace, size_t workspace_bytes, float* out_tokens, float* out_cls, void* out_xaug,
+                             int ld_xaug, void* stream) {
     using namespace vitad;
     int rc = check_device_arch();
     if (rc) return rc;
@@ -77,7 +96,11 @@ extern "C" int vitad_deit_forward(const vitad_deit_weights* wp, const float* ima
 
     // patch embedding: gather patches -> GEMM with (+bias +pos_embed) epilogue into x[:, prefix:, :]
     VITAD_CUDA_OK(cudaMemsetAsync(ws.vt, 0, ws.vt_bytes, s));
-    if ((rc = vitad_patchify(images, ws.patches, batch, 3, w.img, w.patch, s))) return rc;
+    if (images_u8)
+        rc = vitad_patchify_u8(static_cast<const uint8_t*>(images), ws.patches, batch, 3, w.img, w.patch, s);
+    else
+        rc = vitad_patchify(static_cast<const float*>(images), ws.patches, batch, 3, w.img, w.patch, s);
+    if (rc) return rc;
     vitad_linear_args a;
     memset(&a, 0, sizeof(a));
     a.a = ws.patches, a.w = w.patch_w, a.bias = w.patch_b;

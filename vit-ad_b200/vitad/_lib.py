@@ -130,6 +130,10 @@ lib.vitad_deit_workspace_bytes.argtypes = [C.POINTER(DeitWeights), _i]
 lib.vitad_deit_workspace_bytes.restype = _sz
 lib.vitad_deit_forward.argtypes = [C.POINTER(DeitWeights), _vp, _i, _i, _vp, _sz, _vp, _vp, _vp, _i, _vp]
 lib.vitad_deit_forward.restype = _i
+lib.vitad_deit_forward_u8.argtypes = lib.vitad_deit_forward.argtypes
+lib.vitad_deit_forward_u8.restype = _i
+lib.vitad_patchify_u8.argtypes = [_vp, _vp, _i, _i, _i, _i, _vp]
+lib.vitad_patchify_u8.restype = _i
 
 # ------------------------------------------------------------------------------------ Swin / EsViT
 class SwinBlock(C.Structure):

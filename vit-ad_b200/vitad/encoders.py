@@ -185,16 +185,19 @@ class _TimmVitEncoder(TransformerEncoder):
         if self._packed is None or self._packed["device"] != x.device:
             self._pack(x.device)
         pk = self._packed
-        x = x.to(torch.float32).contiguous()
+        # uint8 images (the dataset's native pixels) are taken as they are: the /255 of ToTensor happens in the patch
+        # gather; anything else is the reference's fp32 [0,1] tensor
+        u8 = x.dtype == torch.uint8
+        x = x.contiguous() if u8 else x.to(torch.float32).contiguous()
         B = x.shape[0]
         P, Cdim = self.num_embedded_patches, self.size_patch_embedding
         ws = self._workspace(B, x.device)
         tokens = torch.empty((B, P, Cdim), device=x.device, dtype=torch.float32)
         cls = torch.empty((B, Cdim), device=x.device, dtype=torch.float32)
         xaug = torch.empty((B * P, _lib.MDN_KA), device=x.device, dtype=torch.float16)
-        check(lib.vitad_deit_forward(C.byref(pk["w"]), x.data_ptr(), B, int(block_index), ws.data_ptr(), ws.numel(),
-                                     tokens.data_ptr(), cls.data_ptr(), xaug.data_ptr(), _lib.MDN_KA,
-                                     torch.cuda.current_stream().cuda_stream))
+        fwd = lib.vitad_deit_forward_u8 if u8 else lib.vitad_deit_forward
+        check(fwd(C.byref(pk["w"]), x.data_ptr(), B, int(block_index), ws.data_ptr(), ws.numel(), tokens.data_ptr(),
+                  cls.data_ptr(), xaug.data_ptr(), _lib.MDN_KA, torch.cuda.current_stream().cuda_stream))
         tokens._vitad_xaug = xaug  # fp16 GEMM operand for the MDN head (saves one conversion pass)
         return TransformerEncoderOutput(patch_embedding=tokens, latent_space=cls)
 
