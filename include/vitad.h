@@ -43,6 +43,8 @@ uint64_t vitad_launch_count(void);
 void vitad_set_cta_pair(int enable);
 /* Programmatic dependent launch between the kernels of the scoring chain (default on; 0 = plain stream order). */
 void vitad_set_pdl(int enable);
+/* Fused GMM kernel on clusters of four CTAs sharing the token block by TMA multicast (default on; 0 = CTA pairs). */
+void vitad_set_gmm_cluster4(int enable);
 /* Diagnostics: force 8 or 16 epilogue warps in the CTA-pair GEMM kernels (0 = per-epilogue default). */
 void vitad_set_epilogue_warps(int warps);
 /* Optional in-library profiler: CUDA events around every launch site of this library.

@@ -16,11 +16,13 @@
 #include <atomic>
 
 #include "gemm_pair.cuh"
+#include "gemm_quad.cuh"
 #include "host_util.cuh"
 
 namespace vitad {
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_use_pair;
+std::atomic<int> g_gmm_quad{1};  // fused GMM kernel on 4-CTA clusters with A multicast (0: CTA pairs)
 
 constexpr float kLog2eF = 1.4426950408889634f;
 constexpr float kLn2F = 0.6931471805599453f;
@@ -369,6 +371,35 @@ static int launch_mdn(const void* xaug, const void* wpk, const float* lp2, const
     rc = make_tmap_f16_2d(&tb, wpk, static_cast<uint64_t>(D) * NKC * BN, kMdnKA, kMdnKA, BN);
     if (rc) return rc;
     Epi epi{lp2, x, ll, NKC * KC, ldx, ldl, M, 0.f, 0.f, 0.f};
+    if (g_use_pair.load() && g_gmm_quad.load() && M > 2 * kBlockM && D % 2 == 0) {
+        // clusters of four CTAs: two pairs share the A block of one 256-token tile by TMA multicast (gemm_quad.cuh)
+        using SP = PairSmem<BN>;
+        CUtensorMap ta64;
+        rc = make_tmap_f16_2d(&ta64, xaug, M, kMdnKA, kMdnKA, kBlockM / 2);
+        if (rc) return rc;
+        rc = make_tmap_f16_2d(&tb, wpk, static_cast<uint64_t>(D) * NKC * BN, kMdnKA, kMdnKA, BN / 2);
+        if (rc) return rc;
+        auto kern4 = gemm4_tc_kernel<BN, NKC, Epi>;
+        static int max_clusters4 = -1;
+        if (max_clusters4 < 0) {
+            VITAD_CUDA_OK(cudaFuncSetAttribute(kern4, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::kTotalBytes));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(device_sm_count() / 4 * 4);
+            cfg.blockDim = dim3(kGemmThreads);
+            cfg.dynamicSmemBytes = SP::kTotalBytes;
+            int n = 0;
+            VITAD_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern4, &cfg));  // 33 on a 148-SM B200
+            VITAD_REQUIRE(n > 0, VITAD_ERR_CUDA, "no 4-CTA cluster fits this device");
+            max_clusters4 = n;
+        }
+        const int num_m4 = (M + 2 * kBlockM - 1) / (2 * kBlockM);
+        const int tiles4 = num_m4 * (D / 2);
+        const int clusters = tiles4 < max_clusters4 ? tiles4 : max_clusters4;
+        VITAD_CUDA_OK(launch_pdl(kern4, dim3(4 * clusters), dim3(kGemmThreads), SP::kTotalBytes, stream, ta64, tb, M, D, kMdnKA, epi));
+        VITAD_CUDA_OK(cudaGetLastError());
+        g_launches.fetch_add(1);
+        return VITAD_OK;
+    }
     if (g_use_pair.load() && M > kBlockM) {
         // CTA pairs: rank 0 stages the sigma rows of feature d, rank 1 the mu rows (the two halves of the tile)
         using SP = PairSmem<BN>;
@@ -407,6 +438,8 @@ static int launch_mdn(const void* xaug, const void* wpk, const float* lp2, const
 }  // namespace vitad
 
 using namespace vitad;
+
+extern "C" void vitad_set_gmm_cluster4(int enable) { vitad::g_gmm_quad.store(enable ? 1 : 0); }
 
 extern "C" int vitad_gmm_plan(int num_gaussians, int* n_kc, int* kc, int* kcv) {
     VITAD_REQUIRE(n_kc && kc && kcv, VITAD_ERR_ARG, "null pointer");

@@ -36,6 +36,10 @@ lib.vitad_set_pdl.argtypes = [C.c_int]
 lib.vitad_set_pdl.restype = None
 lib.vitad_set_epilogue_warps.argtypes = [C.c_int]
 lib.vitad_set_epilogue_warps.restype = None
+lib.vitad_set_gmm_cluster4.argtypes = [C.c_int]
+lib.vitad_set_gmm_cluster4.restype = None
+if os.environ.get("VITAD_GMM_CLUSTER4") == "0":  # diagnostics: fused GMM kernel on CTA pairs
+    lib.vitad_set_gmm_cluster4(0)
 if os.environ.get("VITAD_PDL") == "0":  # diagnostics: plain stream order between kernels
     lib.vitad_set_pdl(0)
 
