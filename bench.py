@@ -340,7 +340,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4 + B * 224 * 224 * 4},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "gmm fused sigma/mu projection + logsumexp (gemm2_tc_kernel<208,1,EpiMdn<104>>) + feature mean",
+        "roofline": {"kernel": "gmm fused sigma/mu projection + logsumexp (gemm4_tc_kernel<208,1,EpiMdn<104>>, 4-CTA clusters) + feature mean",
                      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src + ", sustained bf16/fp16 dense",
                      "flops_per_launch": mdn_flops, "ms_per_launch": mdn_ms,

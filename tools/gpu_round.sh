@@ -13,6 +13,6 @@ timeout 300 python tools/gpu_profile_path.py > gpurun_out/profile_path.log 2>&1;
 if [ "${NCU:-1}" = "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 # full-set captures (second step of the target): fused GMM kernel, the four encoder GEMMs + attention + LayerNorm of one block
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm2_tc_kernel -s 1 -c 1 -o gpurun_out/prof_mdn -f python tools/prof_target.py > gpurun_out/ncu_mdn.log 2>&1; echo "ncu mdn rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm4_tc_kernel -s 1 -c 1 -o gpurun_out/prof_mdn -f python tools/prof_target.py > gpurun_out/ncu_mdn.log 2>&1; echo "ncu mdn rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:gemm3_tc_kernel|attention_kernel|layernorm_kernel" -s 60 -c 7 -o gpurun_out/prof_enc -f python tools/prof_target.py > gpurun_out/ncu_enc.log 2>&1; echo "ncu enc rc=$?"
 fi
