@@ -197,16 +197,23 @@ def run_ours(args):
         maps, _ = ops.bilinear_up(prob.view(-1, 14, 14), 224, align_corners=True, post_one_minus=True)
         return scores, maps
 
+    e2e_wall = []  # host wall time between consecutive results of the streaming loop
+
     def run_e2e(n):
         """n batches through the validator's public streaming loop: every batch is copied from pinned host memory
         (H2D, copy-in stream), scored, and its scores + maps land in host numpy arrays (D2H, copy-out stream); the
         copies of neighbouring batches overlap the kernels of the current one."""
         loader = ((host_imgs[i % NBUF], None, None) for i in range(n))
-        got = 0
+        got, acc = 0, 0.0
+        t_prev = time.perf_counter()
         for _bi, s_np, m_np in validator.iter_scores(loader):
-            assert m_np.shape[0] == s_np.shape[0]  # the caller holds both arrays on the host
+            t_now = time.perf_counter()
+            e2e_wall.append((t_now - t_prev) * 1e3)
+            t_prev = t_now
+            assert m_np.shape[0] == s_np.shape[0]  # the caller holds both arrays on the host (pinned staging views)
+            acc += float(s_np[0]) + float(m_np[-1, 0, -1, -1])  # touch first and last bytes of what arrived
             got += s_np.shape[0]
-        assert got == n * B
+        assert got == n * B and acc == acc
 
     def barrier():
         if world > 1:
@@ -244,6 +251,7 @@ def run_ours(args):
         run_e2e(3)
         barrier()
         torch.cuda.synchronize()
+        e2e_wall.clear()
         e0.record()
         run_e2e(args.steps)
         e1.record()
@@ -264,6 +272,26 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 if it >= 10:
                     lat_ms.append((time.perf_counter() - t0) * 1e3)
+            # the same step captured once in a CUDA graph (vitad.graphed.GraphedStep) and replayed
+            lat_graph_ms, graph_err = [], None
+            try:
+                from vitad.graphed import GraphedStep
+
+                def one_step(img):
+                    f1 = enc(img)
+                    prob1, s1 = head.score(f1.patch_embedding, g1)
+                    m1, _ = ops.bilinear_up(prob1.view(-1, 14, 14), 224, align_corners=True, post_one_minus=True)
+                    return s1, m1
+
+                gstep = GraphedStep(one_step, one)
+                for it in range(10 + 100):
+                    t0 = time.perf_counter()
+                    gstep(one)
+                    torch.cuda.synchronize()
+                    if it >= 10:
+                        lat_graph_ms.append((time.perf_counter() - t0) * 1e3)
+            except Exception as e:  # report, do not hide
+                graph_err = repr(e)[:200]
 
         # per-launch-site device times of 3 more steps through the library's event profiler (CUDA events on the launch
         # stream around every launch site; they break programmatic-dependent-launch overlap, so these times are an
@@ -338,7 +366,8 @@ def run_ours(args):
                    "parallelism": f"batch-sharded x{world}, weight replica per rank, no data-path collective"},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4 + B * 224 * 224 * 4},
+                "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4 + B * 224 * 224 * 4,
+                "result_interval_ms": {"p50": round(statistics.median(e2e_wall), 3), "max": round(max(e2e_wall), 3)}},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "gmm fused sigma/mu projection + logsumexp (gemm4_tc_kernel<208,1,EpiMdn<104>>, 4-CTA clusters) + feature mean",
                      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -350,6 +379,11 @@ def run_ours(args):
     if lat_ms:
         out["latency_bs1_ms"] = {"p50": round(statistics.median(lat_ms), 4), "p90": round(sorted(lat_ms)[89], 4),
                                  "iters": len(lat_ms), "how": "host wall clock around one batch-1 step + device synchronize"}
+        if lat_graph_ms:
+            out["latency_bs1_ms"]["cuda_graph_p50"] = round(statistics.median(lat_graph_ms), 4)
+            out["latency_bs1_ms"]["cuda_graph_p90"] = round(sorted(lat_graph_ms)[89], 4)
+        if graph_err:
+            out["latency_bs1_ms"]["cuda_graph_error"] = graph_err
     if world == 1 and not args.no_cpu_baseline:
         sample = 8
         ips, _, cores = cpu_reference_images_per_sec(sample, 2, 1, K)

@@ -74,9 +74,10 @@ class _Pipelined:
 
     DEPTH = 2  # batches in flight
 
-    def _stream_batches(self, batches: Iterable, compute: Callable):
+    def _stream_batches(self, batches: Iterable, compute: Callable, copy: bool = True):
         """`batches` yields (batch_index, host_or_device_images, extra).  `compute(images_dev, batch_index)` returns a
-        tuple of device tensors.  Yields (batch_index, tuple of host numpy arrays, extra) in input order."""
+        tuple of device tensors.  Yields (batch_index, tuple of host numpy arrays, extra) in input order.  With
+        copy=False the arrays are views of the pinned staging buffers, valid until the next item is requested."""
         dev = self.device
         main = torch.cuda.current_stream(dev)
         if not hasattr(self, "_s_in"):
@@ -100,7 +101,7 @@ class _Pipelined:
             while len(inflight) > n_keep:
                 bi, extra, host, ev, slot = inflight.pop(0)
                 ev.synchronize()
-                yield bi, tuple(h.numpy().copy() for h in host), extra
+                yield bi, tuple((h.numpy().copy() if copy else h.numpy()) for h in host), extra
                 self._free_slots.append(slot)
 
         self._free_slots = list(range(self.DEPTH + 1))
@@ -139,14 +140,15 @@ class _Pipelined:
 
     def iter_scores(self, dataloader: Iterable):
         """Streaming form of the valid loops: yields (batch_index, image_scores [B], pixel_scores [B,1,S,S]) as fp32
-        numpy per batch of `dataloader` ((images, pixel_labels, image_labels) tuples), pipelined as above."""
+        numpy per batch of `dataloader` ((images, pixel_labels, image_labels) tuples), pipelined as above.  The arrays
+        are views of pinned staging buffers: consume (or copy) them before asking for the next batch."""
         def mine():
             for bi, (images, _pl, _il) in enumerate(dataloader):
                 if self.shard.mine(bi):
                     yield bi, images, None
 
         with torch.no_grad():
-            for bi, out, _ in self._stream_batches(mine(), self.score_batch):
+            for bi, out, _ in self._stream_batches(mine(), self.score_batch, copy=False):
                 yield bi, out[0], out[1]
 
 
