@@ -250,6 +250,15 @@ int vitad_gmm_pack_weights(const float* sigma_w, const float* sigma_b, const flo
 int vitad_gmm_make_operand(const float* x, int ldx, void* xaug, int tokens, int dim, void* stream);
 int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, const float* pi_b, const float* gumbel, float* lp2,
                      int tokens, int dim, int num_gaussians, void* stream);
+/* The same on the tensor cores (split-fp16 operands x = xh + xl, W = Wh + Wl): pi_packed fp16 [K, 3*dim] from
+ * vitad_gmm_pack_pi (pi.weight fp32 [K, dim]); workspace of vitad_gmm_log_pi_workspace_bytes, 256-byte aligned.
+ * 2x faster, but the tensor core's truncating fp32 accumulation is ~5x less accurate than vitad_gmm_log_pi
+ * (1.1e-4 vs 1.9e-5 on the log2-probabilities, measured); the Python head uses vitad_gmm_log_pi. */
+size_t vitad_gmm_pi_packed_bytes(int dim, int num_gaussians);
+int vitad_gmm_pack_pi(const float* pi_w, int dim, int num_gaussians, void* packed, void* stream);
+size_t vitad_gmm_log_pi_workspace_bytes(int tokens, int dim, int num_gaussians);
+int vitad_gmm_log_pi_tc(const float* x, int ldx, const void* pi_packed, const float* pi_b, const float* gumbel, float* lp2,
+                        int tokens, int dim, int num_gaussians, void* workspace, size_t workspace_bytes, void* stream);
 int vitad_gmm_patch_loglik(const void* xaug, const void* packed, const float* lp2, const float* x, int ldx,
                            float* ll_ws, int ld_ws, float* L, int tokens, int dim, int num_gaussians, void* stream);
 int vitad_gmm_finish(const float* L, float* prob, float* scores, int batch, int patches, void* stream);

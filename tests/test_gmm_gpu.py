@@ -132,3 +132,42 @@ def test_recon_l2_map_matches_reference_golden():
     np.testing.assert_allclose(score.cpu().numpy(), g["image_scores"], rtol=1e-6)
     np.testing.assert_allclose(amap.cpu().numpy()[:, :, ::8, ::8], g["map_sub"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(amap.sum(dim=(1, 2, 3)).cpu().numpy(), g["map_sum"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("K,M", [(100, 6272), (130, 49), (37, 196)])
+def test_log_pi_tensor_core_path_matches_fp32_kernel(K, M):
+    """Mixing weights: the split-fp16 tensor-core GEMM (x = xh + xl, W = Wh + Wl, three exact products; an alternative
+    the library offers) against the fp32 CUDA-core kernel the head uses, both against float64.  Measured on B200:
+    the tensor core's truncating fp32 accumulation leaves ~1.1e-4 on log2(softmax(pi(x)+g)+1e-15), the fp32 kernel
+    ~1.9e-5 — which is why the head stays on the fp32 kernel."""
+    import ctypes as C
+
+    from vitad import _lib
+    from vitad._lib import check, lib
+
+    g = torch.Generator().manual_seed(K + M)
+    x = (torch.randn(M, 768, generator=g) * 1.5).cuda()
+    w = (torch.randn(K, 768, generator=g) * 0.05).cuda()
+    b = (torch.randn(K, generator=g) * 0.1).cuda()
+    gn = gumbel((M, 1, K), 99).reshape(M, K).cuda().contiguous()
+    n_kc, kc, _ = _lib.gmm_plan(K)
+    s = torch.cuda.current_stream().cuda_stream
+    ref = torch.empty(M, n_kc * kc, device="cuda")
+    check(lib.vitad_gmm_log_pi(x.data_ptr(), 768, w.data_ptr(), b.data_ptr(), gn.data_ptr(), ref.data_ptr(), M, 768, K, s))
+    packed = torch.empty(lib.vitad_gmm_pi_packed_bytes(768, K) // 2, device="cuda", dtype=torch.float16)
+    check(lib.vitad_gmm_pack_pi(w.data_ptr(), 768, K, packed.data_ptr(), s))
+    ws = torch.empty(lib.vitad_gmm_log_pi_workspace_bytes(M, 768, K), device="cuda", dtype=torch.uint8)
+    out = torch.empty_like(ref)
+    check(lib.vitad_gmm_log_pi_tc(x.data_ptr(), 768, packed.data_ptr(), b.data_ptr(), gn.data_ptr(), out.data_ptr(), M, 768,
+                                  K, ws.data_ptr(), ws.numel(), s))
+    torch.cuda.synchronize()
+    pad = ref < -1e29
+    assert torch.equal(pad, out < -1e29)
+    exact = torch.log2(torch.softmax(x.double() @ w.double().t() + b.double() + gn.double(), -1) + 1e-15).float()
+    kcv = kc if n_kc == 1 else (K + 1) // 2
+    cols = [(k // kcv) * kc + k % kcv for k in range(K)]
+    err_tc = (out[:, cols] - exact).abs().max().item()
+    err_f32 = (ref[:, cols] - exact).abs().max().item()
+    print(f"log2-probability max error vs float64: tensor-core split-fp16 {err_tc:.2e}, fp32 CUDA-core kernel {err_f32:.2e}")
+    # log2-probabilities reach -20: 1e-4 absolute is a few fp32 ulps of summation-order noise in the 768-term logits
+    assert err_f32 <= 5e-5 and err_tc <= 3e-4, (err_tc, err_f32)

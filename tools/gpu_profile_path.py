@@ -10,7 +10,7 @@ from vitad.mdn import GaussianMixtureDensityNetwork
 
 lib = _lib.lib
 lib.vitad_profile_enable.argtypes = [C.c_int]; lib.vitad_profile_report.argtypes = [C.c_char_p, C.c_int]; lib.vitad_profile_report.restype = C.c_int
-B, K = 32, int(sys.argv[1]) if len(sys.argv) > 1 else 100
+B, K = (int(sys.argv[2]) if len(sys.argv) > 2 else 32), (int(sys.argv[1]) if len(sys.argv) > 1 else 100)
 enc = EncoderDeit(224); enc.load_state_dict(W.make_deit_state_dict(11)); enc = enc.cuda().eval()
 head = GaussianMixtureDensityNetwork(768, 768, K); head.load_state_dict(W.make_mdn_state_dict(21, K)); head = head.cuda().eval()
 imgs = W.synthetic_images(1, B).cuda(); gn = torch.randn(B, 196, K, device="cuda")

@@ -293,6 +293,95 @@ __global__ void __launch_bounds__(256) gmm_logpi_kernel(const float* __restrict_
     }
 }
 
+// ---------------------------------------------------------- mixing weights on the tensor cores
+// The same projection as one fp16 GEMM with fp32-grade accuracy: x = xh + xl, W = Wh + Wl (each an fp16 value, xl and Wl
+// the rounding remainders), and  x.W ~= xh.Wh + xl.Wh + xh.Wl  — every fp16 x fp16 product is exact in the fp32
+// accumulator, the dropped xl.Wl term is 2^-22 relative.  Laid out as K' = 3 * 768:  A' = [xh | xl | xh],
+// B' = [Wh | Wh | Wl].  (A plain fp16 GEMM is not enough here: the logits enter every feature's logsumexp with the same
+// sign.)  The fp32 CUDA-core kernel above needs 88 us at batch 32 and 67 us at batch 1 (7 CTAs, serial k loop); this
+// path is an operand kernel + a 2304-deep GEMM + a per-token softmax kernel.
+__global__ void __launch_bounds__(256) gmm_pi_operand_kernel(const float* __restrict__ x, int ldx, __half* __restrict__ a3,
+                                                             int M, int D) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // one float4 of x
+    const int per_row = D >> 2;
+    if (idx >= static_cast<size_t>(M) * per_row) return;
+    const size_t t = idx / per_row;
+    const int c = static_cast<int>(idx - t * per_row) << 2;
+    const float4 v = *reinterpret_cast<const float4*>(x + t * ldx + c);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hi[j] = to_h(f[j]);
+        lo[j] = to_h(f[j] - __half2float(hi[j]));
+    }
+    __half* row = a3 + t * (3 * static_cast<size_t>(D));
+    *reinterpret_cast<uint2*>(row + c) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(row + D + c) = *reinterpret_cast<const uint2*>(lo);
+    *reinterpret_cast<uint2*>(row + 2 * D + c) = *reinterpret_cast<const uint2*>(hi);
+}
+
+// B' = [Wh | Wh | Wl] from pi.weight fp32 [K, D]
+__global__ void __launch_bounds__(256) gmm_pi_pack_kernel(const float* __restrict__ w, __half* __restrict__ b3, int K,
+                                                          int D) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * D) return;
+    const int k = idx / D, c = idx - k * D;
+    const float f = w[idx];
+    const __half hi = to_h(f);
+    const __half lo = to_h(f - __half2float(hi));
+    __half* row = b3 + static_cast<size_t>(k) * 3 * D;
+    row[c] = hi;
+    row[D + c] = hi;
+    row[2 * D + c] = lo;
+}
+
+// lp2 row of one token from its logits: + bias + gumbel, softmax, log2(. + 1e-15), chunked slot layout.  One warp per token.
+__global__ void __launch_bounds__(256) gmm_pi_softmax_kernel(const float* __restrict__ logits, int ldl,
+                                                             const float* __restrict__ bpi,
+                                                             const float* __restrict__ gumbel, float* __restrict__ lp2,
+                                                             int M, int K, int n_kc, int KC, int KCV) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int tx = threadIdx.x & 31;
+    if (t >= M) return;
+    const int ldp = n_kc * KC;
+    float z[5];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int k = tx + 32 * j;
+        z[j] = (k < K) ? logits[static_cast<size_t>(t) * ldl + k] + bpi[k] + gumbel[static_cast<size_t>(t) * K + k] : -INFINITY;
+        mx = fmaxf(mx, z[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float e[5], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        e[j] = (tx + 32 * j < K) ? expf(z[j] - mx) : 0.f;
+        sum += e[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float* dst = lp2 + static_cast<size_t>(t) * ldp;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int k = tx + 32 * j;
+        if (k < K) {
+            const int kc = k / KCV;
+            dst[kc * KC + (k - kc * KCV)] = log2f(e[j] / sum + 1e-15f);
+        }
+    }
+    for (int s = tx; s < ldp; s += 32) {
+        const int kc = s / KC, j = s - kc * KC;
+        if (j >= KCV || kc * KCV + j >= K) dst[s] = kPadLogPi;
+    }
+}
+
 // ------------------------------------------------------------------------------- score tail
 // L[t] = mean_d LL[d][t]   (torch.mean over features, MixtureDensityNetwork.py:86-88); fixed summation order.
 // CTA = 32 tokens x 32 feature groups (1024 threads): a warp reads 128 contiguous bytes of one feature row, group g
@@ -508,6 +597,66 @@ extern "C" int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, cons
                              static_cast<cudaStream_t>(stream), x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, num_gaussians,
                              n_kc, kc, kcv));
     VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+extern "C" size_t vitad_gmm_pi_packed_bytes(int dim, int num_gaussians) {
+    return static_cast<size_t>(num_gaussians) * 3 * dim * sizeof(__half);
+}
+
+extern "C" int vitad_gmm_pack_pi(const float* pi_w, int dim, int num_gaussians, void* packed, void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(pi_w && packed && dim % 16 == 0 && num_gaussians > 0, VITAD_ERR_ARG, "pack_pi arguments");
+    const int total = num_gaussians * dim;
+    gmm_pi_pack_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        pi_w, static_cast<__half*>(packed), num_gaussians, dim);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+extern "C" size_t vitad_gmm_log_pi_workspace_bytes(int tokens, int dim, int num_gaussians) {
+    const size_t a3 = (static_cast<size_t>(tokens) * 3 * dim * sizeof(__half) + 255) & ~static_cast<size_t>(255);
+    const size_t lg = static_cast<size_t>(tokens) * ((num_gaussians + 3) / 4 * 4) * sizeof(float);
+    return a3 + lg;
+}
+
+extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream);
+
+// Tensor-core form of vitad_gmm_log_pi: pi_packed from vitad_gmm_pack_pi, workspace of vitad_gmm_log_pi_workspace_bytes.
+extern "C" int vitad_gmm_log_pi_tc(const float* x, int ldx, const void* pi_packed, const float* pi_b, const float* gumbel,
+                                   float* lp2, int tokens, int dim, int num_gaussians, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(x && pi_packed && pi_b && gumbel && lp2 && workspace, VITAD_ERR_ARG, "null pointer");
+    VITAD_REQUIRE(dim % 16 == 0 && tokens > 0 && num_gaussians <= kPiMaxK, VITAD_ERR_SHAPE, "dim %% 16 != 0, no tokens or K > 160");
+    VITAD_REQUIRE(ldx % 4 == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, VITAD_ERR_ALIGN,
+                  "log_pi_tc: x 16-byte aligned with ldx %% 4 == 0, workspace 256-byte aligned");
+    VITAD_REQUIRE(workspace_bytes >= vitad_gmm_log_pi_workspace_bytes(tokens, dim, num_gaussians), VITAD_ERR_WORKSPACE,
+                  "log_pi_tc workspace too small");
+    int n_kc, kc, kcv;
+    rc = vitad_gmm_plan(num_gaussians, &n_kc, &kc, &kcv);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    __half* a3 = static_cast<__half*>(workspace);
+    const size_t a3_bytes = (static_cast<size_t>(tokens) * 3 * dim * sizeof(__half) + 255) & ~static_cast<size_t>(255);
+    float* logits = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + a3_bytes);
+    const int ldl = (num_gaussians + 3) / 4 * 4;
+    ProfScope prof("gmm_logpi", s);
+    const size_t n4 = static_cast<size_t>(tokens) * (dim / 4);
+    VITAD_CUDA_OK(launch_pdl(gmm_pi_operand_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, s, x, ldx, a3,
+                             tokens, dim));
+    g_launches.fetch_add(1);
+    vitad_linear_args la;
+    memset(&la, 0, sizeof(la));
+    la.a = a3, la.w = pi_packed, la.m = tokens, la.n = num_gaussians, la.k = 3 * dim, la.lda = 3 * dim, la.ldw = 3 * dim;
+    la.epilogue = VITAD_EPI_F32, la.out = logits, la.ldo = ldl;
+    if ((rc = vitad_linear_f16(&la, s))) return rc;
+    VITAD_CUDA_OK(launch_pdl(gmm_pi_softmax_kernel, dim3((tokens + 7) / 8), dim3(256), 0, s, static_cast<const float*>(logits), ldl,
+                             pi_b, gumbel, lp2, tokens, num_gaussians, n_kc, kc, kcv));
     g_launches.fetch_add(1);
     return VITAD_OK;
 }

@@ -173,6 +173,14 @@ lib.vitad_gmm_make_operand.argtypes = [_vp, _i, _vp, _i, _i, _vp]
 lib.vitad_gmm_make_operand.restype = _i
 lib.vitad_gmm_log_pi.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]
 lib.vitad_gmm_log_pi.restype = _i
+lib.vitad_gmm_pi_packed_bytes.argtypes = [_i, _i]
+lib.vitad_gmm_pi_packed_bytes.restype = _sz
+lib.vitad_gmm_pack_pi.argtypes = [_vp, _i, _i, _vp, _vp]
+lib.vitad_gmm_pack_pi.restype = _i
+lib.vitad_gmm_log_pi_workspace_bytes.argtypes = [_i, _i, _i]
+lib.vitad_gmm_log_pi_workspace_bytes.restype = _sz
+lib.vitad_gmm_log_pi_tc.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]
+lib.vitad_gmm_log_pi_tc.restype = _i
 lib.vitad_gmm_patch_loglik.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp]
 lib.vitad_gmm_patch_loglik.restype = _i
 lib.vitad_gmm_finish.argtypes = [_vp, _vp, _vp, _i, _i, _vp]

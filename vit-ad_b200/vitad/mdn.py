@@ -125,6 +125,10 @@ class GaussianMixtureDensityNetwork(nn.Module):
         g = gumbel.to(device=x.device, dtype=torch.float32).reshape(M, K).contiguous()
         n_kc, kc, _ = _lib.gmm_plan(K)
         lp2 = torch.empty((M, n_kc * kc), device=x.device, dtype=torch.float32)
+        # mixing weights in fp32 on the CUDA cores.  The split-fp16 tensor-core form (vitad_gmm_log_pi_tc) is 2x
+        # faster (88 -> 41 us at batch 32) but the tensor core's truncating fp32 accumulation leaves 1.1e-4 on the
+        # log2-probabilities where this kernel leaves 1.9e-5 (tests/test_gmm_gpu.py), and that error enters every
+        # feature's logsumexp with the same sign: not worth 1.5% of the step.
         check(lib.vitad_gmm_log_pi(xf.data_ptr(), xf.stride(0), pk["pi_w"].data_ptr(), pk["pi_b"].data_ptr(),
                                    g.data_ptr(), lp2.data_ptr(), M, D, K, _stream()))
         ld_ws = (M + 31) // 32 * 32
