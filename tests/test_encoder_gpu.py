@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import golden
+from helpers import golden, gumbel
 
 pytestmark = pytest.mark.gpu
 
@@ -166,3 +166,34 @@ def test_encoder_rejects_cpu_input():
 
     with pytest.raises(RuntimeError):
         EncoderDeit(224)(torch.rand(1, 3, 224, 224))
+
+
+@pytest.mark.parametrize("B", [3, 33, 64])
+def test_scoring_is_batch_invariant(B):
+    """Every per-image quantity (tokens, cls, per-patch log-likelihood) must not depend on which other images share the
+    batch: the tile schedule (full waves + cut tail, 4-CTA clusters, ragged last row block) changes with M, the
+    per-element accumulation order does not — results are bit-identical between one batch of B and single images /
+    sub-batches.  Guards the scheduling code at sizes other than the benchmark's 32."""
+    from oracle import weights as W
+    from vitad.encoders import EncoderDeit
+    from vitad.mdn import GaussianMixtureDensityNetwork
+
+    enc = EncoderDeit(224)
+    enc.load_state_dict(W.make_deit_state_dict(seed=11, stress=True))
+    head = GaussianMixtureDensityNetwork(768, 768, 100)
+    head.load_state_dict(W.make_mdn_state_dict(seed=21, num_gaussians=100, stress=True))
+    enc, head = enc.cuda().eval(), head.cuda().eval()
+    imgs = W.synthetic_images(seed=60 + B, batch=B).cuda()
+    gn = gumbel((B, 196, 100), 17).cuda()
+    with torch.no_grad():
+        full = enc(imgs)
+        L_full = head.patch_log_likelihood(full.patch_embedding, gn)
+        cut = B // 2 + 1
+        parts = [(0, 1), (1, cut), (cut, B)]
+        for lo, hi in parts:
+            sub = enc(imgs[lo:hi].contiguous())
+            assert torch.equal(sub.patch_embedding, full.patch_embedding[lo:hi]), (B, lo, hi)
+            assert torch.equal(sub.latent_space, full.latent_space[lo:hi])
+            L_sub = head.patch_log_likelihood(sub.patch_embedding, gn[lo:hi].contiguous())
+            assert torch.equal(L_sub, L_full[lo:hi]), (B, lo, hi)
+    assert torch.isfinite(L_full).all()
