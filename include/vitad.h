@@ -68,7 +68,10 @@ typedef enum vitad_epilogue {
     VITAD_EPI_QKV = 3,            /* head-major q (pre-scaled), k, transposed v             */
     VITAD_EPI_PATCH_EMBED = 4,    /* + bias + pos_embed, written behind the prefix tokens   */
     VITAD_EPI_F32 = 5,            /* out_f32 = acc (+ bias if non-null)                     */
-    VITAD_EPI_BIAS_RELU_F16 = 6   /* out_f16 = relu(acc + bias)  (FastFlow subnet, NormalizingFlow.py:61-82) */
+    VITAD_EPI_BIAS_RELU_F16 = 6,  /* out_f16 = relu(acc + bias)  (FastFlow subnet, NormalizingFlow.py:61-82) */
+    VITAD_EPI_CONVT_RELU_F16 = 7  /* ConvTranspose2d(k3,s2,p1,op1)+BN+ReLU as one GEMM (CnnDecoder.py:47-117): row =
+                                     input pixel (b,i,j) of a convt_w-wide grid, col = (phase a, phase c, channel);
+                                     out_f16 NHWC [B,2H,2W,N/4] = relu(acc + bias) scattered to pixel (2i+a, 2j+c) */
 } vitad_epilogue;
 
 typedef struct vitad_linear_args {
@@ -97,6 +100,7 @@ typedef struct vitad_linear_args {
      * SwinTransformerModule.py:360-384). */
     int head_dim, windows, win_tokens;
     const int* tok2win;
+    int convt_w;        /* CONVT_RELU_F16: width (= height) of the input pixel grid */
 } vitad_linear_args;
 
 int vitad_linear_f16(const vitad_linear_args* args, void* stream);
@@ -313,6 +317,34 @@ int vitad_bilinear_up(const float* in, float* out, float* image_max, int n, int 
                       int align_corners, int pre_one_minus, int post_one_minus, void* stream);
 int vitad_l2_map_score(const float* recon, const float* x, float* map, float* image_max, int n, int channels, int hw,
                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small CNN decoder of the reconstruction models: DecoderVanillaCNN.forward (src/classes/CnnDecoder.py:16-117) as used by
+ * AutoEncoderDeit(decoder="cnn") (TransformerAutoEncoder.py:152-194): two Linear+ReLU, four ConvTranspose2d(k3,s2,p1,op1)
+ * + BatchNorm2d (inference statistics, folded) + ReLU, and ConvTranspose2d(48->3) + BatchNorm2d + Tanh.
+ * Packed weights (vitad.autoencoders builds them from the reference's state_dict):
+ *   lin1_w fp16 [hidden, latent], lin1_b fp32;  lin2_w fp16 [grid0*grid0*chan[0], hidden] with rows in (h, w, c) order,
+ *   lin2_b fp32 in the same order;  conv_w[l] fp16 [4*chan[l+1], 4*chan[l]]: row (a, c, co) = output phase and channel,
+ *   column (di, dj, ci) = input tap and channel, BN scale folded, dead taps and padding channels zero;  conv_b[l] fp32
+ *   [4*chan[l+1]];  last_w fp32 [3][3][last_cin][3] (ky, kx, ci, co), last_b fp32 [3].
+ * chan[] are channel pitches (multiples of 32: 768, 384, 192, 96, 64 for the reference's 768..48).
+ * latent fp32 [B, latent] -> recon fp32 NCHW [B, 3, 32*grid0, 32*grid0].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct vitad_cnn_decoder_weights {
+    int latent, hidden, grid0, last_cin;
+    int chan[5];
+    const void* lin1_w;
+    const float* lin1_b;
+    const void* lin2_w;
+    const float* lin2_b;
+    const void* conv_w[4];
+    const float* conv_b[4];
+    const float* last_w;
+    const float* last_b;
+} vitad_cnn_decoder_weights;
+size_t vitad_cnn_decoder_workspace_bytes(const vitad_cnn_decoder_weights* w, int batch);
+int vitad_cnn_decoder_forward(const vitad_cnn_decoder_weights* w, const float* latent, int batch, void* workspace,
+                              size_t workspace_bytes, float* recon, void* stream);
 
 #ifdef __cplusplus
 }

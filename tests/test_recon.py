@@ -59,3 +59,24 @@ def test_recon_validator_matches_reference_golden():
     assert np.abs(res["recons"][:, :, ::8, ::8] - g["recons_sub"]).max() <= 2e-3
     assert np.abs(res["image_scores"] - g["image_scores"]).max() <= 1e-3 * np.abs(g["image_scores"]).max()
     assert np.abs(res["pixel_scores"][:, :, ::8, ::8] - g["pixel_scores_sub"]).max() <= 1e-3 * g["pixel_scores_sub"].max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 5, 32])
+def test_cnn_decoder_matches_fp32_modules(B):
+    """the CUDA decoder (two Linear GEMMs, four ConvTranspose2d+BN+ReLU layers as one phase-GEMM each,
+    fused last layer) against the reference module stack evaluated in fp32 on the CPU (CnnDecoder.py:16-117, eval mode:
+    BatchNorm running statistics), on the fixture's decoder weights (running_var ~ 0.015: every layer amplifies)."""
+    from vitad.autoencoders import DecoderVanillaCNN
+
+    dec = DecoderVanillaCNN(z_space=768, first_feature_map_size=7)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in W.make_small_decoder_state_dict(seed=41).items()})
+    dec.eval()
+    lat = torch.randn(B, 768, generator=torch.Generator().manual_seed(B)) * 0.7
+    with torch.no_grad():
+        ref = dec.decoder_cnn(dec.unflatten(dec.decoder_lin(lat)))  # parameter containers, fp32 on the CPU
+        got = dec.cuda()(lat.cuda())
+    torch.cuda.synchronize()
+    assert got.shape == (B, 3, 224, 224)
+    err = (got.cpu() - ref).abs().max().item()
+    assert err <= 1e-3 * max(ref.abs().max().item(), 1e-3) + 2e-4, (err, ref.abs().max().item())

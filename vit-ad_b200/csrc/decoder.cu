@@ -1,0 +1,233 @@
+// vitad_cnn_decoder_forward: the small CNN decoder of the reconstruction models (DecoderVanillaCNN,
+// src/classes/CnnDecoder.py:16-117; used by AutoEncoderDeit(decoder="cnn"), TransformerAutoEncoder.py:152-194) as
+// one C-ABI call:
+//   latent [B,768] -> Linear(768,1536)+ReLU -> Linear(1536,768*7*7)+ReLU -> unflatten [768,7,7]
+//   -> 4 x (ConvTranspose2d(k3,s2,p1,op1) + BatchNorm2d(eval) + ReLU): 768 -> 384 -> 192 -> 96 -> 48 channels, 7 -> 112 px
+//   -> ConvTranspose2d(48 -> 3) + BatchNorm2d + Tanh: 224 x 224 reconstruction.
+// Design:
+//   * activations are NHWC fp16 between layers (the second Linear's rows are permuted at pack time so its output
+//     already is [B,7,7,768]); BatchNorm (inference statistics) is folded into the packed weights and biases;
+//   * a stride-2 transposed 3x3 convolution is four ordinary convolutions, one per output phase (y mod 2, x mod 2),
+//     over the 2x2 input neighbourhood with 1/2/2/4 live taps.  All four run as ONE tcgen05 GEMM per layer:
+//     A = im2col2x2 [B*H*W, 4*C_in], W = [4*C_out, 4*C_in] (dead taps are zero: 16/9 of the minimal FLOPs, still < 60
+//     GFLOP per batch of 32), and the staged epilogue (SEpiConvT, gemm_staged.cuh) adds the folded bias, applies ReLU
+//     and scatters each phase to its output pixel;
+//   * the last layer has 3 output channels: a CUDA-core kernel (1296 FMAs per 2x2 output block) with the folded
+//     BatchNorm and tanh, writing the reconstruction as fp32 NCHW (what the validator returns and the L2-map kernel reads).
+#include <atomic>
+
+#include "host_util.cuh"
+#include "ptx.cuh"
+
+extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream);
+
+namespace vitad {
+extern std::atomic<uint64_t> g_launches;
+
+__global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, size_t n4) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 u;
+    u.x = pack_h2(v.x, v.y);
+    u.y = pack_h2(v.z, v.w);
+    reinterpret_cast<uint2*>(y)[i] = u;
+}
+
+// A[(b,i,j)][(di,dj,c)] = in[b, i+di, j+dj, c] (NHWC fp16, C channels per pixel), zero outside the Wg x Wg grid.
+// One thread moves 8 channels (16 bytes).
+__global__ void __launch_bounds__(256) im2col2x2_kernel(const __half* __restrict__ in, __half* __restrict__ a, int Wg,
+                                                        int C, size_t total8) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total8) return;
+    const int c8 = C >> 3;
+    const int c = static_cast<int>(idx % c8) << 3;
+    size_t r = idx / c8;
+    const int tap = static_cast<int>(r & 3);
+    r >>= 2;  // pixel row (b, i, j)
+    const int di = tap >> 1, dj = tap & 1;
+    const int j = static_cast<int>(r % Wg);
+    const int i = static_cast<int>((r / Wg) % Wg);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (i + di < Wg && j + dj < Wg)
+        v = *reinterpret_cast<const uint4*>(in + (r + static_cast<size_t>(di) * Wg + dj) * C + c);
+    *reinterpret_cast<uint4*>(a + (r * 4 + tap) * C + c) = v;
+}
+
+// Last layer: ConvTranspose2d(C_in -> 3, k3, s2, p1, op1) + folded BatchNorm + tanh.  in NHWC fp16 [B,Hi,Hi,Cp] (Cp = padded
+// channel pitch, C_in live channels), w fp32 [3 ky][3 kx][C_in][3] with the BN scale folded, bias fp32 [3];
+// out fp32 NCHW [B,3,2Hi,2Hi].  One thread = one input pixel = one 2x2 output block.
+template <int CIN>
+__global__ void __launch_bounds__(256) convt_last_kernel(const __half* __restrict__ in, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                         int Hi, int Cp) {
+    griddep_launch_dependents();
+    __shared__ __align__(16) float ws[9 * CIN * 3];
+    for (int i = threadIdx.x; i < 9 * CIN * 3; i += 256) ws[i] = w[i];
+    griddep_wait();
+    __syncthreads();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * Hi * Hi) return;
+    const int j = idx % Hi;
+    const int i = (idx / Hi) % Hi;
+    const int b = idx / (Hi * Hi);
+    float acc[2][2][3];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int co = 0; co < 3; ++co) acc[a][c][co] = bias[co];
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+        const int di = tap >> 1, dj = tap & 1;
+        if (i + di >= Hi || j + dj >= Hi) continue;
+        const __half* px = in + (static_cast<size_t>(b * Hi + i + di) * Hi + j + dj) * Cp;
+#pragma unroll
+        for (int c8 = 0; c8 < CIN; c8 += 8) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(px + c8);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+            float xv[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                xv[2 * e] = f.x;
+                xv[2 * e + 1] = f.y;
+            }
+            // output phase (a, c) sees this tap through kernel element ky = a + 1 - 2 di, kx = c + 1 - 2 dj
+#pragma unroll
+            for (int a = di; a < 2; ++a) {
+#pragma unroll
+                for (int c = dj; c < 2; ++c) {
+                    const int ky = a + 1 - 2 * di, kx = c + 1 - 2 * dj;
+                    // 8 channels x 3 outputs = 24 consecutive weights: six broadcast LDS.128 instead of 24 scalar loads
+                    const float4* wk4 = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * CIN + c8) * 3);
+                    float wk[24];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        const float4 t4 = wk4[q];
+                        wk[4 * q + 0] = t4.x, wk[4 * q + 1] = t4.y, wk[4 * q + 2] = t4.z, wk[4 * q + 3] = t4.w;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        acc[a][c][0] = fmaf(xv[e], wk[e * 3 + 0], acc[a][c][0]);
+                        acc[a][c][1] = fmaf(xv[e], wk[e * 3 + 1], acc[a][c][1]);
+                        acc[a][c][2] = fmaf(xv[e], wk[e * 3 + 2], acc[a][c][2]);
+                    }
+                }
+            }
+        }
+    }
+    const int Ho = 2 * Hi;
+#pragma unroll
+    for (int co = 0; co < 3; ++co)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            float2 v;
+            v.x = tanhf(acc[a][0][co]);
+            v.y = tanhf(acc[a][1][co]);
+            *reinterpret_cast<float2*>(out + ((static_cast<size_t>(b) * 3 + co) * Ho + 2 * i + a) * Ho + 2 * j) = v;
+        }
+}
+
+namespace {
+struct Carve {
+    uint8_t* p;
+    size_t used = 0;
+    void* take(size_t bytes) {
+        void* r = p ? p + used : nullptr;
+        used += (bytes + 255) & ~static_cast<size_t>(255);
+        return r;
+    }
+};
+struct DecWs {
+    void *lat, *h1, *act[5], *col[4];
+    size_t total;
+};
+DecWs carve(const vitad_cnn_decoder_weights& w, int batch, void* base) {
+    Carve c{static_cast<uint8_t*>(base)};
+    DecWs s;
+    s.lat = c.take(static_cast<size_t>(batch) * w.latent * 2);
+    s.h1 = c.take(static_cast<size_t>(batch) * w.hidden * 2);
+    int g = w.grid0;
+    s.act[0] = c.take(static_cast<size_t>(batch) * g * g * w.chan[0] * 2);
+    for (int l = 0; l < 4; ++l) {
+        s.col[l] = c.take(static_cast<size_t>(batch) * g * g * 4 * w.chan[l] * 2);
+        g *= 2;
+        s.act[l + 1] = c.take(static_cast<size_t>(batch) * g * g * w.chan[l + 1] * 2);
+    }
+    s.total = c.used;
+    return s;
+}
+}  // namespace
+}  // namespace vitad
+
+using namespace vitad;
+
+extern "C" size_t vitad_cnn_decoder_workspace_bytes(const vitad_cnn_decoder_weights* w, int batch) {
+    if (!w || batch <= 0) return 0;
+    return carve(*w, batch, nullptr).total;
+}
+
+extern "C" int vitad_cnn_decoder_forward(const vitad_cnn_decoder_weights* wp, const float* latent, int batch,
+                                         void* workspace, size_t workspace_bytes, float* recon, void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(wp && latent && workspace && recon, VITAD_ERR_ARG, "null pointer");
+    const vitad_cnn_decoder_weights& w = *wp;
+    VITAD_REQUIRE(batch > 0 && w.latent % 16 == 0 && w.hidden % 32 == 0 && w.grid0 > 0 && w.last_cin == 48, VITAD_ERR_SHAPE,
+                  "unsupported decoder geometry");
+    for (int l = 0; l < 5; ++l)
+        VITAD_REQUIRE(w.chan[l] % 32 == 0 && w.chan[l] > 0, VITAD_ERR_SHAPE, "channel pitches must be multiples of 32");
+    VITAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && aligned16(latent) && aligned16(recon), VITAD_ERR_ALIGN,
+                  "decoder buffers alignment");
+    DecWs ws = carve(w, batch, workspace);
+    VITAD_REQUIRE(workspace_bytes >= ws.total, VITAD_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.total);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    {
+        ProfScope prof("dec_cast", s);
+        const size_t n4 = static_cast<size_t>(batch) * w.latent / 4;
+        VITAD_CUDA_OK(launch_pdl(cast_f16_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, s, latent,
+                                 static_cast<__half*>(ws.lat), n4));
+        g_launches.fetch_add(1);
+    }
+    vitad_linear_args a;
+    memset(&a, 0, sizeof(a));
+    a.a = ws.lat, a.w = w.lin1_w, a.bias = w.lin1_b, a.m = batch, a.n = w.hidden, a.k = w.latent, a.lda = w.latent,
+    a.ldw = w.latent, a.epilogue = VITAD_EPI_BIAS_RELU_F16, a.out = ws.h1, a.ldo = w.hidden;
+    if ((rc = vitad_linear_f16(&a, s))) return rc;
+    const int n2 = w.grid0 * w.grid0 * w.chan[0];
+    memset(&a, 0, sizeof(a));
+    a.a = ws.h1, a.w = w.lin2_w, a.bias = w.lin2_b, a.m = batch, a.n = n2, a.k = w.hidden, a.lda = w.hidden, a.ldw = w.hidden;
+    a.epilogue = VITAD_EPI_BIAS_RELU_F16, a.out = ws.act[0], a.ldo = n2;
+    if ((rc = vitad_linear_f16(&a, s))) return rc;
+    int g = w.grid0;
+    for (int l = 0; l < 4; ++l) {
+        const int cin = w.chan[l], cout = w.chan[l + 1];
+        const int M = batch * g * g;
+        {
+            ProfScope prof("dec_im2col", s);
+            const size_t total8 = static_cast<size_t>(M) * 4 * (cin / 8);
+            VITAD_CUDA_OK(launch_pdl(im2col2x2_kernel, dim3(static_cast<unsigned>((total8 + 255) / 256)), dim3(256), 0, s,
+                                     static_cast<const __half*>(ws.act[l]), static_cast<__half*>(ws.col[l]), g, cin, total8));
+            g_launches.fetch_add(1);
+        }
+        memset(&a, 0, sizeof(a));
+        a.a = ws.col[l], a.w = w.conv_w[l], a.bias = w.conv_b[l], a.m = M, a.n = 4 * cout, a.k = 4 * cin, a.lda = 4 * cin,
+        a.ldw = 4 * cin, a.epilogue = VITAD_EPI_CONVT_RELU_F16, a.out = ws.act[l + 1], a.ldo = 2 * cout, a.convt_w = g;
+        if ((rc = vitad_linear_f16(&a, s))) return rc;
+        g *= 2;
+    }
+    {
+        ProfScope prof("dec_last", s);
+        const int pixels = batch * g * g;
+        VITAD_CUDA_OK(launch_pdl(convt_last_kernel<48>, dim3((pixels + 255) / 256), dim3(256), 0, s,
+                                 static_cast<const __half*>(ws.act[4]), w.last_w, w.last_b, recon, batch, g, w.chan[4]));
+        g_launches.fetch_add(1);
+    }
+    return VITAD_OK;
+}

@@ -501,6 +501,41 @@ struct SEpiPatchEmbed {
     }
 };
 
+// ConvTranspose2d(kernel 3, stride 2, padding 1, output_padding 1) + folded BatchNorm + ReLU as ONE GEMM
+// (CnnDecoder.py:47-117): GEMM row r = input pixel (b, i, j) of a Wg x Wg grid, K = the 2x2 input neighbourhood x C_in
+// (im2col2x2), GEMM column = a*(2*Cp) + c*Cp + co for output phase (a, c) — the output pixel (2i+a, 2j+c).  The two
+// c-phases of a row are adjacent NHWC pixels, so with output "rows" (b, y, j) of 2*Cp channels:
+//   out_row = 2r - (r mod Wg) + a*Wg,   out_col = col mod (2*Cp).
+struct SEpiConvT {
+    static constexpr bool kRowCtx = true;
+    static constexpr int kDefaultEpiWarps = 8;
+    using Pre = NoPre;
+    using ColC = float4;
+    const float* bias;  // [N] = per (phase, channel), BN folded
+    __half* out;        // NHWC fp16 [B, 2Wg, 2Wg, Cp]
+    int M, N, Wg;       // N = 4*Cp
+    __device__ __forceinline__ RowCtx row_ctx(int row) const {
+        if (row >= M) return RowCtx{0, -1};
+        return RowCtx{2 * row - (row % Wg), 0};
+    }
+    __device__ __forceinline__ bool direct(int) const { return false; }
+    __device__ __forceinline__ void direct_unit(int, RowCtx, int, const uint32_t (&)[32]) const {}
+    __device__ __forceinline__ Pre prefetch(int, RowCtx, int) const { return NoPre{}; }
+    __device__ __forceinline__ ColC col_const(int col) const {
+        return col < N ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ void store(int, RowCtx ctx, int col, float4 a, Pre, ColC b) const {
+        if (ctx.b < 0 || col >= N) return;
+        const int half_n = N >> 1;  // 2*Cp
+        const int pa = col >= half_n ? 1 : 0;
+        const int cc = col - pa * half_n;
+        uint2 u;
+        u.x = pack_h2(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f));
+        u.y = pack_h2(fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
+        *reinterpret_cast<uint2*>(out + (static_cast<size_t>(ctx.a) + pa * Wg) * half_n + cc) = u;
+    }
+};
+
 // Plain fp32 output (+ optional bias), any N and pitch: used by tests and small projections.
 struct SEpiBiasF32 {
     static constexpr bool kRowCtx = false;

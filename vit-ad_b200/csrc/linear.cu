@@ -100,6 +100,8 @@ static int dispatch_staged(const vitad_linear_args& a, cudaStream_t stream) {
                 a, SEpiPatchEmbed{a.bias, a.pos, static_cast<float*>(a.out), a.m, a.patches, a.prefix, a.n}, stream);
         case VITAD_EPI_F32:
             return launch_gemm_staged<BLOCK_N>(a, SEpiBiasF32{a.bias, static_cast<float*>(a.out), a.ldo, a.m, a.n}, stream);
+        case VITAD_EPI_CONVT_RELU_F16:
+            return launch_gemm_staged<BLOCK_N>(a, SEpiConvT{a.bias, static_cast<__half*>(a.out), a.m, a.n, a.convt_w}, stream);
         default:
             set_error("unknown epilogue %d", a.epilogue);
             return VITAD_ERR_ARG;
@@ -260,6 +262,10 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
                               (a.windows <= 1 || (a.tok2win && a.windows * a.win_tokens == a.tokens)),
                           VITAD_ERR_SHAPE, "QKV epilogue window layout (windows*win_tokens == tokens, map given)");
             break;
+        case VITAD_EPI_CONVT_RELU_F16:
+            VITAD_REQUIRE(a.out && aligned16(a.out) && a.n % 128 == 0 && a.convt_w > 0 && a.m % (a.convt_w * a.convt_w) == 0,
+                          VITAD_ERR_SHAPE, "conv-transpose epilogue needs N = 4*Cp with Cp %% 32 == 0 and M = B*Wg*Wg");
+            break;
         case VITAD_EPI_PATCH_EMBED:
             VITAD_REQUIRE(a.out && a.pos && aligned16(a.out) && aligned16(a.pos) && a.patches > 0 &&
                               a.m % a.patches == 0 && a.prefix >= 0,
@@ -269,7 +275,8 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
             break;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const bool pair = g_use_pair.load() && a.m > kBlockM;
+    // the conv-transpose scatter exists only as a staged epilogue of the CTA-pair kernel (which handles any M)
+    const bool pair = (g_use_pair.load() && a.m > kBlockM) || a.epilogue == VITAD_EPI_CONVT_RELU_F16;
     // block_n is a hint: widths the selected kernel does not instantiate fall back to the library's choice
     const bool hint_ok = pair ? (a.block_n == 128 || a.block_n == 256) : (a.block_n == 96 || a.block_n == 128 || a.block_n == 256);
     const int bn = hint_ok ? a.block_n : (pair ? pick_block_n_pair(a.m, a.n) : pick_block_n_single(a.m, a.n));

@@ -49,6 +49,8 @@ EPI_RESIDUAL_F32 = 2
 EPI_QKV = 3
 EPI_PATCH_EMBED = 4
 EPI_F32 = 5
+EPI_BIAS_RELU_F16 = 6
+EPI_CONVT_RELU_F16 = 7
 
 
 class LinearArgs(C.Structure):
@@ -80,6 +82,7 @@ class LinearArgs(C.Structure):
         ("windows", C.c_int),
         ("win_tokens", C.c_int),
         ("tok2win", C.c_void_p),
+        ("convt_w", C.c_int),
     ]
 
 
@@ -206,6 +209,18 @@ lib.vitad_nf_workspace_bytes.argtypes = [C.POINTER(NfWeights), _i]
 lib.vitad_nf_workspace_bytes.restype = _sz
 lib.vitad_nf_forward.argtypes = [C.POINTER(NfWeights), _vp, _i, _vp, _sz, _vp, _vp, _vp]
 lib.vitad_nf_forward.restype = _i
+
+# ------------------------------------------------------------------------- small CNN decoder
+class CnnDecoderWeights(C.Structure):
+    _fields_ = [("latent", _i), ("hidden", _i), ("grid0", _i), ("last_cin", _i), ("chan", _i * 5),
+                ("lin1_w", _vp), ("lin1_b", _vp), ("lin2_w", _vp), ("lin2_b", _vp), ("conv_w", _vp * 4),
+                ("conv_b", _vp * 4), ("last_w", _vp), ("last_b", _vp)]
+
+
+lib.vitad_cnn_decoder_workspace_bytes.argtypes = [C.POINTER(CnnDecoderWeights), _i]
+lib.vitad_cnn_decoder_workspace_bytes.restype = _sz
+lib.vitad_cnn_decoder_forward.argtypes = [C.POINTER(CnnDecoderWeights), _vp, _i, _vp, _sz, _vp, _vp]
+lib.vitad_cnn_decoder_forward.restype = _i
 
 MDN_KA = 784  # K extent of the packed MDN operands (768 + 16)
 
