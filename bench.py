@@ -156,7 +156,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from oracle import weights as W  # seeded synthetic weights/inputs only (no oracle compute on this arm)
+    from vitad import synth_weights as W  # seeded synthetic weights / inputs (product package, not oracle/)
     from vitad import _lib, ops
     from vitad.encoders import EncoderDeit
     from vitad.mdn import GaussianMixtureDensityNetwork

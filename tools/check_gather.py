@@ -3,7 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "vit-ad_b200"))
 import numpy as np, torch, torch.distributed as dist
-from oracle import weights as W
+from vitad import synth_weights as W
 from vitad.encoders import EncoderDeit
 from vitad.nf import NormalizingFlow
 from vitad.parallel import gather_results, init_from_env

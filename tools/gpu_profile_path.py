@@ -3,7 +3,7 @@ import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "vit-ad_b200")); sys.path.insert(0, ROOT)
 import torch
-from oracle import weights as W
+from vitad import synth_weights as W
 from vitad import _lib, ops
 from vitad.encoders import EncoderDeit
 from vitad.mdn import GaussianMixtureDensityNetwork

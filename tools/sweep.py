@@ -22,7 +22,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from oracle import weights as W  # noqa: E402  (seeded synthetic weights only)
+from vitad import synth_weights as W  # noqa: E402  (seeded synthetic weights only)
 from vitad.encoders import EncoderDeit  # noqa: E402
 from vitad.mdn import GaussianMixtureDensityNetwork  # noqa: E402
 from vitad.gpu_metrics import calc_all_metrics_device  # noqa: E402
