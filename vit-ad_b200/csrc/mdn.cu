@@ -185,85 +185,92 @@ __global__ void __launch_bounds__(256) gmm_operand_kernel(const float* __restric
 // ---------------------------------------------------------------------------- mixing weights
 // lp2[t][kmap(k)] = log2( softmax_k(x[t].Wpi[k] + bpi[k] + g[t][k]) + 1e-15 )   — fp32 on CUDA cores: the
 // logits enter every feature's logsumexp with the same sign, so they need better than fp16-GEMM accuracy.
-// CTA = 32 tokens x up to 160 mixtures; 256 threads, thread (ty,tx) accumulates tokens ty*4..+3 x mixtures tx+32*j.
-constexpr int kPiBM = 32, kPiBK = 32, kPiMaxK = 160;
-__global__ void __launch_bounds__(256) gmm_logpi_kernel(const float* __restrict__ x, int ldx,
-                                                        const float* __restrict__ wpi, const float* __restrict__ bpi,
-                                                        const float* __restrict__ gumbel, float* __restrict__ lp2,
-                                                        int M, int D, int K, int n_kc, int KC, int KCV) {
+// CTA = 4 warps x TPW tokens x up to 160 mixtures: lane tx of warp ty accumulates tokens (ty*TPW .. +TPW-1) x mixtures
+// tx+32*j in registers, so a token's logits stay inside its warp and the softmax needs shuffles only.  TPW is chosen
+// by the host so that the tokens fill the 148 SMs in ONE balanced wave (M = 6272 -> TPW 11, 143 CTAs): with a fixed
+// 32-token CTA the 196 CTAs left 48 SMs with two CTAs and the rest with one (88 us; this form: see DESIGN.md 4.5).
+constexpr int kPiBK = 32, kPiMaxK = 160;
+template <int TPW, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) gmm_logpi_kernel(const float* __restrict__ x, int ldx,
+                                                               const float* __restrict__ wpi, const float* __restrict__ bpi,
+                                                               const float* __restrict__ gumbel, float* __restrict__ lp2,
+                                                               int M, int D, int K, int n_kc, int KC, int KCV) {
     griddep_launch_dependents();
     griddep_wait();
-    // k is the contiguous index of both staging arrays and is read four at a time (LDS.128): 9 shared loads per
-    // 80 FMAs.  Row pitch 36 floats: 16-byte aligned, and the 8 lanes of a quarter-warp land on 8 distinct bank groups.
+    constexpr int BM = WARPS * TPW;
+    constexpr int kPiThreads = 32 * WARPS;
+    // k is the contiguous index of both staging arrays and is read four at a time (LDS.128; the x reads are warp-wide
+    // broadcasts).  Row pitch 36 floats: 16-byte aligned, the 8 lanes of a quarter-warp land on 8 distinct bank groups.
     constexpr int kPitch = kPiBK + 4;
-    __shared__ __align__(16) float xs[kPiBM][kPitch];
+    __shared__ __align__(16) float xs[BM][kPitch];
     __shared__ __align__(16) float wsh[kPiMaxK][kPitch];
-    __shared__ float logit[kPiBM][kPiMaxK + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int m0 = blockIdx.x * kPiBM;
-    float acc[4][5];
+    const int m0 = blockIdx.x * BM;
+    float acc[TPW][5];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TPW; ++i)
 #pragma unroll
         for (int j = 0; j < 5; ++j) acc[i][j] = 0.f;
-    // global -> register prefetch of the next k-block overlaps the FMAs of the current one (one float4 of x and
-    // five of Wpi per thread per k-block)
-    constexpr int kQ = kPiBK / 4;  // float4 per staged row
+    // global -> register prefetch of the next k-block overlaps the FMAs of the current one
+    constexpr int kQ = kPiBK / 4;                  // float4 per staged row
+    constexpr int kRowsPerPass = kPiThreads / kQ;  // 16 rows staged per pass
+    constexpr int kXPasses = (BM + kRowsPerPass - 1) / kRowsPerPass;
     const int xr = threadIdx.x / kQ, xc = (threadIdx.x % kQ) * 4;
-    float4 px, pw[5];
+    float4 px[kXPasses], pw[kPiMaxK / kRowsPerPass];
     auto fetch = [&](int k0) {
-        px = (m0 + xr < M) ? *reinterpret_cast<const float4*>(x + static_cast<size_t>(m0 + xr) * ldx + k0 + xc)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const int r = xr + 32 * j;  // 160 rows = 5 x 32
+        for (int j = 0; j < kXPasses; ++j) {
+            const int r = xr + kRowsPerPass * j;
+            px[j] = (r < BM && m0 + r < M) ? *reinterpret_cast<const float4*>(x + static_cast<size_t>(m0 + r) * ldx + k0 + xc)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < kPiMaxK / kRowsPerPass; ++j) {
+            const int r = xr + kRowsPerPass * j;
             pw[j] = (r < K) ? __ldg(reinterpret_cast<const float4*>(wpi + static_cast<size_t>(r) * D + k0 + xc))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     fetch(0);
     for (int k0 = 0; k0 < D; k0 += kPiBK) {
-        *reinterpret_cast<float4*>(&xs[xr][xc]) = px;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) *reinterpret_cast<float4*>(&wsh[xr + 32 * j][xc]) = pw[j];
+        for (int j = 0; j < kXPasses; ++j)
+            if (xr + kRowsPerPass * j < BM) *reinterpret_cast<float4*>(&xs[xr + kRowsPerPass * j][xc]) = px[j];
+#pragma unroll
+        for (int j = 0; j < kPiMaxK / kRowsPerPass; ++j) *reinterpret_cast<float4*>(&wsh[xr + kRowsPerPass * j][xc]) = pw[j];
         __syncthreads();
         if (k0 + kPiBK < D) fetch(k0 + kPiBK);
 #pragma unroll
         for (int k = 0; k < kPiBK; k += 4) {
-            float4 xv[4], wv[5];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(&xs[ty * 4 + i][k]);
+            float4 wv[5];
 #pragma unroll
             for (int j = 0; j < 5; ++j) wv[j] = *reinterpret_cast<const float4*>(&wsh[tx + 32 * j][k]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < TPW; ++i) {
+                const float4 xv = *reinterpret_cast<const float4*>(&xs[ty * TPW + i][k]);
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
-                    acc[i][j] = fmaf(xv[i].x, wv[j].x, acc[i][j]);
-                    acc[i][j] = fmaf(xv[i].y, wv[j].y, acc[i][j]);
-                    acc[i][j] = fmaf(xv[i].z, wv[j].z, acc[i][j]);
-                    acc[i][j] = fmaf(xv[i].w, wv[j].w, acc[i][j]);
+                    acc[i][j] = fmaf(xv.x, wv[j].x, acc[i][j]);
+                    acc[i][j] = fmaf(xv.y, wv[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(xv.z, wv[j].z, acc[i][j]);
+                    acc[i][j] = fmaf(xv.w, wv[j].w, acc[i][j]);
                 }
+            }
         }
         __syncthreads();
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 5; ++j) logit[ty * 4 + i][tx + 32 * j] = acc[i][j];
-    __syncthreads();
-    // softmax + log per token: warp ty handles tokens ty*4..+3
+    // softmax + log per token, straight from the accumulators: lane tx holds mixtures tx + 32 j of each of its warp's tokens
     const int ldp = n_kc * KC;
-    for (int i = 0; i < 4; ++i) {
-        const int r = ty * 4 + i;
-        const int t = m0 + r;
-        if (t >= M) break;
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+        const int t = m0 + ty * TPW + i;
+        if (t >= M) break;  // warp-uniform
         float z[5];
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
             const int k = tx + 32 * j;
-            z[j] = (k < K) ? logit[r][k] + bpi[k] + gumbel[static_cast<size_t>(t) * K + k] : -INFINITY;
+            z[j] = (k < K) ? acc[i][j] + bpi[k] + gumbel[static_cast<size_t>(t) * K + k] : -INFINITY;
             mx = fmaxf(mx, z[j]);
         }
 #pragma unroll
@@ -291,6 +298,13 @@ __global__ void __launch_bounds__(256) gmm_logpi_kernel(const float* __restrict_
             if (j >= KCV || kc * KCV + j >= K) dst[s] = kPadLogPi;
         }
     }
+}
+
+template <int TPW, int WARPS>
+static cudaError_t launch_logpi(cudaStream_t s, const float* x, int ldx, const float* pi_w, const float* pi_b,
+                                const float* gumbel, float* lp2, int tokens, int dim, int K, int n_kc, int kc, int kcv) {
+    return launch_pdl(gmm_logpi_kernel<TPW, WARPS>, dim3((tokens + WARPS * TPW - 1) / (WARPS * TPW)), dim3(32 * WARPS), 0, s,
+                      x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, K, n_kc, kc, kcv);
 }
 
 // ---------------------------------------------------------- mixing weights on the tensor cores
@@ -586,16 +600,33 @@ extern "C" int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, cons
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(x && pi_w && pi_b && gumbel && lp2, VITAD_ERR_ARG, "null pointer");
-    VITAD_REQUIRE(dim % kPiBK == 0 && tokens > 0, VITAD_ERR_SHAPE, "dim %% 32 != 0 or no tokens");
+    VITAD_REQUIRE(dim % kPiBK == 0 && tokens > 0 && num_gaussians <= kPiMaxK, VITAD_ERR_SHAPE, "dim %% 32 != 0, no tokens or K > 160");
     VITAD_REQUIRE(ldx % 4 == 0 && aligned16(x) && aligned16(pi_w), VITAD_ERR_ALIGN,
                   "log_pi: x / pi_w must be 16-byte aligned with ldx %% 4 == 0");
     int n_kc, kc, kcv;
     rc = vitad_gmm_plan(num_gaussians, &n_kc, &kc, &kcv);
     if (rc) return rc;
     ProfScope prof("gmm_logpi", static_cast<cudaStream_t>(stream));
-    VITAD_CUDA_OK(launch_pdl(gmm_logpi_kernel, dim3((tokens + kPiBM - 1) / kPiBM), dim3(256), 0,
-                             static_cast<cudaStream_t>(stream), x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, num_gaussians,
-                             n_kc, kc, kcv));
+    // tokens per warp so that one wave of CTAs covers the device: 8 warps per CTA (two per scheduler hide the
+    // shared-memory and FMA latencies), 4 for small inputs so that enough CTAs exist
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int sms = device_sm_count();
+    cudaError_t e;
+#define VITAD_LOGPI(T, W) e = launch_logpi<T, W>(s, x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, num_gaussians, n_kc, kc, kcv)
+    if (tokens <= 8 * sms) {
+        const int per_warp = (tokens + 4 * sms - 1) / (4 * sms);
+        if (per_warp <= 1) VITAD_LOGPI(1, 4);
+        else VITAD_LOGPI(2, 4);
+    } else {
+        const int per_warp = (tokens + 8 * sms - 1) / (8 * sms);
+        if (per_warp <= 2) VITAD_LOGPI(2, 8);
+        else if (per_warp <= 3) VITAD_LOGPI(3, 8);
+        else if (per_warp <= 4) VITAD_LOGPI(4, 8);
+        else if (per_warp <= 6) VITAD_LOGPI(6, 8);
+        else VITAD_LOGPI(8, 8);
+    }
+#undef VITAD_LOGPI
+    VITAD_CUDA_OK(e);
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;
