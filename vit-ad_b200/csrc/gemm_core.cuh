@@ -252,20 +252,4 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
 }
 
-// Helper for plain epilogues: walk accumulator columns [c0, c1) in chunks of 32 and hand each chunk
-// (as floats) to `f(col_in_block, v[32])`.  All lanes execute the tcgen05.ld.
-template <class F>
-__device__ __forceinline__ void for_each_chunk32(uint32_t taddr, int c0, int c1, F&& f) {
-#pragma unroll 1
-    for (int c = c0; c < c1; c += 32) {
-        uint32_t r[32];
-        tmem_ld_x32(taddr + c, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        f(c, v);
-    }
-}
-
 }  // namespace vitad

@@ -35,7 +35,7 @@ void set_error(const char* fmt, ...);
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // 2-D fp16 row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols],
-// 128-byte swizzle (matches make_smem_desc_sw128).  Out-of-bounds box elements read as zero.
+// 128-byte swizzle (matches the shared-memory matrix descriptors of ptx.cuh).  Out-of-bounds box elements read as zero.
 int make_tmap_f16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols = 64);
 // 3-D variant: [d2, rows, cols] with pitches ld (elements, rows) and ld2 (elements, slabs).

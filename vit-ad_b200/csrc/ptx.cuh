@@ -35,9 +35,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -83,22 +80,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                                 uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, "
-        "%4}], [%2], %5;"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-        : "memory");
-}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
-static constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
 // ------------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -147,15 +134,6 @@ constexpr uint32_t kSmemDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t smem_desc_join(uint32_t lo) {
     return (static_cast<uint64_t>(kSmemDescHiSw128) << 32) | lo;
-}
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t addr) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);  // start address
-    d |= static_cast<uint64_t>(1) << 16;                // leading byte offset (ignored for swizzled K-major)
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;        // stride byte offset
-    d |= static_cast<uint64_t>(1) << 46;                // descriptor version (Blackwell)
-    d |= static_cast<uint64_t>(2) << 61;                // SWIZZLE_128B
-    return d;
 }
 
 // TMEM -> registers: 32 lanes x 32-bit, N consecutive columns; thread i of the warp reads lane
