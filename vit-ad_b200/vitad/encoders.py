@@ -486,6 +486,8 @@ class EncoderEsVit(TransformerEncoder):
         if self._packed is None or self._packed["device"] != x.device:
             self._pack(x.device)
         pk = self._packed
+        if x.dtype == torch.uint8:  # native pixels: the /255 of ToTensor (GeneralDataset.py:46-53)
+            x = x.to(torch.float32).div_(255.0)
         x = x.to(torch.float32).contiguous()
         B = x.shape[0]
         P, Cdim = self.num_embedded_patches, self.size_patch_embedding

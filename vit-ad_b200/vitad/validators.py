@@ -285,7 +285,9 @@ class ValidatorRecon(_Pipelined):
 
     def score_batch(self, images: torch.Tensor, batch_index: int = 0):
         """ValidatorRecon.py:107-116 → (image_scores [B], pixel_scores [B,1,S,S], reconstruction)."""
-        images = images.to(self.device, non_blocking=True).to(torch.float32)
+        images = images.to(self.device, non_blocking=True)
+        # uint8 pixels -> the fp32 [0,1] tensor ToTensor produces (the L2 map compares against it)
+        images = images.to(torch.float32).div_(255.0) if images.dtype == torch.uint8 else images.to(torch.float32)
         output = self.model(images)
         amap, score = self.model.anomaly_map_and_score(output.reconstruction, images)
         return score, amap, output.reconstruction
