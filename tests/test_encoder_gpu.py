@@ -44,6 +44,28 @@ def test_layernorm_token_remap_and_augmentation():
     assert (o16[:, 768:770] == 1).all() and (o16[:, 770:] == 0).all()
 
 
+@pytest.mark.parametrize("C,rows", [(96, 100352), (96, 37), (192, 25088), (192, 5)])
+def test_layernorm_narrow_rows(C, rows):
+    """Swin stages 0/1: the sub-warp kernel (8 / 16 lanes per row), fp16 + fp32 outputs, ragged row counts, and the
+    in-place fp32 form the patch-embed norm uses (SwinTransformerModule.py:645-655)."""
+    from vitad import ops
+
+    g = torch.Generator().manual_seed(C + rows)
+    x = (torch.randn(rows, C, generator=g) * 2 + 0.3).cuda()
+    w = (1 + 0.1 * torch.randn(C, generator=g)).cuda()
+    b = (0.1 * torch.randn(C, generator=g)).cuda()
+    ref = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5)
+    o16 = torch.empty(rows, C, device="cuda", dtype=torch.float16)
+    o32 = torch.empty(rows, C, device="cuda")
+    ops.layernorm(x, w, b, 1e-5, out_f16=o16, out_f32=o32)
+    xin = x.clone()
+    ops.layernorm(xin, w, b, 1e-5, out_f32=xin)  # in place
+    torch.cuda.synchronize()
+    assert (o32 - ref).abs().max().item() <= 2e-5
+    assert (o16.float() - ref).abs().max().item() <= 4e-3
+    assert torch.equal(xin, o32)
+
+
 def test_patchify_matches_unfold():
     from vitad import ops
 

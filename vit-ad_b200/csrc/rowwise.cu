@@ -110,6 +110,76 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
+// Narrow rows (Swin stages 0/1: C = 96, 192 over 100 352 / 25 088 rows): LPR lanes per row, 32/LPR rows per warp pass and
+// kLnRows passes per warp, every lane holds VPL float4 of its row (C = 4*LPR*VPL exactly).  The one-warp-per-two-rows
+// kernel above leaves 8 of 32 lanes idle at C = 96 and needs 6272 blocks (8 waves) for stage 0.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) layernorm_narrow_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ b, __half* __restrict__ out_h,
+                                                               float* __restrict__ out_f, int rows, int ldx, int ldh,
+                                                               int ldf, float eps) {
+    griddep_launch_dependents();
+    griddep_wait();
+    constexpr int C = 4 * LPR * VPL;
+    constexpr int kRowsPerPass = 32 / LPR;
+    constexpr int kPasses = 4;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, l = lane % LPR;
+    const int row0 = warp * kRowsPerPass * kPasses + sub;
+    float4 v[kPasses][VPL];
+    float s[kPasses];
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p) {
+        const int row = min(row0 + p * kRowsPerPass, rows - 1);
+        const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
+        s[p] = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            v[p][j] = xr[l + LPR * j];
+            s[p] += (v[p][j].x + v[p][j].y) + (v[p][j].z + v[p][j].w);
+        }
+    }
+    float mean[kPasses], rstd[kPasses];
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p) {
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) s[p] += __shfl_xor_sync(0xffffffffu, s[p], o);
+        mean[p] = s[p] / C;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const float a = v[p][j].x - mean[p], bb = v[p][j].y - mean[p], c = v[p][j].z - mean[p], d = v[p][j].w - mean[p];
+            q += (a * a + bb * bb) + (c * c + d * d);
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        rstd[p] = rsqrtf(q / C + eps);
+    }
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+        const int i = l + LPR * j;
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + i), bb = __ldg(reinterpret_cast<const float4*>(b) + i);
+#pragma unroll
+        for (int p = 0; p < kPasses; ++p) {
+            const int row = row0 + p * kRowsPerPass;
+            if (row >= rows) continue;
+            float4 y;
+            y.x = (v[p][j].x - mean[p]) * rstd[p] * ww.x + bb.x;
+            y.y = (v[p][j].y - mean[p]) * rstd[p] * ww.y + bb.y;
+            y.z = (v[p][j].z - mean[p]) * rstd[p] * ww.z + bb.z;
+            y.w = (v[p][j].w - mean[p]) * rstd[p] * ww.w + bb.w;
+            if (out_f) reinterpret_cast<float4*>(out_f + static_cast<size_t>(row) * ldf)[i] = y;
+            if (out_h) {
+                uint2 u;
+                u.x = pack_h2(y.x, y.y);
+                u.y = pack_h2(y.z, y.w);
+                reinterpret_cast<uint2*>(out_h + static_cast<size_t>(row) * ldh)[i] = u;
+            }
+        }
+    }
+}
+
 // Patch gathering for the non-overlapping PxP/sP conv (timm PatchEmbed.proj): images fp32 [B,Cin,S,S]
 // -> A fp16 [B*g*g, Cin*P*P], column order (c, i, j) = the conv weight's flattened order.
 // One thread moves 8 consecutive j (two float4 loads, one 16-byte store).
@@ -210,8 +280,23 @@ extern "C" int vitad_layernorm(const float* x, const float* weight, const float*
     VITAD_REQUIRE(in_tokens > 0 && out_tokens > 0 && skip >= 0 && skip + out_tokens <= in_tokens, VITAD_ERR_SHAPE,
                   "token remap");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int blocks = (rows + 8 * kLnRows - 1) / (8 * kLnRows);
     ProfScope prof("layernorm", s);
+    // narrow rows without token remap / operand augmentation: sub-warp lane groups per row
+    const bool plain = in_tokens == out_tokens && skip == 0 && aug_ones == 0;
+    if (plain && (c == 96 || c == 192)) {
+        const int rows_per_warp = (c == 96 ? 4 : 2) * 4;
+        const int nblocks = (rows + 8 * rows_per_warp - 1) / (8 * rows_per_warp);
+        if (c == 96)
+            VITAD_CUDA_OK(launch_pdl(layernorm_narrow_kernel<8, 3>, dim3(nblocks), dim3(256), 0, s, x, weight, bias,
+                                     static_cast<__half*>(out_f16), out_f32, rows, ldx, ld_f16, ld_f32, eps));
+        else
+            VITAD_CUDA_OK(launch_pdl(layernorm_narrow_kernel<16, 3>, dim3(nblocks), dim3(256), 0, s, x, weight, bias,
+                                     static_cast<__half*>(out_f16), out_f32, rows, ldx, ld_f16, ld_f32, eps));
+        VITAD_CUDA_OK(cudaGetLastError());
+        g_launches.fetch_add(1);
+        return VITAD_OK;
+    }
+    const int blocks = (rows + 8 * kLnRows - 1) / (8 * kLnRows);
     if (c <= 768)
         VITAD_CUDA_OK(launch_pdl(layernorm_kernel<6>, dim3(blocks), dim3(256), 0, s, x, weight, bias,
                                  static_cast<__half*>(out_f16), out_f32, rows, c, ldx, ld_f16, ld_f32, in_tokens, out_tokens,
