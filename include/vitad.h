@@ -69,9 +69,18 @@ typedef enum vitad_epilogue {
     VITAD_EPI_PATCH_EMBED = 4,    /* + bias + pos_embed, written behind the prefix tokens   */
     VITAD_EPI_F32 = 5,            /* out_f32 = acc (+ bias if non-null)                     */
     VITAD_EPI_BIAS_RELU_F16 = 6,  /* out_f16 = relu(acc + bias)  (FastFlow subnet, NormalizingFlow.py:61-82) */
-    VITAD_EPI_CONVT_RELU_F16 = 7  /* ConvTranspose2d(k3,s2,p1,op1)+BN+ReLU as one GEMM (CnnDecoder.py:47-117): row =
+    VITAD_EPI_CONVT_RELU_F16 = 7, /* ConvTranspose2d(k3,s2,p1,op1)+BN+ReLU as one GEMM (CnnDecoder.py:47-117): row =
                                      input pixel (b,i,j) of a convt_w-wide grid, col = (phase a, phase c, channel);
                                      out_f16 NHWC [B,2H,2W,N/4] = relu(acc + bias) scattered to pixel (2i+a, 2j+c) */
+    VITAD_EPI_RES16_RELU_F16 = 8, /* out_f16 = relu(acc + bias + resid16): the tail of a reverse-ResNet Bottleneck
+                                     (ReverseResNet.py:86-103: conv1 + bn1, `out += identity`, relu).  res_grid = 0: the
+                                     residual row is the output row; res_grid = g > 0: the identity path is a stride-2
+                                     1x1 transposed convolution computed on the g x g input grid (:190-195), so output
+                                     pixel (b,y,x) of the 2g x 2g grid adds row (b,y/2,x/2) when y and x are even and
+                                     nothing otherwise (its BatchNorm shift is folded into bias) */
+    VITAD_EPI_TANH_PIX4_F32 = 9   /* reverse-ResNet image head (CnnDecoder.py:189-194): row = pixel (b,J,I) of a
+                                     convt_w-wide grid, col = c*16 + py*4 + px (48 live of 64); out fp32 NCHW
+                                     [B,3,4W,4W][b][c][4J+py][4I+px] = tanh(acc + bias[col]) */
 } vitad_epilogue;
 
 typedef struct vitad_linear_args {
@@ -100,7 +109,9 @@ typedef struct vitad_linear_args {
      * SwinTransformerModule.py:360-384). */
     int head_dim, windows, win_tokens;
     const int* tok2win;
-    int convt_w;        /* CONVT_RELU_F16: width (= height) of the input pixel grid */
+    int convt_w;        /* CONVT_RELU_F16 / TANH_PIX4_F32: width (= height) of the input pixel grid */
+    const void* resid16; /* RES16_RELU_F16: fp16 residual rows, pitch ldr elements */
+    int ldr, res_grid;
 } vitad_linear_args;
 
 int vitad_linear_f16(const vitad_linear_args* args, void* stream);
@@ -345,6 +356,55 @@ typedef struct vitad_cnn_decoder_weights {
 size_t vitad_cnn_decoder_workspace_bytes(const vitad_cnn_decoder_weights* w, int batch);
 int vitad_cnn_decoder_forward(const vitad_cnn_decoder_weights* w, const float* latent, int batch, void* workspace,
                               size_t workspace_bytes, float* recon, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Reverse-ResNet decoder of the reconstruction models: DecoderResNetVariableEmbeddingSize.forward
+ * (src/classes/CnnDecoder.py:158-196) over ReverseResNet (src/classes/resnet/ReverseResNet.py:106-242), the default
+ * decoder of AutoEncoderDeit (TransformerAutoEncoder.py:155-181, get_model("ae_deit")):
+ *   latent [B,768] -> Linear+ReLU (1536) -> Linear+ReLU (2048) -> nearest upsample of the 1x1 feature to grid0 x grid0
+ *   -> 16 Bottleneck blocks (layer4: 3 at 7x7, layer3: 4 at 14x14, layer2: 6 at 28x28, layer1: 3 at 56x56; the last
+ *   block of layers 4..2 doubles the grid) -> nearest upsample to 112 -> ConvTranspose2d(64->3, k7, s2, p3, op1)
+ *   -> BatchNorm2d -> Tanh: fp32 NCHW [B,3,224,224].
+ * Every convolution is a tcgen05 GEMM over NHWC fp16 activations with BatchNorm (inference statistics) folded:
+ *   w3 fp16 [width, cin]                  conv3 (1x1 transposed conv = per-pixel Linear), b3 fp32 [width]
+ *   w2 fp16 [width, 9*width]  (stride 1)  conv2 as a 3x3 convolution over im2col rows, column (ty, tx, ci) holds the
+ *                                         transposed-conv weight [ci, co, 2-ty, 2-tx]; b2 fp32 [width]
+ *      fp16 [4*width, 4*width] (stride 2) conv2 as the four-phase GEMM of VITAD_EPI_CONVT_RELU_F16; b2 fp32 [4*width]
+ *   w1 fp16 [cout, width]                 conv1; b1 fp32 [cout] = bn1 shift (+ the identity path's BatchNorm shift)
+ *   wup fp16 [cout, cin] or null          1x1 transposed conv of the identity path (`upsample`, :186-196); bup fp32
+ *                                         [cout] = its BatchNorm shift when stride 1, zeros when stride 2 (the shift
+ *                                         then belongs in b1: it reaches every output pixel, the convolution only
+ *                                         the even ones)
+ *   last_w fp16 [64, 9*64]                nearest-upsample + 7x7 stride-2 transposed conv + BatchNorm scale collapsed to
+ *                                         a 3x3 convolution on the 56x56 grid that produces a 4x4 pixel block x 3
+ *                                         channels per input pixel (row c*16+py*4+px, 48 live); last_b fp32 [64]
+ * Channel counts must be multiples of 32.  Workspace: vitad_resnet_decoder_workspace_bytes.
+ * ------------------------------------------------------------------------------------------ */
+#define VITAD_RESNET_MAX_BLOCKS 24
+typedef struct vitad_resnet_block {
+    int cin, width, cout, stride; /* stride 1 or 2 */
+    const void* w3;
+    const float* b3;
+    const void* w2;
+    const float* b2;
+    const void* w1;
+    const float* b1;
+    const void* wup;
+    const float* bup;
+} vitad_resnet_block;
+typedef struct vitad_resnet_decoder_weights {
+    int latent, hidden, feat, grid0, n_blocks, last_c;
+    const void* fc1_w;
+    const float* fc1_b;
+    const void* fc2_w;
+    const float* fc2_b;
+    vitad_resnet_block blocks[VITAD_RESNET_MAX_BLOCKS];
+    const void* last_w;
+    const float* last_b;
+} vitad_resnet_decoder_weights;
+size_t vitad_resnet_decoder_workspace_bytes(const vitad_resnet_decoder_weights* w, int batch);
+int vitad_resnet_decoder_forward(const vitad_resnet_decoder_weights* w, const float* latent, int batch, void* workspace,
+                                 size_t workspace_bytes, float* recon, void* stream);
 
 #ifdef __cplusplus
 }

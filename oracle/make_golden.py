@@ -253,6 +253,41 @@ def case_recon_validator():
          pixel_scores_sum=res["pixel_scores"].sum(axis=(1, 2, 3)), recons_sub=res["recons"][:, :, ::8, ::8])
 
 
+def case_resnet_decoder():
+    """DecoderResNetVariableEmbeddingSize(768) (CnnDecoder.py:158-196, imported unchanged) in eval mode on seeded latents."""
+    from src.classes.CnnDecoder import DecoderResNetVariableEmbeddingSize
+
+    dec = DecoderResNetVariableEmbeddingSize(embedding_size=768)
+    sd = W.make_resnet_decoder_state_dict(seed=43)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()})
+    dec.eval()
+    z = torch.randn(2, 768, generator=torch.Generator().manual_seed(1)) * 0.7
+    with torch.no_grad():
+        recon = dec(z)
+    save("resnet_decoder", recon_sub=recon[:, :, ::4, ::4].numpy(), recon_sum=recon.sum(dim=(2, 3)).numpy(),
+         state_dict_keys=np.array(sorted(dec.state_dict().keys())))
+
+
+def case_recon_validator_resnet():
+    """ValidatorRecon.valid_loop_mse with get_model('ae_deit') (DeiT stress weights + reverse-ResNet decoder), B=2."""
+    from src.pipeline.ValidatorRecon import ValidatorRecon
+    from src.util.ModelHelper import get_model
+
+    model = get_model("ae_deit", 224, requires_grad=True)
+    sd = {("encoder." + k): v for k, v in W.make_deit_state_dict(seed=11, stress=True).items()}
+    sd.update(W.make_resnet_decoder_state_dict(seed=43))
+    imgs = W.synthetic_images(seed=8, batch=2)
+    pl, il = synthetic_labels(2, seed=0)
+    batches = [(imgs, pl, il)]
+    props = {"dataset": "synthetic", "dataclass": "x", "fp_thres": 0.3}
+    val = ValidatorRecon(model, ListLoader(batches), props, weights_object=sd)
+    with torch.no_grad():
+        res = val.valid_loop_mse(batches)
+    save("recon_validator_resnet", image_scores=res["image_scores"], pixel_scores_sub=res["pixel_scores"][:, :, ::8, ::8],
+         pixel_scores_sum=res["pixel_scores"].sum(axis=(1, 2, 3)), recons_sub=res["recons"][:, :, ::8, ::8],
+         state_dict_keys=np.array(sorted(model.state_dict().keys())))
+
+
 CASES = {
     "deit": case_deit,
     "vit": case_vit,
@@ -262,6 +297,8 @@ CASES = {
     "nf_validator": case_nf_validator,
     "recon_l2": case_recon_l2,
     "recon_validator": case_recon_validator,
+    "resnet_decoder": case_resnet_decoder,
+    "recon_validator_resnet": case_recon_validator_resnet,
 }
 
 if __name__ == "__main__":

@@ -338,6 +338,46 @@ def small_decoder_forward(sd: dict, z: Tensor, prefix: str = "decoder.", fmap: i
     return h
 
 
+def _bn_eval(h: Tensor, sd: dict, name: str, eps: float = 1e-5) -> Tensor:
+    """nn.BatchNorm2d in eval mode (running statistics)."""
+    h = (h - sd[name + "running_mean"].view(1, -1, 1, 1)) / torch.sqrt(sd[name + "running_var"].view(1, -1, 1, 1) + eps)
+    return h * sd[name + "weight"].view(1, -1, 1, 1) + sd[name + "bias"].view(1, -1, 1, 1)
+
+
+RESNET_DECODER_LAYERS = (("layer4", 3, 2), ("layer3", 4, 2), ("layer2", 6, 2), ("layer1", 3, 1))  # name, blocks, last stride
+
+
+def resnet_decoder_forward(sd: dict, z: Tensor, prefix: str = "decoder.") -> Tensor:
+    """DecoderResNetVariableEmbeddingSize.forward in eval mode (src/classes/CnnDecoder.py:158-196) over
+    ReverseResNet._forward_cnns_only (src/classes/resnet/ReverseResNet.py:228-235) and Bottleneck.forward (:86-103):
+    fc1/fc2 + ReLU, unflatten to [2048,1,1], nearest upsample to 7x7, layer4..layer1 (the last block of a layer carries
+    the stride-2 conv2 and the `upsample` identity path, :186-209), nearest upsample to 112, de_conv1 (k7 s2 p3 op1),
+    bn1, tanh."""
+    p = prefix
+    h = F.relu(z @ sd[p + "fc1.0.weight"].t() + sd[p + "fc1.0.bias"])
+    h = F.relu(h @ sd[p + "fc2.0.weight"].t() + sd[p + "fc2.0.bias"])
+    h = h.reshape(z.shape[0], -1, 1, 1)
+    h = F.interpolate(h, size=7, mode="nearest")
+    for layer, blocks, last_stride in RESNET_DECODER_LAYERS:
+        for i in range(blocks):
+            b = f"{p}{layer}.{i}."
+            last = i == blocks - 1
+            stride = last_stride if last else 1
+            op = stride - 1  # output_padding 1 with stride 2 (:180), 0 for layer1's last block (:141-143)
+            out = F.relu(_bn_eval(F.conv_transpose2d(h, sd[b + "conv3.weight"]), sd, b + "bn3."))
+            out = F.conv_transpose2d(out, sd[b + "conv2.weight"], stride=stride, padding=1, output_padding=op)
+            out = F.relu(_bn_eval(out, sd, b + "bn2."))
+            out = _bn_eval(F.conv_transpose2d(out, sd[b + "conv1.weight"]), sd, b + "bn1.")
+            identity = h
+            if last:
+                identity = F.conv_transpose2d(h, sd[b + "upsample.0.weight"], stride=stride, output_padding=op)
+                identity = _bn_eval(identity, sd, b + "upsample.1.")
+            h = F.relu(out + identity)
+    h = F.interpolate(h, size=112, mode="nearest")
+    h = F.conv_transpose2d(h, sd[p + "de_conv1.weight"], stride=2, padding=3, output_padding=1)
+    return torch.tanh(_bn_eval(h, sd, p + "bn1."))
+
+
 def recon_l2_scores(recon: Tensor, images: Tensor):
     """MSELoss(reduction='none') → mean over channels (keepdim) → amax per image."""
     amap = ((recon - images) ** 2).mean(dim=1, keepdim=True)

@@ -25,7 +25,7 @@ def profile(fn, n=3):
     for _ in range(n): fn()
     buf = C.create_string_buffer(1 << 16); lib.vitad_profile_report(buf, len(buf)); lib.vitad_profile_enable(0)
     rows = [l.split() for l in buf.value.decode().strip().split("\n")]
-    for r in sorted(rows, key=lambda r: -float(r[2]))[:10]:
+    for r in sorted(rows, key=lambda r: -float(r[2]))[:14]:
         print(f"      {r[0]:34s} n/step {int(r[1])/n:5.1f} per-step {float(r[2])/n:8.1f} us")
 
 B = 32
@@ -60,4 +60,11 @@ with torch.no_grad():
     t = timeit(c4); print(f"config 4  DeiT + CNN decoder + L2 map: {t:.3f} ms -> {B/t*1e3:.0f} img/s")
     lat = ae.encoder(imgs).latent_space
     t = timeit(lambda: ae.decoder(lat)); print(f"   decoder alone (CUDA path; torch/cuDNN fp32 was 0.814 ms): {t:.3f} ms")
+    profile(lambda: ae.decoder(lat))
+    # config 4 with the reference's default decoder: DeiT + reverse-ResNet decoder (vitad_resnet_decoder_forward) + L2 map
+    ae = get_model("ae_deit", 224, requires_grad=True)
+    ae.decoder.load_state_dict({k[len("decoder."):]: v for k, v in W.make_resnet_decoder_state_dict(43).items()})
+    ae = ae.cuda().eval()
+    t = timeit(c4); print(f"config 4  DeiT + reverse-ResNet decoder + L2 map: {t:.3f} ms -> {B/t*1e3:.0f} img/s")
+    t = timeit(lambda: ae.decoder(lat)); print(f"   reverse-ResNet decoder alone: {t:.3f} ms ({8.18e9*B/t/1e9:.1f} TFLOP/s of the reference's 8.18 GFLOP/img)")
     profile(lambda: ae.decoder(lat))

@@ -14,6 +14,7 @@
 //     and scatters each phase to its output pixel;
 //   * the last layer has 3 output channels: a CUDA-core kernel (1296 FMAs per 2x2 output block) with the folded
 //     BatchNorm and tanh, writing the reconstruction as fp32 NCHW (what the validator returns and the L2-map kernel reads).
+#include <algorithm>
 #include <atomic>
 
 #include "host_util.cuh"
@@ -134,6 +135,40 @@ __global__ void __launch_bounds__(256) convt_last_kernel(const __half* __restric
         }
 }
 
+// 3x3 im2col on a g x g grid per image, zero padding: in fp16 [M][cw] -> out fp16 [M][9*cw], column (tap, c),
+// tap = ty*3+tx reads pixel (y+ty-1, x+tx-1).  One thread moves 8 channels (16 bytes).
+__global__ void __launch_bounds__(256) dec_im2col3x3_kernel(const __half* __restrict__ in, __half* __restrict__ out, int cw,
+                                                            int g, size_t total) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int v_per_tap = cw >> 3;
+    const int v = static_cast<int>(idx % v_per_tap);
+    const size_t r = idx / v_per_tap;
+    const int tap = static_cast<int>(r % 9);
+    const size_t t = r / 9;
+    const int p = static_cast<int>(t % (static_cast<size_t>(g) * g));
+    const int py = p / g, px = p - py * g;
+    const int y = py + tap / 3 - 1, x = px + tap % 3 - 1;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < g && x >= 0 && x < g)
+        val = *reinterpret_cast<const uint4*>(in + (t - p + static_cast<size_t>(y) * g + x) * cw + v * 8);
+    *reinterpret_cast<uint4*>(out + (t * 9 + tap) * cw + v * 8) = val;
+}
+
+// nn.Upsample(size=g, mode="nearest") of a 1x1 feature map (ReverseResNet.py:135,229): out[(b, p)][c] = in[b][c].
+__global__ void __launch_bounds__(256) dec_replicate_kernel(const __half* __restrict__ in, __half* __restrict__ out, int pix,
+                                                            int c8, size_t total) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int v = static_cast<int>(idx % c8);
+    const size_t b = idx / c8 / pix;
+    reinterpret_cast<uint4*>(out)[idx] = reinterpret_cast<const uint4*>(in)[b * c8 + v];
+}
+
 namespace {
 struct Carve {
     uint8_t* p;
@@ -162,6 +197,57 @@ DecWs carve(const vitad_cnn_decoder_weights& w, int batch, void* base) {
     }
     s.total = c.used;
     return s;
+}
+struct ResWs {
+    void *lat, *h, *f, *x[2], *h1, *col, *h2, *up;
+    size_t total;
+};
+ResWs carve_resnet(const vitad_resnet_decoder_weights& w, int batch, void* base) {
+    size_t x_el = static_cast<size_t>(batch) * w.grid0 * w.grid0 * w.feat, h1_el = 0, col_el = 0, h2_el = 0, up_el = 0;
+    int g = w.grid0;
+    for (int i = 0; i < w.n_blocks; ++i) {
+        const vitad_resnet_block& b = w.blocks[i];
+        const size_t M = static_cast<size_t>(batch) * g * g;
+        const size_t Mo = b.stride == 2 ? 4 * M : M;
+        x_el = std::max(x_el, std::max(M * b.cin, Mo * b.cout));
+        h1_el = std::max(h1_el, M * b.width);
+        col_el = std::max(col_el, M * b.width * (b.stride == 2 ? 4 : 9));
+        h2_el = std::max(h2_el, Mo * b.width);
+        if (b.wup) up_el = std::max(up_el, M * b.cout);
+        if (b.stride == 2) g *= 2;
+    }
+    col_el = std::max(col_el, static_cast<size_t>(batch) * g * g * 9 * w.last_c);
+    Carve c{static_cast<uint8_t*>(base)};
+    ResWs s;
+    s.lat = c.take(static_cast<size_t>(batch) * w.latent * 2);
+    s.h = c.take(static_cast<size_t>(batch) * w.hidden * 2);
+    s.f = c.take(static_cast<size_t>(batch) * w.feat * 2);
+    s.x[0] = c.take(x_el * 2);
+    s.x[1] = c.take(x_el * 2);
+    s.h1 = c.take(h1_el * 2);
+    s.col = c.take(col_el * 2);
+    s.h2 = c.take(h2_el * 2);
+    s.up = c.take(up_el * 2);
+    s.total = c.used;
+    return s;
+}
+int check_resnet(const vitad_resnet_decoder_weights& w) {
+    VITAD_REQUIRE(w.latent % 16 == 0 && w.hidden % 32 == 0 && w.feat % 32 == 0 && w.grid0 > 0 && w.n_blocks > 0 &&
+                      w.n_blocks <= VITAD_RESNET_MAX_BLOCKS && w.last_c == 64 && w.fc1_w && w.fc1_b && w.fc2_w && w.fc2_b &&
+                      w.last_w && w.last_b,
+                  VITAD_ERR_SHAPE, "unsupported reverse-ResNet decoder geometry");
+    int cin = w.feat;
+    for (int i = 0; i < w.n_blocks; ++i) {
+        const vitad_resnet_block& b = w.blocks[i];
+        VITAD_REQUIRE(b.cin == cin && b.width % 32 == 0 && b.cout % 32 == 0 && b.width > 0 && b.cout > 0 &&
+                          (b.stride == 1 || b.stride == 2) && b.w3 && b.b3 && b.w2 && b.b2 && b.w1 && b.b1,
+                      VITAD_ERR_SHAPE, "reverse-ResNet block %d: channels must chain and be multiples of 32", i);
+        VITAD_REQUIRE((b.wup && b.bup) || (!b.wup && b.stride == 1 && b.cin == b.cout), VITAD_ERR_SHAPE,
+                      "reverse-ResNet block %d: an identity path without a convolution needs stride 1 and cin == cout", i);
+        cin = b.cout;
+    }
+    VITAD_REQUIRE(cin == w.last_c, VITAD_ERR_SHAPE, "the last block must end in %d channels", w.last_c);
+    return VITAD_OK;
 }
 }  // namespace
 }  // namespace vitad
@@ -230,4 +316,108 @@ extern "C" int vitad_cnn_decoder_forward(const vitad_cnn_decoder_weights* wp, co
         g_launches.fetch_add(1);
     }
     return VITAD_OK;
+}
+
+extern "C" size_t vitad_resnet_decoder_workspace_bytes(const vitad_resnet_decoder_weights* w, int batch) {
+    if (!w || batch <= 0 || check_resnet(*w)) return 0;
+    return carve_resnet(*w, batch, nullptr).total;
+}
+
+extern "C" int vitad_resnet_decoder_forward(const vitad_resnet_decoder_weights* wp, const float* latent, int batch,
+                                            void* workspace, size_t workspace_bytes, float* recon, void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(wp && latent && workspace && recon && batch > 0, VITAD_ERR_ARG, "null pointer or empty batch");
+    const vitad_resnet_decoder_weights& w = *wp;
+    if ((rc = check_resnet(w))) return rc;
+    VITAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && aligned16(latent) && aligned16(recon), VITAD_ERR_ALIGN,
+                  "decoder buffers alignment");
+    ResWs ws = carve_resnet(w, batch, workspace);
+    VITAD_REQUIRE(workspace_bytes >= ws.total, VITAD_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.total);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    auto blocks_for = [](size_t n) { return dim3(static_cast<unsigned>((n + 255) / 256)); };
+    {
+        ProfScope prof("dec_cast", s);
+        const size_t n4 = static_cast<size_t>(batch) * w.latent / 4;
+        VITAD_CUDA_OK(launch_pdl(cast_f16_kernel, blocks_for(n4), dim3(256), 0, s, latent, static_cast<__half*>(ws.lat), n4));
+        g_launches.fetch_add(1);
+    }
+    vitad_linear_args a;
+    auto gemm = [&](const void* A, int M, int K, const void* W, const float* bias, int N, int epi, void* out, int ldo) {
+        memset(&a, 0, sizeof(a));
+        a.a = A, a.w = W, a.bias = bias, a.m = M, a.n = N, a.k = K, a.lda = K, a.ldw = K, a.epilogue = epi, a.out = out, a.ldo = ldo;
+    };
+    // fc1, fc2 (CnnDecoder.py:171-179, 185-186)
+    gemm(ws.lat, batch, w.latent, w.fc1_w, w.fc1_b, w.hidden, VITAD_EPI_BIAS_RELU_F16, ws.h, w.hidden);
+    if ((rc = vitad_linear_f16(&a, s))) return rc;
+    gemm(ws.h, batch, w.hidden, w.fc2_w, w.fc2_b, w.feat, VITAD_EPI_BIAS_RELU_F16, ws.f, w.feat);
+    if ((rc = vitad_linear_f16(&a, s))) return rc;
+    int g = w.grid0;
+    {
+        ProfScope prof("dec_replicate", s);
+        const size_t total = static_cast<size_t>(batch) * g * g * (w.feat / 8);
+        VITAD_CUDA_OK(launch_pdl(dec_replicate_kernel, blocks_for(total), dim3(256), 0, s, static_cast<const __half*>(ws.f),
+                                 static_cast<__half*>(ws.x[0]), g * g, w.feat / 8, total));
+        g_launches.fetch_add(1);
+    }
+    int cur = 0;
+    for (int i = 0; i < w.n_blocks; ++i) {
+        const vitad_resnet_block& b = w.blocks[i];
+        const int M = batch * g * g;
+        const void* x = ws.x[cur];
+        void* y = ws.x[cur ^ 1];
+        // conv3 + bn3 + relu (ReverseResNet.py:89-91)
+        gemm(x, M, b.cin, b.w3, b.b3, b.width, VITAD_EPI_BIAS_RELU_F16, ws.h1, b.width);
+        if ((rc = vitad_linear_f16(&a, s))) return rc;
+        // conv2 + bn2 + relu (:92-94)
+        int Mo = M;
+        if (b.stride == 1) {
+            {
+                ProfScope prof("dec_im2col3", s);
+                const size_t total = static_cast<size_t>(M) * 9 * (b.width / 8);
+                VITAD_CUDA_OK(launch_pdl(dec_im2col3x3_kernel, blocks_for(total), dim3(256), 0, s,
+                                         static_cast<const __half*>(ws.h1), static_cast<__half*>(ws.col), b.width, g, total));
+                g_launches.fetch_add(1);
+            }
+            gemm(ws.col, M, 9 * b.width, b.w2, b.b2, b.width, VITAD_EPI_BIAS_RELU_F16, ws.h2, b.width);
+            if ((rc = vitad_linear_f16(&a, s))) return rc;
+        } else {
+            {
+                ProfScope prof("dec_im2col", s);
+                const size_t total8 = static_cast<size_t>(M) * 4 * (b.width / 8);
+                VITAD_CUDA_OK(launch_pdl(im2col2x2_kernel, blocks_for(total8), dim3(256), 0, s,
+                                         static_cast<const __half*>(ws.h1), static_cast<__half*>(ws.col), g, b.width, total8));
+                g_launches.fetch_add(1);
+            }
+            gemm(ws.col, M, 4 * b.width, b.w2, b.b2, 4 * b.width, VITAD_EPI_CONVT_RELU_F16, ws.h2, 2 * b.width);
+            a.convt_w = g;
+            if ((rc = vitad_linear_f16(&a, s))) return rc;
+            Mo = 4 * M;
+        }
+        // identity path (:98-99, 186-196): a 1x1 transposed convolution on the input grid, or the block input itself
+        const void* resid = x;
+        if (b.wup) {
+            gemm(x, M, b.cin, b.wup, b.bup, b.cout, VITAD_EPI_BIAS_F16, ws.up, b.cout);
+            if ((rc = vitad_linear_f16(&a, s))) return rc;
+            resid = ws.up;
+        }
+        // conv1 + bn1 + identity + relu (:95-101)
+        gemm(ws.h2, Mo, b.width, b.w1, b.b1, b.cout, VITAD_EPI_RES16_RELU_F16, y, b.cout);
+        a.resid16 = resid, a.ldr = b.cout, a.res_grid = b.stride == 2 ? g : 0;
+        if ((rc = vitad_linear_f16(&a, s))) return rc;
+        cur ^= 1;
+        if (b.stride == 2) g *= 2;
+    }
+    // image head (CnnDecoder.py:189-194) as a 3x3 convolution producing 4x4 pixel blocks
+    const int M = batch * g * g;
+    {
+        ProfScope prof("dec_im2col3", s);
+        const size_t total = static_cast<size_t>(M) * 9 * (w.last_c / 8);
+        VITAD_CUDA_OK(launch_pdl(dec_im2col3x3_kernel, blocks_for(total), dim3(256), 0, s,
+                                 static_cast<const __half*>(ws.x[cur]), static_cast<__half*>(ws.col), w.last_c, g, total));
+        g_launches.fetch_add(1);
+    }
+    gemm(ws.col, M, 9 * w.last_c, w.last_w, w.last_b, 64, VITAD_EPI_TANH_PIX4_F32, recon, 0);
+    a.convt_w = g;
+    return vitad_linear_f16(&a, s);
 }

@@ -536,6 +536,90 @@ struct SEpiConvT {
     }
 };
 
+// Tail of a reverse-ResNet Bottleneck (ReverseResNet.py:86-103): out_f16 = relu(acc + bias + identity).
+// rg == 0: identity row = output row.  rg = g > 0: the identity path was computed on the g x g input grid (stride-2 1x1
+// transposed convolution, :190-195) and lands on the even pixels of the 2g x 2g output grid; the other pixels only see
+// its BatchNorm shift, which the host folds into `bias`.
+struct SEpiResReluH {
+    static constexpr bool kRowCtx = true;
+    static constexpr int kDefaultEpiWarps = 8;
+    using Pre = uint2;
+    using ColC = float4;
+    const float* bias;
+    const __half* resid;
+    __half* out;
+    int ldo, ldr, M, N, rg;
+    // ctx.a = residual row (-1: none), ctx.b = -1 when the output row is out of range
+    __device__ __forceinline__ RowCtx row_ctx(int row) const {
+        if (row >= M) return RowCtx{-1, -1};
+        if (rg == 0) return RowCtx{row, 0};
+        const int G = 2 * rg;
+        const int x = row % G;
+        const int t = row / G;
+        const int y = t % G;
+        const int b = t / G;
+        if ((x | y) & 1) return RowCtx{-1, 0};
+        return RowCtx{(b * rg + (y >> 1)) * rg + (x >> 1), 0};
+    }
+    __device__ __forceinline__ bool direct(int) const { return false; }
+    __device__ __forceinline__ void direct_unit(int, RowCtx, int, const uint32_t (&)[32]) const {}
+    __device__ __forceinline__ Pre prefetch(int, RowCtx ctx, int col) const {
+        return (ctx.a >= 0 && col < N) ? *reinterpret_cast<const uint2*>(resid + static_cast<size_t>(ctx.a) * ldr + col)
+                                       : make_uint2(0u, 0u);
+    }
+    __device__ __forceinline__ ColC col_const(int col) const {
+        return col < N ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ void store(int row, RowCtx ctx, int col, float4 a, Pre r, ColC b) const {
+        if (ctx.b < 0 || col >= N) return;
+        const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+        const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        uint2 u;
+        u.x = pack_h2(fmaxf(a.x + b.x + r0.x, 0.f), fmaxf(a.y + b.y + r0.y, 0.f));
+        u.y = pack_h2(fmaxf(a.z + b.z + r1.x, 0.f), fmaxf(a.w + b.w + r1.y, 0.f));
+        *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * ldo + col) = u;
+    }
+};
+
+// Image head of the reverse-ResNet decoder (CnnDecoder.py:189-194: nearest upsample 56 -> 112, ConvTranspose2d(64 -> 3,
+// k7, s2, p3, op1), BatchNorm2d, Tanh) after the host collapsed it to a 3x3 convolution on the Wg x Wg grid: GEMM row =
+// pixel (b, J, I), column = c*16 + py*4 + px; out[b][c][4J+py][4I+px] = tanh(acc + bias).  A thread's 4 columns are the
+// 4 px of one (c, py): one 16-byte store.
+struct SEpiTanhPix4 {
+    static constexpr bool kRowCtx = true;
+    static constexpr int kDefaultEpiWarps = 8;
+    using Pre = NoPre;
+    using ColC = float4;
+    const float* bias;  // [64], 48 live
+    float* out;         // fp32 NCHW [B, 3, 4Wg, 4Wg]
+    int M, Wg;
+    // ctx.a = b*3*(4Wg)^2/4 ... kept as two ints: a = b, b = J*Wg + I (-1: out of range)
+    __device__ __forceinline__ RowCtx row_ctx(int row) const {
+        if (row >= M) return RowCtx{0, -1};
+        const int pix = Wg * Wg;
+        const int b = row / pix;
+        return RowCtx{b, row - b * pix};
+    }
+    __device__ __forceinline__ bool direct(int) const { return false; }
+    __device__ __forceinline__ void direct_unit(int, RowCtx, int, const uint32_t (&)[32]) const {}
+    __device__ __forceinline__ Pre prefetch(int, RowCtx, int) const { return NoPre{}; }
+    __device__ __forceinline__ ColC col_const(int col) const {
+        return col < 48 ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ void store(int, RowCtx ctx, int col, float4 a, Pre, ColC b) const {
+        if (ctx.b < 0 || col >= 48) return;
+        const int c = col >> 4, py = (col >> 2) & 3;
+        const int J = ctx.b / Wg, I = ctx.b - J * Wg;
+        const int S = 4 * Wg;
+        float4 o;
+        o.x = tanhf(a.x + b.x);
+        o.y = tanhf(a.y + b.y);
+        o.z = tanhf(a.z + b.z);
+        o.w = tanhf(a.w + b.w);
+        *reinterpret_cast<float4*>(out + ((static_cast<size_t>(ctx.a) * 3 + c) * S + 4 * J + py) * S + 4 * I) = o;
+    }
+};
+
 // Plain fp32 output (+ optional bias), any N and pitch: used by tests and small projections.
 struct SEpiBiasF32 {
     static constexpr bool kRowCtx = false;

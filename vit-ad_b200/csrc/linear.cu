@@ -102,6 +102,12 @@ static int dispatch_staged(const vitad_linear_args& a, cudaStream_t stream) {
             return launch_gemm_staged<BLOCK_N>(a, SEpiBiasF32{a.bias, static_cast<float*>(a.out), a.ldo, a.m, a.n}, stream);
         case VITAD_EPI_CONVT_RELU_F16:
             return launch_gemm_staged<BLOCK_N>(a, SEpiConvT{a.bias, static_cast<__half*>(a.out), a.m, a.n, a.convt_w}, stream);
+        case VITAD_EPI_RES16_RELU_F16:
+            return launch_gemm_staged<BLOCK_N>(a, SEpiResReluH{a.bias, static_cast<const __half*>(a.resid16),
+                                                               static_cast<__half*>(a.out), a.ldo, a.ldr, a.m, a.n, a.res_grid},
+                                               stream);
+        case VITAD_EPI_TANH_PIX4_F32:
+            return launch_gemm_staged<BLOCK_N>(a, SEpiTanhPix4{a.bias, static_cast<float*>(a.out), a.m, a.convt_w}, stream);
         default:
             set_error("unknown epilogue %d", a.epilogue);
             return VITAD_ERR_ARG;
@@ -266,6 +272,16 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
             VITAD_REQUIRE(a.out && aligned16(a.out) && a.n % 128 == 0 && a.convt_w > 0 && a.m % (a.convt_w * a.convt_w) == 0,
                           VITAD_ERR_SHAPE, "conv-transpose epilogue needs N = 4*Cp with Cp %% 32 == 0 and M = B*Wg*Wg");
             break;
+        case VITAD_EPI_RES16_RELU_F16:
+            VITAD_REQUIRE(a.out && a.resid16 && aligned16(a.out) && aligned16(a.resid16) && a.ldo % 8 == 0 && a.ldo >= a.n &&
+                              a.ldr % 8 == 0 && a.ldr >= a.n && a.res_grid >= 0 &&
+                              (a.res_grid == 0 || a.m % (4 * a.res_grid * a.res_grid) == 0),
+                          VITAD_ERR_ALIGN, "fp16 residual epilogue: aligned out/resid16, pitches %% 8, M = B*(2*res_grid)^2");
+            break;
+        case VITAD_EPI_TANH_PIX4_F32:
+            VITAD_REQUIRE(a.out && aligned16(a.out) && a.n == 64 && a.convt_w > 0 && a.m % (a.convt_w * a.convt_w) == 0,
+                          VITAD_ERR_SHAPE, "image-head epilogue needs N = 64 (48 live) and M = B*Wg*Wg");
+            break;
         case VITAD_EPI_PATCH_EMBED:
             VITAD_REQUIRE(a.out && a.pos && aligned16(a.out) && aligned16(a.pos) && a.patches > 0 &&
                               a.m % a.patches == 0 && a.prefix >= 0,
@@ -276,7 +292,8 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // the conv-transpose scatter exists only as a staged epilogue of the CTA-pair kernel (which handles any M)
-    const bool pair = (g_use_pair.load() && a.m > kBlockM) || a.epilogue == VITAD_EPI_CONVT_RELU_F16;
+    const bool pair = (g_use_pair.load() && a.m > kBlockM) || a.epilogue == VITAD_EPI_CONVT_RELU_F16 ||
+                      a.epilogue == VITAD_EPI_RES16_RELU_F16 || a.epilogue == VITAD_EPI_TANH_PIX4_F32;
     // block_n is a hint: widths the selected kernel does not instantiate fall back to the library's choice
     const bool hint_ok = pair ? (a.block_n == 128 || a.block_n == 256) : (a.block_n == 96 || a.block_n == 128 || a.block_n == 256);
     const int bn = hint_ok ? a.block_n : (pair ? pick_block_n_pair(a.m, a.n) : pick_block_n_single(a.m, a.n));

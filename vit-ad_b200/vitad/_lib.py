@@ -51,6 +51,8 @@ EPI_PATCH_EMBED = 4
 EPI_F32 = 5
 EPI_BIAS_RELU_F16 = 6
 EPI_CONVT_RELU_F16 = 7
+EPI_RES16_RELU_F16 = 8
+EPI_TANH_PIX4_F32 = 9
 
 
 class LinearArgs(C.Structure):
@@ -83,6 +85,9 @@ class LinearArgs(C.Structure):
         ("win_tokens", C.c_int),
         ("tok2win", C.c_void_p),
         ("convt_w", C.c_int),
+        ("resid16", C.c_void_p),
+        ("ldr", C.c_int),
+        ("res_grid", C.c_int),
     ]
 
 
@@ -221,6 +226,26 @@ lib.vitad_cnn_decoder_workspace_bytes.argtypes = [C.POINTER(CnnDecoderWeights), 
 lib.vitad_cnn_decoder_workspace_bytes.restype = _sz
 lib.vitad_cnn_decoder_forward.argtypes = [C.POINTER(CnnDecoderWeights), _vp, _i, _vp, _sz, _vp, _vp]
 lib.vitad_cnn_decoder_forward.restype = _i
+
+# ------------------------------------------------------------------- reverse-ResNet decoder
+RESNET_MAX_BLOCKS = 24
+
+
+class ResnetBlock(C.Structure):
+    _fields_ = [("cin", _i), ("width", _i), ("cout", _i), ("stride", _i), ("w3", _vp), ("b3", _vp), ("w2", _vp),
+                ("b2", _vp), ("w1", _vp), ("b1", _vp), ("wup", _vp), ("bup", _vp)]
+
+
+class ResnetDecoderWeights(C.Structure):
+    _fields_ = [("latent", _i), ("hidden", _i), ("feat", _i), ("grid0", _i), ("n_blocks", _i), ("last_c", _i),
+                ("fc1_w", _vp), ("fc1_b", _vp), ("fc2_w", _vp), ("fc2_b", _vp), ("blocks", ResnetBlock * RESNET_MAX_BLOCKS),
+                ("last_w", _vp), ("last_b", _vp)]
+
+
+lib.vitad_resnet_decoder_workspace_bytes.argtypes = [C.POINTER(ResnetDecoderWeights), _i]
+lib.vitad_resnet_decoder_workspace_bytes.restype = _sz
+lib.vitad_resnet_decoder_forward.argtypes = [C.POINTER(ResnetDecoderWeights), _vp, _i, _vp, _sz, _vp, _vp]
+lib.vitad_resnet_decoder_forward.restype = _i
 
 MDN_KA = 784  # K extent of the packed MDN operands (768 + 16)
 

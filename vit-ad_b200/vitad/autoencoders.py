@@ -2,11 +2,11 @@
 (src/classes/transformer/TransformerAutoEncoder.py:152-194, src/classes/CnnAutoEncoder.py:18-74,
 src/classes/CnnDecoder.py:16-117).
 
-The encoder is the CUDA DeiT, the small CNN decoder one C-ABI call (`vitad_cnn_decoder_forward`: tcgen05 GEMMs for the two
-Linear layers and for each stride-2 transposed convolution, BatchNorm folded, NHWC fp16 activations), the per-pixel L2
-map + per-image max the CUDA kernel `vitad_l2_map_score`.  The nn.Modules only hold the parameters under the
-reference's names, so reference checkpoints load unchanged.  Only the small CNN decoder (`ae_deit_small`,
-decoder="cnn") is provided; the reverse-ResNet decoder raises.
+The encoder is the CUDA DeiT, each decoder one C-ABI call (`vitad_cnn_decoder_forward` for `ae_deit_small`,
+`vitad_resnet_decoder_forward` for `ae_deit`'s reverse ResNet: tcgen05 GEMMs for the Linear layers and for every
+(transposed) convolution, BatchNorm folded, NHWC fp16 activations), the per-pixel L2 map + per-image max the CUDA kernel
+`vitad_l2_map_score`.  The nn.Modules only hold the parameters under the reference's names, so reference checkpoints
+load unchanged.
 """
 from __future__ import annotations
 
@@ -145,16 +145,199 @@ class DecoderVanillaCNN(nn.Module):
         return recon
 
 
+def _convt(cin, cout, k, stride=1, padding=0, output_padding=0):
+    return nn.ConvTranspose2d(cin, cout, kernel_size=k, stride=stride, padding=padding, output_padding=output_padding,
+                              bias=False)
+
+
+class Bottleneck(nn.Module):
+    """Parameter container with the attribute names of ReverseResNet.py:46-84 (conv3/bn3 run first, conv1/bn1 last)."""
+
+    expansion = 4
+
+    def __init__(self, inplanes: int, planes: int, stride: int = 1, output_padding: int = 0, upsample=None) -> None:
+        super().__init__()
+        self.conv3 = _convt(planes * self.expansion, planes, 1)
+        self.bn3 = nn.BatchNorm2d(planes)
+        self.conv2 = _convt(planes, planes, 3, stride, 1, output_padding)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv1 = _convt(planes, inplanes, 1)
+        self.bn1 = nn.BatchNorm2d(inplanes)
+        self.upsample = upsample
+        self.stride = stride
+
+
+def _fold(bn: nn.BatchNorm2d):
+    s = bn.weight.detach().float().cpu() / torch.sqrt(bn.running_var.detach().float().cpu() + bn.eps)
+    return s, bn.bias.detach().float().cpu() - bn.running_mean.detach().float().cpu() * s
+
+
+def pack_resnet_decoder(dec: "DecoderResNetVariableEmbeddingSize") -> dict:
+    """BatchNorm-folded fp32 GEMM matrices in the layouts include/vitad.h documents for vitad_resnet_decoder_weights
+    (device-independent; `_pack` casts and uploads them).  Weight layout of ConvTranspose2d: [C_in, C_out, ky, kx]."""
+    blocks = []
+    for layer in (dec.layer4, dec.layer3, dec.layer2, dec.layer1):
+        for blk in layer:
+            s3, t3 = _fold(blk.bn3)
+            s2, t2 = _fold(blk.bn2)
+            s1, t1 = _fold(blk.bn1)
+            w3 = blk.conv3.weight.detach().float().cpu()[:, :, 0, 0].t() * s3.view(-1, 1)  # [width, cin]
+            wt = blk.conv2.weight.detach().float().cpu() * s2.view(1, -1, 1, 1)  # [ci, co, ky, kx]
+            width = wt.shape[0]
+            if blk.stride == 1:
+                # transposed conv (s1, p1) = convolution with the flipped kernel: tap (ty, tx) reads pixel (y+ty-1, x+tx-1)
+                # and meets kernel element (2-ty, 2-tx)
+                w2 = wt.flip(2, 3).permute(1, 2, 3, 0).reshape(width, 9 * width)  # [co, (ty, tx, ci)]
+                b2 = t2
+            else:
+                # four output phases (a, c) over the 2x2 input neighbourhood (di, dj): ky = a + 1 - 2 di (csrc/decoder.cu)
+                w2 = torch.zeros(4 * width, 4 * width)
+                b2 = t2.repeat(4)
+                for a in range(2):
+                    for c in range(2):
+                        r0 = (a * 2 + c) * width
+                        for di in range(2):
+                            for dj in range(2):
+                                ky, kx = a + 1 - 2 * di, c + 1 - 2 * dj
+                                if 0 <= ky <= 2 and 0 <= kx <= 2:
+                                    k0 = (di * 2 + dj) * width
+                                    w2[r0:r0 + width, k0:k0 + width] = wt[:, :, ky, kx].t()
+            w1 = blk.conv1.weight.detach().float().cpu()[:, :, 0, 0].t() * s1.view(-1, 1)  # [cout, width]
+            b1 = t1.clone()
+            wup = bup = None
+            if blk.upsample is not None:
+                su, tu = _fold(blk.upsample[1])
+                wup = blk.upsample[0].weight.detach().float().cpu()[:, :, 0, 0].t() * su.view(-1, 1)  # [cout, cin]
+                if blk.stride == 2:  # the shift reaches every output pixel, the convolution only the even ones
+                    b1 = b1 + tu
+                    bup = torch.zeros_like(tu)
+                else:
+                    bup = tu
+            blocks.append(dict(cin=w3.shape[1], width=width, cout=w1.shape[0], stride=blk.stride, w3=w3, b3=t3, w2=w2,
+                               b2=b2, w1=w1, b1=b1, wup=wup, bup=bup))
+    # image head: nearest upsample (56 -> 112) + ConvTranspose2d(k7, s2, p3, op1) + bn1.  Output row y = 4J + py gets input
+    # row iy = 2j + r (r in {0,1}: both are pixel j of the 56-grid) through kernel row ky = y + 3 - 2 iy
+    # = 4 (J - j) + py + 3 - 2 r; with j = J + ty - 1 that is a 3x3 convolution whose weights are sums over r.
+    sl, tl = _fold(dec.bn1)
+    wl = dec.de_conv1.weight.detach().float().cpu() * sl.view(1, -1, 1, 1)  # [ci, 3, 7, 7]
+    cl = wl.shape[0]
+    last = torch.zeros(3, 4, 4, 3, 3, cl)  # [c, py, px, ty, tx, ci]
+    for py in range(4):
+        for ty in range(3):
+            kys = [k for k in (4 * (1 - ty) + py + 3 - 2 * r for r in range(2)) if 0 <= k <= 6]
+            for px in range(4):
+                for tx in range(3):
+                    kxs = [k for k in (4 * (1 - tx) + px + 3 - 2 * r for r in range(2)) if 0 <= k <= 6]
+                    for ky in kys:
+                        for kx in kxs:
+                            last[:, py, px, ty, tx, :] += wl[:, :, ky, kx].t()
+    last_w = torch.zeros(64, 9 * cl)
+    last_w[:48] = last.reshape(48, 9 * cl)
+    last_b = torch.zeros(64)
+    last_b[:48] = tl.view(3, 1).expand(3, 16).reshape(48)
+    fc1, fc2 = dec.fc1[0], dec.fc2[0]
+    return dict(fc1_w=fc1.weight.detach().float().cpu(), fc1_b=fc1.bias.detach().float().cpu(), fc2_w=fc2.weight.detach().float().cpu(),
+                fc2_b=fc2.bias.detach().float().cpu(), blocks=blocks, last_w=last_w, last_b=last_b, last_c=cl, grid0=7)
+
+
+class DecoderResNetVariableEmbeddingSize(nn.Module):
+    """Reverse-ResNet decoder (CnnDecoder.py:158-196 over ReverseResNet.py:106-209) with the reference's attribute names
+    and `state_dict` layout: fc1/fc2, layer4 (3 blocks, 2048 -> 1024 ch, 7 -> 14 px), layer3 (4, -> 512, 28), layer2
+    (6, -> 256, 56), layer1 (3, -> 64), de_conv1 + bn1 + tanh.  The modules are parameter containers; forward is one
+    C-ABI call (`vitad_resnet_decoder_forward`).  BatchNorm uses its running statistics (the validators call
+    `model.eval()`, ValidatorRecon.py:104)."""
+
+    def __init__(self, embedding_size: int) -> None:
+        super().__init__()
+        self.inplanes = 2048
+        self.de_conv1 = _convt(64, 3, 7, stride=2, padding=3, output_padding=1)
+        self.bn1 = nn.BatchNorm2d(3)
+        self.layer4 = self._make_layer(512, 3, stride=2)
+        self.layer3 = self._make_layer(256, 4, stride=2)
+        self.layer2 = self._make_layer(128, 6, stride=2)
+        self.layer1 = self._make_layer(64, 3, output_padding=0, last_block_dim=64)
+        hidden = 2 * embedding_size
+        self.fc1 = nn.Sequential(nn.Linear(embedding_size, hidden), nn.ReLU(inplace=True))
+        self.fc2 = nn.Sequential(nn.Linear(hidden, 2048), nn.ReLU(inplace=True))
+
+    @staticmethod
+    def _make_layer(planes, blocks, stride=1, output_padding=1, last_block_dim=0):
+        """ReverseResNet.py:169-209: `blocks - 1` plain Bottlenecks, then the block that changes width / resolution."""
+        inplanes = planes * Bottleneck.expansion
+        if last_block_dim == 0:
+            last_block_dim = inplanes // 2
+        upsample = nn.Sequential(_convt(inplanes, last_block_dim, 1, stride, 0, output_padding),
+                                 nn.BatchNorm2d(last_block_dim))
+        layers = [Bottleneck(inplanes, planes) for _ in range(1, blocks)]
+        layers.append(Bottleneck(last_block_dim, planes, stride, output_padding, upsample))
+        return nn.Sequential(*layers)
+
+    # -- CUDA path ---------------------------------------------------------------------------------
+    _packed = None
+
+    def _apply(self, fn, recurse=True):
+        self._packed = None
+        return super()._apply(fn, recurse)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        self._packed = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def _pack(self, device):
+        keep = []
+
+        def dev(t, dtype):
+            t = t.to(device=device, dtype=dtype).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        pk = pack_resnet_decoder(self)
+        w = _lib.ResnetDecoderWeights()
+        w.latent, w.hidden, w.feat = pk["fc1_w"].shape[1], pk["fc1_w"].shape[0], pk["fc2_w"].shape[0]
+        w.grid0, w.n_blocks, w.last_c = pk["grid0"], len(pk["blocks"]), pk["last_c"]
+        w.fc1_w, w.fc1_b = dev(pk["fc1_w"], torch.float16), dev(pk["fc1_b"], torch.float32)
+        w.fc2_w, w.fc2_b = dev(pk["fc2_w"], torch.float16), dev(pk["fc2_b"], torch.float32)
+        for i, b in enumerate(pk["blocks"]):
+            cb = w.blocks[i]
+            cb.cin, cb.width, cb.cout, cb.stride = b["cin"], b["width"], b["cout"], b["stride"]
+            for n in ("w3", "w2", "w1"):
+                setattr(cb, n, dev(b[n], torch.float16))
+            for n in ("b3", "b2", "b1"):
+                setattr(cb, n, dev(b[n], torch.float32))
+            if b["wup"] is not None:
+                cb.wup, cb.bup = dev(b["wup"], torch.float16), dev(b["bup"], torch.float32)
+        w.last_w, w.last_b = dev(pk["last_w"], torch.float16), dev(pk["last_b"], torch.float32)
+        self._packed = dict(w=w, keep=keep, device=device, ws=None, ws_batch=0)
+
+    def forward(self, x, indices=None):
+        """latent [B, embedding_size] → reconstruction fp32 [B, 3, 224, 224] (tanh range)."""
+        if not x.is_cuda:
+            raise RuntimeError("DecoderResNetVariableEmbeddingSize (vitad): CUDA input required — this implementation has no CPU path")
+        if self._packed is None or self._packed["device"] != x.device:
+            self._pack(x.device)
+        pk = self._packed
+        x = x.to(torch.float32).contiguous()
+        B = x.shape[0]
+        if pk["ws"] is None or pk["ws_batch"] < B:
+            nbytes = lib.vitad_resnet_decoder_workspace_bytes(C.byref(pk["w"]), B)
+            if nbytes == 0:
+                raise _lib.VitadError(f"vitad_resnet_decoder_workspace_bytes: {lib.vitad_last_error().decode()}")
+            pk["ws"], pk["ws_batch"] = torch.empty(nbytes, device=x.device, dtype=torch.uint8), B
+        recon = torch.empty((B, 3, 224, 224), device=x.device, dtype=torch.float32)
+        check(lib.vitad_resnet_decoder_forward(C.byref(pk["w"]), x.data_ptr(), B, pk["ws"].data_ptr(), pk["ws"].numel(),
+                                               recon.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return recon
+
+
 class AutoEncoderDeit(nn.Module):
-    """Drop-in for TransformerAutoEncoder.py:152-194 (`ae_deit_small`): EncoderDeit → cls token → decoder."""
+    """Drop-in for TransformerAutoEncoder.py:152-194: EncoderDeit → cls token → decoder (`ae_deit`: reverse ResNet,
+    `ae_deit_small`: small CNN)."""
 
     def __init__(self, img_size: int, requires_grad: bool = False, red_mse="mean", red_ssim="elementwise_mean",
                  decoder="resnet") -> None:
         super().__init__()
-        if decoder != "cnn":
-            raise NotImplementedError(
-                "vitad AutoEncoderDeit: only the small CNN decoder (get_model('ae_deit_small'), decoder='cnn') is "
-                "provided; the reverse-ResNet decoder stack is outside this round's scope (DESIGN.md §8)")
+        if decoder not in ("cnn", "resnet"):
+            raise ValueError(f"vitad AutoEncoderDeit: decoder must be 'resnet' or 'cnn', got {decoder!r}")
         self.img_size = img_size
         self.red_mse = red_mse
         self.mse = nn.MSELoss(reduction=red_mse)
@@ -163,7 +346,10 @@ class AutoEncoderDeit(nn.Module):
         self.feature_map_size = math.ceil(img_size / (2**5))
         self.size_patch_embedding = self.encoder.size_patch_embedding
         self.num_embedded_patches = self.encoder.num_embedded_patches
-        self.decoder = DecoderVanillaCNN(z_space=self.z_space, first_feature_map_size=self.feature_map_size)
+        if decoder == "resnet":  # TransformerAutoEncoder.py:176-179
+            self.decoder = DecoderResNetVariableEmbeddingSize(embedding_size=self.encoder.size_patch_embedding)
+        else:  # VanillaAutoEncoder's own decoder (CnnAutoEncoder.py)
+            self.decoder = DecoderVanillaCNN(z_space=self.z_space, first_feature_map_size=self.feature_map_size)
         self.architecture = "transformer"
 
     def forward(self, x) -> AutoEncoderOutput:

@@ -211,6 +211,54 @@ def make_small_decoder_state_dict(seed: int, z_space: int = 768, fmap: int = 7, 
     return {prefix + k: v for k, v in sd.items()}
 
 
+RESNET_DECODER_LAYERS = (("layer4", 512, 3, 2, 1024), ("layer3", 256, 4, 2, 512), ("layer2", 128, 6, 2, 256),
+                         ("layer1", 64, 3, 1, 64))  # name, planes, blocks, stride of the last block, its output channels
+
+
+def make_resnet_decoder_state_dict(seed: int, embedding: int = 768, prefix: str = "decoder.") -> dict:
+    """DecoderResNetVariableEmbeddingSize(embedding_size=768) (CnnDecoder.py:158-196, ReverseResNet.py:106-209): the key
+    layout of the reference's state_dict.  The reference's default initialisation leaves the transposed convolutions at
+    kaiming-uniform(a=sqrt 5) and the BatchNorms at identity, so activations die out through 16 blocks and the image is
+    tanh(~0); these weights are He-scaled with non-trivial BatchNorm affine/running statistics instead, so that every
+    layer (and eval-mode BatchNorm folding) matters in the parity tests."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def bn(name, c, gamma=1.0):
+        sd[name + ".weight"] = gamma * (1 + 0.1 * torch.randn(c, generator=g))
+        sd[name + ".bias"] = 0.05 * torch.randn(c, generator=g)
+        sd[name + ".running_mean"] = 0.05 * torch.randn(c, generator=g)
+        sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".num_batches_tracked"] = torch.tensor(1)
+
+    def convt(name, cin, cout, k, taps):
+        # ConvTranspose2d weight is [in, out, k, k]; `taps` = kernel elements that reach one output pixel on average
+        sd[name + ".weight"] = torch.randn(cin, cout, k, k, generator=g) * math.sqrt(2.0 / (cin * taps))
+
+    sd["fc1.0.weight"] = torch.randn(2 * embedding, embedding, generator=g) * math.sqrt(2.0 / embedding)
+    sd["fc1.0.bias"] = 0.02 * torch.randn(2 * embedding, generator=g)
+    sd["fc2.0.weight"] = torch.randn(2048, 2 * embedding, generator=g) * math.sqrt(2.0 / (2 * embedding))
+    sd["fc2.0.bias"] = 0.02 * torch.randn(2048, generator=g)
+    for layer, planes, blocks, stride, last_dim in RESNET_DECODER_LAYERS:
+        cin = planes * 4
+        for i in range(blocks):
+            b = f"{layer}.{i}"
+            last = i == blocks - 1
+            cout = last_dim if last else cin
+            convt(b + ".conv3", cin, planes, 1, 1)
+            bn(b + ".bn3", planes)
+            convt(b + ".conv2", planes, planes, 3, 9 / 4 if (last and stride == 2) else 9)
+            bn(b + ".bn2", planes)
+            convt(b + ".conv1", planes, cout, 1, 1)
+            bn(b + ".bn1", cout, gamma=0.5)
+            if last:
+                convt(b + ".upsample.0", cin, cout, 1, 1)
+                bn(b + ".upsample.1", cout, gamma=0.7)
+    convt("de_conv1", 64, 3, 7, 49 / 4 * 4)  # nearest-upsampled input: neighbouring taps see the same pixel
+    bn("bn1", 3, gamma=0.6)
+    return {prefix + k: v for k, v in sd.items()}
+
+
 def synthetic_images(seed: int, batch: int, size: int = 224) -> torch.Tensor:
     """fp32 NCHW in [0,1] — the loader's ToTensor contract (GeneralDataset.py:38-59)."""
     g = torch.Generator().manual_seed(1000 + seed)
