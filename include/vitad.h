@@ -112,6 +112,12 @@ typedef struct vitad_linear_args {
     int convt_w;        /* CONVT_RELU_F16 / TANH_PIX4_F32: width (= height) of the input pixel grid */
     const void* resid16; /* RES16_RELU_F16: fp16 residual rows, pitch ldr elements */
     int ldr, res_grid;
+    /* Implicit 3x3 convolution (stride 1, zero padding 1) without an im2col pass, for BIAS_F16 / BIAS_RELU_F16 /
+     * TANH_PIX4_F32.  conv_grid = g > 0: `a` is the zero-bordered NHWC activation [B, g+2, g+2, C] (pitch lda >= C,
+     * C % 64 == 0), k = 9*C with W columns ordered (ty, tx, c), m = B*(g+2)*(g+2) GEMM rows of which the B*g*g interior
+     * ones are written as plain pixel rows.  out_pad_grid = g > 0 (BIAS_*_F16, RES16_RELU_F16): the GEMM's m = B*g*g
+     * plain pixel rows are written into such a zero-bordered layout (the caller zeroes the border once). */
+    int conv_grid, out_pad_grid;
 } vitad_linear_args;
 
 int vitad_linear_f16(const vitad_linear_args* args, void* stream);
@@ -356,6 +362,21 @@ typedef struct vitad_cnn_decoder_weights {
 size_t vitad_cnn_decoder_workspace_bytes(const vitad_cnn_decoder_weights* w, int batch);
 int vitad_cnn_decoder_forward(const vitad_cnn_decoder_weights* w, const float* latent, int batch, void* workspace,
                               size_t workspace_bytes, float* recon, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Input path: the loader's transforms.Resize((S,S)) + ToTensor (src/data_loader/GeneralDataset.py:38-59) on the device.
+ * torchvision resizes PIL images with Pillow's BILINEAR filter (antialiased triangle filter, 8-bit fixed point, horizontal
+ * pass then vertical pass with a uint8 intermediate; Pillow Resample.c); these entry points reproduce it bit for bit.
+ *   vitad_resize_ksize   taps per output pixel for one axis
+ *   vitad_resize_plan    HOST memory: plan[0..S) first source pixel, plan[S..2S) tap count, plan[2S + i*ksize + t]
+ *                        int32 coefficients (22 fractional bits); the caller copies the plan to the device once per geometry
+ *   vitad_resize_bilinear_u8  in uint8 HWC [B,H,W,3] -> tmp uint8 [B,H,S,3] -> out uint8 planar [B,3,S,S] (what
+ *                        vitad_deit_forward_u8 reads; ToTensor's /255 is folded into its patch gather)
+ * ------------------------------------------------------------------------------------------ */
+int vitad_resize_ksize(int in_size, int out_size);
+int vitad_resize_plan(int in_size, int out_size, int32_t* plan);
+int vitad_resize_bilinear_u8(const uint8_t* in, int batch, int height, int width, int out_size, const int32_t* plan_h,
+                             const int32_t* plan_v, uint8_t* tmp, uint8_t* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Reverse-ResNet decoder of the reconstruction models: DecoderResNetVariableEmbeddingSize.forward

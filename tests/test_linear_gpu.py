@@ -126,3 +126,41 @@ def test_cta_pair_and_single_cta_kernels_agree(pair):
             assert (out - ref).abs().max().item() <= 1e-4 * ref.abs().max().item(), (pair, m, n, k)
     finally:
         _lib.lib.vitad_set_cta_pair(1)
+
+
+@pytest.mark.parametrize("B,g,c,n", [(32, 28, 128, 128), (3, 14, 256, 256), (32, 14, 384, 64), (2, 56, 64, 64), (1, 14, 64, 32)])
+def test_implicit_conv3x3_matches_conv2d(B, g, c, n):
+    """conv_grid mode of vitad_linear_f16 (tap-shifted TMA loads of a zero-bordered activation) against F.conv2d."""
+    from vitad import ops
+
+    gen = torch.Generator().manual_seed(g * c)
+    x = (torch.randn(B, c, g, g, generator=gen) * 0.5).half()
+    w = (torch.randn(n, c, 3, 3, generator=gen) * 0.03).half()
+    b = torch.randn(n, generator=gen) * 0.1
+    ref = torch.nn.functional.conv2d(x.float().cuda(), w.float().cuda(), b.cuda(), padding=1)  # [B, n, g, g]
+    rows = x.permute(0, 2, 3, 1).reshape(B * g * g, c).contiguous().cuda()
+    wk = w.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous().cuda()
+    for relu in (False, True):
+        out = ops.conv3x3(ops.pad_pixels(rows, B, g), wk, b.cuda(), B, g, relu=relu)
+        torch.cuda.synchronize()
+        r = ref.relu() if relu else ref
+        r = r.permute(0, 2, 3, 1).reshape(B * g * g, n)
+        assert (out.float() - r).abs().max().item() <= 2e-3 * r.abs().max().item()
+
+
+def test_out_pad_grid_scatters_into_the_bordered_layout():
+    from vitad import _lib, ops
+    import ctypes as C
+
+    B, g, k, n = 3, 14, 256, 128
+    a, w, b = _mk(B * g * g, n, k, seed=7)
+    out = torch.zeros(B * (g + 2) ** 2, n, device="cuda", dtype=torch.float16)
+    args = _lib.LinearArgs()
+    args.a, args.w, args.bias = a.data_ptr(), w.data_ptr(), b.data_ptr()
+    args.m, args.n, args.k, args.lda, args.ldw = a.shape[0], n, k, k, k
+    args.epilogue, args.out, args.ldo, args.out_pad_grid = _lib.EPI_BIAS_RELU_F16, out.data_ptr(), n, g
+    _lib.check(_lib.lib.vitad_linear_f16(C.byref(args), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = ops.pad_pixels(_ref(a, w, b).relu().half(), B, g)
+    assert (out.float() - ref.float()).abs().max().item() <= 2e-3 * ref.float().abs().max().item()
+    assert torch.equal(out.view(B, g + 2, g + 2, n)[:, 0], torch.zeros_like(out.view(B, g + 2, g + 2, n)[:, 0]))

@@ -198,25 +198,34 @@ DecWs carve(const vitad_cnn_decoder_weights& w, int batch, void* base) {
     s.total = c.used;
     return s;
 }
+// conv2 of a stride-1 block runs as an implicit 3x3 convolution (no im2col pass) when the (g+2)^2/g^2 extra MMA work on
+// border rows is cheaper than writing and re-reading the 9x larger im2col matrix
+inline bool implicit_conv(const vitad_resnet_block& b, int g) { return b.stride == 1 && g >= 14 && b.width % 64 == 0; }
+
 struct ResWs {
     void *lat, *h, *f, *x[2], *h1, *col, *h2, *up;
     size_t total;
 };
 ResWs carve_resnet(const vitad_resnet_decoder_weights& w, int batch, void* base) {
-    size_t x_el = static_cast<size_t>(batch) * w.grid0 * w.grid0 * w.feat, h1_el = 0, col_el = 0, h2_el = 0, up_el = 0;
+    size_t x_el = static_cast<size_t>(batch) * w.grid0 * w.grid0 * w.feat, h1_el = 0, col_el = 64, h2_el = 0, up_el = 0;
     int g = w.grid0;
     for (int i = 0; i < w.n_blocks; ++i) {
         const vitad_resnet_block& b = w.blocks[i];
         const size_t M = static_cast<size_t>(batch) * g * g;
+        const size_t Mp = static_cast<size_t>(batch) * (g + 2) * (g + 2);  // zero-bordered layout
         const size_t Mo = b.stride == 2 ? 4 * M : M;
         x_el = std::max(x_el, std::max(M * b.cin, Mo * b.cout));
-        h1_el = std::max(h1_el, M * b.width);
-        col_el = std::max(col_el, M * b.width * (b.stride == 2 ? 4 : 9));
+        if (implicit_conv(b, g)) {
+            h1_el = std::max(h1_el, Mp * b.width);
+        } else {
+            h1_el = std::max(h1_el, M * b.width);
+            col_el = std::max(col_el, M * b.width * (b.stride == 2 ? 4 : 9));
+        }
         h2_el = std::max(h2_el, Mo * b.width);
         if (b.wup) up_el = std::max(up_el, M * b.cout);
         if (b.stride == 2) g *= 2;
     }
-    col_el = std::max(col_el, static_cast<size_t>(batch) * g * g * 9 * w.last_c);
+    x_el = std::max(x_el, static_cast<size_t>(batch) * (g + 2) * (g + 2) * w.last_c);  // the image head reads a bordered map
     Carve c{static_cast<uint8_t*>(base)};
     ResWs s;
     s.lat = c.take(static_cast<size_t>(batch) * w.latent * 2);
@@ -361,17 +370,31 @@ extern "C" int vitad_resnet_decoder_forward(const vitad_resnet_decoder_weights* 
         g_launches.fetch_add(1);
     }
     int cur = 0;
+    int bordered_g = 0, bordered_w = 0;  // geometry whose zero border ws.h1 currently holds
     for (int i = 0; i < w.n_blocks; ++i) {
         const vitad_resnet_block& b = w.blocks[i];
         const int M = batch * g * g;
+        const int Mp = batch * (g + 2) * (g + 2);
+        const bool implicit = implicit_conv(b, g);
+        const bool last = i == w.n_blocks - 1;
         const void* x = ws.x[cur];
         void* y = ws.x[cur ^ 1];
         // conv3 + bn3 + relu (ReverseResNet.py:89-91)
+        if (implicit && (bordered_g != g || bordered_w != b.width)) {
+            VITAD_CUDA_OK(cudaMemsetAsync(ws.h1, 0, static_cast<size_t>(Mp) * b.width * 2, s));
+            bordered_g = g, bordered_w = b.width;
+        }
+        if (!implicit) bordered_g = 0;
         gemm(x, M, b.cin, b.w3, b.b3, b.width, VITAD_EPI_BIAS_RELU_F16, ws.h1, b.width);
+        a.out_pad_grid = implicit ? g : 0;
         if ((rc = vitad_linear_f16(&a, s))) return rc;
         // conv2 + bn2 + relu (:92-94)
         int Mo = M;
-        if (b.stride == 1) {
+        if (implicit) {
+            gemm(ws.h1, Mp, 9 * b.width, b.w2, b.b2, b.width, VITAD_EPI_BIAS_RELU_F16, ws.h2, b.width);
+            a.lda = b.width, a.conv_grid = g;
+            if ((rc = vitad_linear_f16(&a, s))) return rc;
+        } else if (b.stride == 1) {
             {
                 ProfScope prof("dec_im2col3", s);
                 const size_t total = static_cast<size_t>(M) * 9 * (b.width / 8);
@@ -401,23 +424,18 @@ extern "C" int vitad_resnet_decoder_forward(const vitad_resnet_decoder_weights* 
             if ((rc = vitad_linear_f16(&a, s))) return rc;
             resid = ws.up;
         }
-        // conv1 + bn1 + identity + relu (:95-101)
+        // conv1 + bn1 + identity + relu (:95-101); the last block writes the zero-bordered layout the image head reads
+        const int go = b.stride == 2 ? 2 * g : g;
+        if (last) VITAD_CUDA_OK(cudaMemsetAsync(y, 0, static_cast<size_t>(batch) * (go + 2) * (go + 2) * b.cout * 2, s));
         gemm(ws.h2, Mo, b.width, b.w1, b.b1, b.cout, VITAD_EPI_RES16_RELU_F16, y, b.cout);
-        a.resid16 = resid, a.ldr = b.cout, a.res_grid = b.stride == 2 ? g : 0;
+        a.resid16 = resid, a.ldr = b.cout, a.res_grid = b.stride == 2 ? g : 0, a.out_pad_grid = last ? go : 0;
         if ((rc = vitad_linear_f16(&a, s))) return rc;
         cur ^= 1;
-        if (b.stride == 2) g *= 2;
+        g = go;
     }
-    // image head (CnnDecoder.py:189-194) as a 3x3 convolution producing 4x4 pixel blocks
-    const int M = batch * g * g;
-    {
-        ProfScope prof("dec_im2col3", s);
-        const size_t total = static_cast<size_t>(M) * 9 * (w.last_c / 8);
-        VITAD_CUDA_OK(launch_pdl(dec_im2col3x3_kernel, blocks_for(total), dim3(256), 0, s,
-                                 static_cast<const __half*>(ws.x[cur]), static_cast<__half*>(ws.col), w.last_c, g, total));
-        g_launches.fetch_add(1);
-    }
-    gemm(ws.col, M, 9 * w.last_c, w.last_w, w.last_b, 64, VITAD_EPI_TANH_PIX4_F32, recon, 0);
+    // image head (CnnDecoder.py:189-194) as an implicit 3x3 convolution producing 4x4 pixel blocks
+    gemm(ws.x[cur], batch * (g + 2) * (g + 2), 9 * w.last_c, w.last_w, w.last_b, 64, VITAD_EPI_TANH_PIX4_F32, recon, 0);
+    a.lda = w.last_c, a.conv_grid = g;
     a.convt_w = g;
     return vitad_linear_f16(&a, s);
 }

@@ -23,6 +23,10 @@ struct TileSched {
     int tail_tiles;  // = (tiles cut) * tail_split
     int tail_split;  // pieces per cut tile (1, 2, 4, 8)
     int tail_w;      // BLOCK_N / tail_split (multiple of 32)
+    // implicit 3x3 convolution (conv_kpt > 0): A is a zero-bordered NHWC activation [B*(g+2)*(g+2), C]; the K loop walks
+    // 9 taps x conv_kpt = C/64 k-blocks, tap (ty, tx) reads the A rows shifted by (ty-1)*conv_pitch + (tx-1), conv_pitch =
+    // g+2 (rows outside the tensor are zero-filled by TMA and only reach border rows, which the epilogue drops)
+    int conv_kpt, conv_pitch;
 };
 
 template <int BLOCK_N, int EPI_WARPS>
@@ -200,10 +204,16 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             const CUtensorMap* bmap = t.tail ? &tma_b_tail : &tma_b;
             const uint32_t tx = 2u * static_cast<uint32_t>(S::kABytes + (t.w >> 1) * (kBlockK * 2));
             for (int kb = 0; kb < num_kb; ++kb) {
+                int a_k = kb * kBlockK, a_row = row0;
+                if (sched.conv_kpt > 0) {
+                    const int tap = kb / sched.conv_kpt;
+                    a_k = (kb - tap * sched.conv_kpt) * kBlockK;
+                    a_row = row0 + (tap / 3 - 1) * sched.conv_pitch + (tap % 3 - 1);
+                }
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
-                    tma_load_2d_pair(smem_a + stage * S::kABytes, &tma_a, &full_bar[stage], kb * kBlockK, row0);
+                    tma_load_2d_pair(smem_a + stage * S::kABytes, &tma_a, &full_bar[stage], a_k, a_row);
                     tma_load_2d_pair(smem_b + stage * S::kBBytes, bmap, &full_bar[stage], kb * kBlockK, n_row0);
                     if (tile == cluster_id && kb == 0) VITAD_TL(3);
                     VITAD_TL(4);
@@ -345,6 +355,57 @@ struct SEpiBiasH {
             u.y = pack_h2(act(a.z + b.z), act(a.w + b.w));
             *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * ldo + col) = u;
         }
+    }
+};
+
+// Pixel-row maps between the plain NHWC layout [B, g, g] and the zero-bordered one [B, g+2, g+2] that the implicit 3x3
+// convolution reads (TileSched::conv_kpt).  -1: the row has no image (out of range, or a border row).
+__device__ __forceinline__ int row_plain_to_padded(int row, int g) {
+    const int x = row % g;
+    const int t = row / g;
+    const int y = t % g;
+    const int b = t / g;
+    const int P = g + 2;
+    return (b * P + y + 1) * P + x + 1;
+}
+__device__ __forceinline__ int row_padded_to_plain(int row, int g) {
+    const int P = g + 2;
+    const int xp = row % P;
+    const int t = row / P;
+    const int yp = t % P;
+    const int b = t / P;
+    if (xp < 1 || xp > g || yp < 1 || yp > g) return -1;
+    return (b * g + yp - 1) * g + xp - 1;
+}
+
+// SEpiBiasH with a pixel-row map: mode 1 writes plain GEMM rows into the zero-bordered layout (the producer of an
+// implicit 3x3 convolution), mode 2 writes the interior rows of a zero-bordered GEMM (the convolution itself) as plain rows.
+template <int ACT>
+struct SEpiBiasHMap {
+    static constexpr bool kRowCtx = true;
+    static constexpr int kDefaultEpiWarps = 8;
+    using Pre = NoPre;
+    using ColC = float4;
+    const float* bias;
+    __half* out;
+    int ldo, M, N, mode, g;
+    __device__ __forceinline__ RowCtx row_ctx(int row) const {
+        if (row >= M) return RowCtx{0, -1};
+        const int r = mode == 1 ? row_plain_to_padded(row, g) : row_padded_to_plain(row, g);
+        return RowCtx{r, r < 0 ? -1 : 0};
+    }
+    __device__ __forceinline__ bool direct(int) const { return false; }
+    __device__ __forceinline__ void direct_unit(int, RowCtx, int, const uint32_t (&)[32]) const {}
+    __device__ __forceinline__ Pre prefetch(int, RowCtx, int) const { return NoPre{}; }
+    __device__ __forceinline__ ColC col_const(int col) const {
+        return col < N ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ void store(int, RowCtx ctx, int col, float4 a, Pre, ColC b) const {
+        if (ctx.b < 0 || col >= N) return;
+        uint2 u;
+        u.x = pack_h2(SEpiBiasH<ACT>::act(a.x + b.x), SEpiBiasH<ACT>::act(a.y + b.y));
+        u.y = pack_h2(SEpiBiasH<ACT>::act(a.z + b.z), SEpiBiasH<ACT>::act(a.w + b.w));
+        *reinterpret_cast<uint2*>(out + static_cast<size_t>(ctx.a) * ldo + col) = u;
     }
 };
 
@@ -549,17 +610,19 @@ struct SEpiResReluH {
     const __half* resid;
     __half* out;
     int ldo, ldr, M, N, rg;
-    // ctx.a = residual row (-1: none), ctx.b = -1 when the output row is out of range
+    int pad_g;  // > 0: output rows go to the zero-bordered layout [B, pad_g+2, pad_g+2] (feeds an implicit 3x3 convolution)
+    // ctx.a = residual row (-1: none), ctx.b = output row (-1 when out of range)
     __device__ __forceinline__ RowCtx row_ctx(int row) const {
         if (row >= M) return RowCtx{-1, -1};
-        if (rg == 0) return RowCtx{row, 0};
+        const int orow = pad_g > 0 ? row_plain_to_padded(row, pad_g) : row;
+        if (rg == 0) return RowCtx{row, orow};
         const int G = 2 * rg;
         const int x = row % G;
         const int t = row / G;
         const int y = t % G;
         const int b = t / G;
-        if ((x | y) & 1) return RowCtx{-1, 0};
-        return RowCtx{(b * rg + (y >> 1)) * rg + (x >> 1), 0};
+        if ((x | y) & 1) return RowCtx{-1, orow};
+        return RowCtx{(b * rg + (y >> 1)) * rg + (x >> 1), orow};
     }
     __device__ __forceinline__ bool direct(int) const { return false; }
     __device__ __forceinline__ void direct_unit(int, RowCtx, int, const uint32_t (&)[32]) const {}
@@ -570,14 +633,14 @@ struct SEpiResReluH {
     __device__ __forceinline__ ColC col_const(int col) const {
         return col < N ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __device__ __forceinline__ void store(int row, RowCtx ctx, int col, float4 a, Pre r, ColC b) const {
+    __device__ __forceinline__ void store(int, RowCtx ctx, int col, float4 a, Pre r, ColC b) const {
         if (ctx.b < 0 || col >= N) return;
         const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
         const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
         uint2 u;
         u.x = pack_h2(fmaxf(a.x + b.x + r0.x, 0.f), fmaxf(a.y + b.y + r0.y, 0.f));
         u.y = pack_h2(fmaxf(a.z + b.z + r1.x, 0.f), fmaxf(a.w + b.w + r1.y, 0.f));
-        *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * ldo + col) = u;
+        *reinterpret_cast<uint2*>(out + static_cast<size_t>(ctx.b) * ldo + col) = u;
     }
 };
 
@@ -593,9 +656,14 @@ struct SEpiTanhPix4 {
     const float* bias;  // [64], 48 live
     float* out;         // fp32 NCHW [B, 3, 4Wg, 4Wg]
     int M, Wg;
-    // ctx.a = b*3*(4Wg)^2/4 ... kept as two ints: a = b, b = J*Wg + I (-1: out of range)
+    int padded;         // GEMM rows are the zero-bordered pixels of an implicit convolution
+    // ctx.a = image b, ctx.b = J*Wg + I (-1: out of range or a border row)
     __device__ __forceinline__ RowCtx row_ctx(int row) const {
         if (row >= M) return RowCtx{0, -1};
+        if (padded) {
+            row = row_padded_to_plain(row, Wg);
+            if (row < 0) return RowCtx{0, -1};
+        }
         const int pix = Wg * Wg;
         const int b = row / pix;
         return RowCtx{b, row - b * pix};

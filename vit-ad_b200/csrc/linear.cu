@@ -28,6 +28,8 @@ static TileSched make_sched(int m, int n, int bn, int clusters) {
     while (s.tail_split < 8 && rest * s.tail_split * 2 <= clusters && bn / (s.tail_split * 2) >= 32) s.tail_split *= 2;
     s.tail_tiles = rest * s.tail_split;
     s.tail_w = bn / s.tail_split;
+    s.conv_kpt = 0;
+    s.conv_pitch = 0;
     return s;
 }
 // Relative cost of a schedule in units of "one 256 x 256 tile": a cut piece still streams the whole 256-row A block,
@@ -44,9 +46,14 @@ template <int BLOCK_N, int EPI_WARPS, class Epi>
 static int launch_gemm_staged_w(const vitad_linear_args& a, const Epi& epi, cudaStream_t stream) {
     using S = StagedSmem<BLOCK_N, EPI_WARPS>;
     const int max_clusters = device_sm_count() / 2;
-    const TileSched sched = make_sched(a.m, a.n, BLOCK_N, max_clusters);
+    TileSched sched = make_sched(a.m, a.n, BLOCK_N, max_clusters);
+    const int a_cols = a.conv_grid > 0 ? a.k / 9 : a.k;
+    if (a.conv_grid > 0) {
+        sched.conv_kpt = a_cols / kBlockK;
+        sched.conv_pitch = a.conv_grid + 2;
+    }
     CUtensorMap ta, tb, tbt;
-    int rc = make_tmap_f16_2d(&ta, a.a, a.m, a.k, a.lda, kBlockM);
+    int rc = make_tmap_f16_2d(&ta, a.a, a.m, a_cols, a.lda, kBlockM);
     if (rc) return rc;
     rc = make_tmap_f16_2d(&tb, a.w, a.n, a.k, a.ldw, BLOCK_N / 2);
     if (rc) return rc;
@@ -79,10 +86,18 @@ template <int BLOCK_N>
 static int dispatch_staged(const vitad_linear_args& a, cudaStream_t stream) {
     switch (a.epilogue) {
         case VITAD_EPI_BIAS_F16:
+            if (a.conv_grid > 0 || a.out_pad_grid > 0)
+                return launch_gemm_staged<BLOCK_N>(a, SEpiBiasHMap<0>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n,
+                                                                     a.conv_grid > 0 ? 2 : 1,
+                                                                     a.conv_grid > 0 ? a.conv_grid : a.out_pad_grid}, stream);
             return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<0>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n}, stream);
         case VITAD_EPI_BIAS_GELU_F16:
             return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<1>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n}, stream);
         case VITAD_EPI_BIAS_RELU_F16:
+            if (a.conv_grid > 0 || a.out_pad_grid > 0)
+                return launch_gemm_staged<BLOCK_N>(a, SEpiBiasHMap<2>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n,
+                                                                     a.conv_grid > 0 ? 2 : 1,
+                                                                     a.conv_grid > 0 ? a.conv_grid : a.out_pad_grid}, stream);
             return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<2>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n}, stream);
         case VITAD_EPI_RESIDUAL_F32:
             return launch_gemm_staged<BLOCK_N>(a, SEpiResidualF32{a.bias, a.resid, static_cast<float*>(a.out), a.ldo, a.m, a.n},
@@ -104,10 +119,12 @@ static int dispatch_staged(const vitad_linear_args& a, cudaStream_t stream) {
             return launch_gemm_staged<BLOCK_N>(a, SEpiConvT{a.bias, static_cast<__half*>(a.out), a.m, a.n, a.convt_w}, stream);
         case VITAD_EPI_RES16_RELU_F16:
             return launch_gemm_staged<BLOCK_N>(a, SEpiResReluH{a.bias, static_cast<const __half*>(a.resid16),
-                                                               static_cast<__half*>(a.out), a.ldo, a.ldr, a.m, a.n, a.res_grid},
+                                                               static_cast<__half*>(a.out), a.ldo, a.ldr, a.m, a.n, a.res_grid,
+                                                               a.out_pad_grid},
                                                stream);
         case VITAD_EPI_TANH_PIX4_F32:
-            return launch_gemm_staged<BLOCK_N>(a, SEpiTanhPix4{a.bias, static_cast<float*>(a.out), a.m, a.convt_w}, stream);
+            return launch_gemm_staged<BLOCK_N>(a, SEpiTanhPix4{a.bias, static_cast<float*>(a.out), a.m, a.convt_w, a.conv_grid > 0 ? 1 : 0},
+                                               stream);
         default:
             set_error("unknown epilogue %d", a.epilogue);
             return VITAD_ERR_ARG;
@@ -237,7 +254,23 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
     VITAD_REQUIRE(a.a && a.w, VITAD_ERR_ARG, "null operand");
     VITAD_REQUIRE(a.m > 0 && a.n > 0 && a.k > 0, VITAD_ERR_SHAPE, "empty GEMM %dx%dx%d", a.m, a.n, a.k);
     VITAD_REQUIRE(a.k % 16 == 0, VITAD_ERR_SHAPE, "K=%d must be a multiple of 16", a.k);
-    VITAD_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0 && a.lda >= a.k && a.ldw >= a.k, VITAD_ERR_ALIGN,
+    VITAD_REQUIRE(a.conv_grid >= 0 && a.out_pad_grid >= 0 && !(a.conv_grid > 0 && a.out_pad_grid > 0), VITAD_ERR_ARG,
+                  "conv_grid / out_pad_grid: at most one, non-negative");
+    if (a.conv_grid > 0) {
+        const int P = a.conv_grid + 2;
+        VITAD_REQUIRE(a.k % (9 * kBlockK) == 0 && a.m % (P * P) == 0 &&
+                          (a.epilogue == VITAD_EPI_BIAS_F16 || a.epilogue == VITAD_EPI_BIAS_RELU_F16 ||
+                           a.epilogue == VITAD_EPI_TANH_PIX4_F32),
+                      VITAD_ERR_SHAPE, "implicit 3x3 convolution: K = 9*C with C %% 64 == 0, M = B*(g+2)^2, bias/ReLU/image-head epilogue");
+        VITAD_REQUIRE(a.epilogue != VITAD_EPI_TANH_PIX4_F32 || a.convt_w == a.conv_grid, VITAD_ERR_SHAPE,
+                      "image-head epilogue over an implicit convolution: convt_w must equal conv_grid");
+    }
+    if (a.out_pad_grid > 0)
+        VITAD_REQUIRE(a.m % (a.out_pad_grid * a.out_pad_grid) == 0 &&
+                          (a.epilogue == VITAD_EPI_BIAS_F16 || a.epilogue == VITAD_EPI_BIAS_RELU_F16 ||
+                           a.epilogue == VITAD_EPI_RES16_RELU_F16),
+                      VITAD_ERR_SHAPE, "out_pad_grid: M = B*g*g and a bias/ReLU/residual fp16 epilogue");
+    VITAD_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0 && a.lda >= (a.conv_grid > 0 ? a.k / 9 : a.k) && a.ldw >= a.k, VITAD_ERR_ALIGN,
                   "pitches must be >= K and multiples of 8 elements (lda=%d ldw=%d)", a.lda, a.ldw);
     if (a.epilogue == VITAD_EPI_F32) {
         VITAD_REQUIRE(a.out && a.ldo >= a.n, VITAD_ERR_ARG, "bad fp32 output");
@@ -279,7 +312,8 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
                           VITAD_ERR_ALIGN, "fp16 residual epilogue: aligned out/resid16, pitches %% 8, M = B*(2*res_grid)^2");
             break;
         case VITAD_EPI_TANH_PIX4_F32:
-            VITAD_REQUIRE(a.out && aligned16(a.out) && a.n == 64 && a.convt_w > 0 && a.m % (a.convt_w * a.convt_w) == 0,
+            VITAD_REQUIRE(a.out && aligned16(a.out) && a.n == 64 && a.convt_w > 0 &&
+                              (a.conv_grid > 0 || a.m % (a.convt_w * a.convt_w) == 0),
                           VITAD_ERR_SHAPE, "image-head epilogue needs N = 64 (48 live) and M = B*Wg*Wg");
             break;
         case VITAD_EPI_PATCH_EMBED:
@@ -293,12 +327,13 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // the conv-transpose scatter exists only as a staged epilogue of the CTA-pair kernel (which handles any M)
     const bool pair = (g_use_pair.load() && a.m > kBlockM) || a.epilogue == VITAD_EPI_CONVT_RELU_F16 ||
-                      a.epilogue == VITAD_EPI_RES16_RELU_F16 || a.epilogue == VITAD_EPI_TANH_PIX4_F32;
+                      a.epilogue == VITAD_EPI_RES16_RELU_F16 || a.epilogue == VITAD_EPI_TANH_PIX4_F32 || a.conv_grid > 0 ||
+                      a.out_pad_grid > 0;
     // block_n is a hint: widths the selected kernel does not instantiate fall back to the library's choice
     const bool hint_ok = pair ? (a.block_n == 128 || a.block_n == 256) : (a.block_n == 96 || a.block_n == 128 || a.block_n == 256);
     const int bn = hint_ok ? a.block_n : (pair ? pick_block_n_pair(a.m, a.n) : pick_block_n_single(a.m, a.n));
     char pname[64];
-    snprintf(pname, sizeof(pname), "gemm_epi%d_n%d_k%d_bn%d", a.epilogue, a.n, a.k, bn);
+    snprintf(pname, sizeof(pname), "gemm_epi%d_n%d_k%d_bn%d%s", a.epilogue, a.n, a.k, bn, a.conv_grid > 0 ? "_conv3x3" : "");
     ProfScope prof(pname, s);
     if (pair) {
         if (bn == 256) return dispatch_staged<256>(a, s);

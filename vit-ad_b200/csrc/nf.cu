@@ -93,9 +93,10 @@ __global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restr
         if (c0 + i < cols && r0 + tx < rows) out[static_cast<size_t>(c0 + i) * ld_out + r0 + tx] = tile[tx][i];
 }
 
-// xT [.. >= c1][ld] fp32 -> out fp16 [M][c1] (first c1 channels, token-major GEMM operand).
+// xT [.. >= c1][ld] fp32 -> out fp16 [M][c1] (first c1 channels, token-major GEMM operand).  pad_g > 0: token (b, y, x) of
+// the pad_g x pad_g grid goes to row (b, y+1, x+1) of the zero-bordered layout the implicit 3x3 convolution reads.
 __global__ void __launch_bounds__(256) stream_to_operand_kernel(const float* __restrict__ xT, int ld,
-                                                                __half* __restrict__ out, int M, int c1) {
+                                                                __half* __restrict__ out, int M, int c1, int pad_g) {
     __shared__ float tile[32][33];
     const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -103,7 +104,14 @@ __global__ void __launch_bounds__(256) stream_to_operand_kernel(const float* __r
         if (c0 + i < c1 && t0 + tx < M) tile[i][tx] = xT[static_cast<size_t>(c0 + i) * ld + t0 + tx];
     __syncthreads();
     for (int i = ty; i < 32; i += 8)
-        if (t0 + i < M && c0 + tx < c1) out[static_cast<size_t>(t0 + i) * c1 + c0 + tx] = to_h(tile[tx][i]);
+        if (t0 + i < M && c0 + tx < c1) {
+            int row = t0 + i;
+            if (pad_g > 0) {
+                const int x = row % pad_g, t = row / pad_g;
+                row = ((t / pad_g) * (pad_g + 2) + t % pad_g + 1) * (pad_g + 2) + x + 1;
+            }
+            out[static_cast<size_t>(row) * c1 + c0 + tx] = to_h(tile[tx][i]);
+        }
 }
 
 // 3x3 im2col on a g x g grid per image, zero padding: in fp16 [M][cw] -> out fp16 [M][9*cw], column (tap, c),
@@ -205,7 +213,7 @@ static int launch_couple(const void* a2, const void* w2p, int M, int C, int K2, 
 namespace {
 struct NfWs {
     float *xa, *xb, *sjac;
-    void *x1h, *a1, *h, *a2;
+    void *x1h, *x1p, *h, *a2;
     int ld;
     size_t total;
 };
@@ -225,7 +233,7 @@ NfWs carve_nf(const vitad_nf_weights& w, int batch, void* base) {
     s.xb = static_cast<float*>(take(static_cast<size_t>(w.channels) * s.ld * 4));
     s.sjac = static_cast<float*>(take(static_cast<size_t>(w.steps) * (w.channels / kNfTile) * s.ld * 4));
     s.x1h = take(M * c1 * 2);
-    s.a1 = take(M * 9 * c1 * 2);
+    s.x1p = take(static_cast<size_t>(batch) * (w.grid + 2) * (w.grid + 2) * c1 * 2);  // zero-bordered x1 of the 3x3 steps
     s.h = take(M * w.hidden_pad * 2);
     s.a2 = take(M * 9 * w.hidden_pad * 2);
     s.total = used;
@@ -267,31 +275,29 @@ extern "C" int vitad_nf_forward(const vitad_nf_weights* wp, const float* tokens,
     }
     float* xin = ws.xa;
     float* xout = ws.xb;
+    const int Mp = batch * (w.grid + 2) * (w.grid + 2);
+    bool bordered = false;  // ws.x1p's border has been zeroed in this call
     for (int i = 0; i < w.steps; ++i) {
         const vitad_nf_step& st = w.step[i];
         VITAD_REQUIRE(st.ksize == 1 || st.ksize == 3, VITAD_ERR_SHAPE, "subnet kernel size %d", st.ksize);
+        // subnet conv 1 (+ReLU): 1x1 = plain GEMM; 3x3 = implicit convolution over the zero-bordered operand (no im2col)
+        const bool k3 = st.ksize == 3;
+        if (k3 && !bordered) {
+            VITAD_CUDA_OK(cudaMemsetAsync(ws.x1p, 0, static_cast<size_t>(Mp) * c1 * 2, s));
+            bordered = true;
+        }
         {
             ProfScope prof("nf_operand", s);
             dim3 grid((M + 31) / 32, (c1 + 31) / 32);
-            stream_to_operand_kernel<<<grid, 256, 0, s>>>(xin, ws.ld, static_cast<__half*>(ws.x1h), M, c1);
+            stream_to_operand_kernel<<<grid, 256, 0, s>>>(xin, ws.ld, static_cast<__half*>(k3 ? ws.x1p : ws.x1h), M, c1,
+                                                          k3 ? w.grid : 0);
             VITAD_CUDA_OK(cudaGetLastError());
             g_launches.fetch_add(1);
-        }
-        const void* a1 = ws.x1h;
-        int k1 = c1;
-        if (st.ksize == 3) {
-            ProfScope prof("nf_im2col", s);
-            const size_t total = static_cast<size_t>(M) * 9 * (c1 / 8);
-            im2col3x3_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
-                static_cast<const __half*>(ws.x1h), static_cast<__half*>(ws.a1), M, c1, w.grid, total);
-            VITAD_CUDA_OK(cudaGetLastError());
-            g_launches.fetch_add(1);
-            a1 = ws.a1;
-            k1 = 9 * c1;
         }
         vitad_linear_args la;
         memset(&la, 0, sizeof(la));
-        la.a = a1, la.w = st.w0p, la.bias = st.b0p, la.m = M, la.n = w.hidden_pad, la.k = k1, la.lda = k1, la.ldw = k1;
+        la.a = k3 ? ws.x1p : ws.x1h, la.w = st.w0p, la.bias = st.b0p, la.m = k3 ? Mp : M, la.n = w.hidden_pad;
+        la.k = k3 ? 9 * c1 : c1, la.lda = c1, la.ldw = la.k, la.conv_grid = k3 ? w.grid : 0;
         la.epilogue = VITAD_EPI_BIAS_RELU_F16, la.out = ws.h, la.ldo = w.hidden_pad;
         if ((rc = vitad_linear_f16(&la, s))) return rc;
         const void* a2 = ws.h;

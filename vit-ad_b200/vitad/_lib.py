@@ -88,6 +88,8 @@ class LinearArgs(C.Structure):
         ("resid16", C.c_void_p),
         ("ldr", C.c_int),
         ("res_grid", C.c_int),
+        ("conv_grid", C.c_int),
+        ("out_pad_grid", C.c_int),
     ]
 
 
@@ -246,6 +248,14 @@ lib.vitad_resnet_decoder_workspace_bytes.argtypes = [C.POINTER(ResnetDecoderWeig
 lib.vitad_resnet_decoder_workspace_bytes.restype = _sz
 lib.vitad_resnet_decoder_forward.argtypes = [C.POINTER(ResnetDecoderWeights), _vp, _i, _vp, _sz, _vp, _vp]
 lib.vitad_resnet_decoder_forward.restype = _i
+
+# ------------------------------------------------------------------------------ input resize
+lib.vitad_resize_ksize.argtypes = [_i, _i]
+lib.vitad_resize_ksize.restype = _i
+lib.vitad_resize_plan.argtypes = [_i, _i, _vp]
+lib.vitad_resize_plan.restype = _i
+lib.vitad_resize_bilinear_u8.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
+lib.vitad_resize_bilinear_u8.restype = _i
 
 MDN_KA = 784  # K extent of the packed MDN operands (768 + 16)
 

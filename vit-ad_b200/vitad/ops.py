@@ -52,6 +52,67 @@ def linear(
     return out
 
 
+def pad_pixels(x: torch.Tensor, batch: int, grid: int) -> torch.Tensor:
+    """Plain NHWC pixel rows fp16 [B*g*g, C] → the zero-bordered layout [B*(g+2)*(g+2), C] the implicit convolution reads."""
+    c = x.shape[1]
+    out = torch.zeros((batch, grid + 2, grid + 2, c), device=x.device, dtype=x.dtype)
+    out[:, 1:-1, 1:-1, :] = x.view(batch, grid, grid, c)
+    return out.view(-1, c)
+
+
+def conv3x3(xp: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, batch: int, grid: int, relu: bool = False,
+            out: torch.Tensor | None = None) -> torch.Tensor:
+    """3x3 convolution (stride 1, zero padding 1) as one tcgen05 GEMM without an im2col pass.  xp: zero-bordered NHWC
+    fp16 [B*(g+2)*(g+2), C] (C % 64 == 0); w: fp16 [N, 9*C], columns (ty, tx, c) = kernel element [n, c, ty, tx] of an
+    nn.Conv2d; returns plain pixel rows fp16 [B*g*g, N]."""
+    _need_cuda(xp, w, bias, out)
+    assert xp.dtype == torch.float16 and w.dtype == torch.float16 and xp.stride(1) == 1 and w.stride(1) == 1
+    c = xp.shape[1]
+    n = w.shape[0]
+    assert xp.shape[0] == batch * (grid + 2) ** 2 and w.shape[1] == 9 * c
+    if out is None:
+        out = torch.empty((batch * grid * grid, n), device=xp.device, dtype=torch.float16)
+    args = _lib.LinearArgs()
+    args.a, args.w, args.bias = xp.data_ptr(), w.data_ptr(), bias.data_ptr()
+    args.m, args.n, args.k = xp.shape[0], n, 9 * c
+    args.lda, args.ldw = xp.stride(0), w.stride(0)
+    args.epilogue = _lib.EPI_BIAS_RELU_F16 if relu else _lib.EPI_BIAS_F16
+    args.out, args.ldo = out.data_ptr(), out.stride(0)
+    args.conv_grid = grid
+    check(lib.vitad_linear_f16(C.byref(args), _stream()))
+    return out
+
+
+def resize_plan(in_size: int, out_size: int) -> torch.Tensor:
+    """Host plan of one axis of Pillow's BILINEAR resize (int32: first source pixel | tap count | coefficients)."""
+    ks = lib.vitad_resize_ksize(in_size, out_size)
+    plan = torch.empty(2 * out_size + out_size * ks, dtype=torch.int32)
+    check(lib.vitad_resize_plan(in_size, out_size, plan.data_ptr()))
+    return plan
+
+
+_resize_plans: dict = {}
+
+
+def resize_u8(images_hwc: torch.Tensor, size: int) -> torch.Tensor:
+    """transforms.Resize((size, size)) of the reference's loader (GeneralDataset.py:38-59) on the device, bit-identical
+    to Pillow: uint8 [B, H, W, 3] (decoded images, HWC) → uint8 [B, 3, size, size] (planar; feed it to the encoders'
+    uint8 path, which folds ToTensor's /255 into the patch gather)."""
+    _need_cuda(images_hwc)
+    assert images_hwc.dtype == torch.uint8 and images_hwc.dim() == 4 and images_hwc.shape[3] == 3
+    images_hwc = images_hwc.contiguous()
+    b, h, w, _ = images_hwc.shape
+    key = (h, w, size, images_hwc.device)
+    if key not in _resize_plans:
+        _resize_plans[key] = (resize_plan(w, size).to(images_hwc.device), resize_plan(h, size).to(images_hwc.device))
+    plan_h, plan_v = _resize_plans[key]
+    tmp = torch.empty((b, h, size, 3), device=images_hwc.device, dtype=torch.uint8)
+    out = torch.empty((b, 3, size, size), device=images_hwc.device, dtype=torch.uint8)
+    check(lib.vitad_resize_bilinear_u8(images_hwc.data_ptr(), b, h, w, size, plan_h.data_ptr(), plan_v.data_ptr(),
+                                       tmp.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
 def linear_qkv(
     a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, batch: int, tokens: int, heads: int, tokens_pad: int,
     q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, q_scale: float, block_n: int = 0, head_dim: int = 0,
