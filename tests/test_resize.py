@@ -78,3 +78,26 @@ def test_resized_uint8_feeds_the_encoder_like_the_loader_tensor():
         a = enc(torch.from_numpy(cpu).cuda()).patch_embedding
         b = enc(ops.resize_u8(torch.from_numpy(imgs).cuda(), 224)).patch_embedding
     assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_validator_accepts_decoded_uint8_images():
+    """ValidatorNF.score_batch on raw-size uint8 HWC images == on the loader's Resize + ToTensor tensors, bit for bit."""
+    from oracle import weights as W
+    from vitad.encoders import EncoderDeit
+    from vitad.nf import NormalizingFlow
+    from vitad.validators import ValidatorNF
+
+    imgs = np.stack([_image(900, 900, 7), _image(900, 900, 8), _image(900, 900, 9)])
+    cpu = np.stack([resize_bilinear_u8(im, 224) for im in imgs]).transpose(0, 3, 1, 2).astype(np.float32) / 255.0
+    enc = EncoderDeit(224)
+    enc.load_state_dict(W.make_deit_state_dict(seed=11, stress=True))
+    np.random.seed(0)
+    nf = NormalizingFlow(768, 224, 196, 0.16, 20)
+    props = {"dataset": "synthetic", "dataclass": "x", "fp_thres": 0.3}
+    val = ValidatorNF([nf], enc, None, props, weights_object=[W.make_nf_state_dict(31)])
+    labels = (torch.zeros(3, 1, 224, 224), torch.tensor([0, 1, 0]))
+    a = val.valid_loop_transformer_nf([(torch.from_numpy(cpu), *labels)], keep_origs=False)
+    b = val.valid_loop_transformer_nf([(torch.from_numpy(imgs), *labels)], keep_origs=False)
+    np.testing.assert_array_equal(a["image_scores"], b["image_scores"])
+    np.testing.assert_array_equal(a["pixel_scores"], b["pixel_scores"])

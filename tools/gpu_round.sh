@@ -16,3 +16,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm4_tc_kernel -s 1 -c 1 -o gpurun_out/prof_mdn -f python tools/prof_target.py > gpurun_out/ncu_mdn.log 2>&1; echo "ncu mdn rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:gemm3_tc_kernel|attention_kernel|layernorm_kernel" -s 60 -c 7 -o gpurun_out/prof_enc -f python tools/prof_target.py > gpurun_out/ncu_enc.log 2>&1; echo "ncu enc rc=$?"
 fi
+timeout 300 python tools/gpu_diag_configs.py > gpurun_out/other_configs.txt 2>&1; echo "configs rc=$?"
+timeout 300 python tools/gpu_diag_resize.py > gpurun_out/resize_decoder.txt 2>&1; echo "resize rc=$?"

@@ -113,6 +113,15 @@ def resize_u8(images_hwc: torch.Tensor, size: int) -> torch.Tensor:
     return out
 
 
+def prepare_images(images: torch.Tensor, size: int) -> torch.Tensor:
+    """Device-side half of the loader's image transform: a uint8 HWC batch of decoded images [B, H, W, 3] (any H, W) is
+    resized like transforms.Resize((size, size)) does on the CPU and returned as uint8 NCHW; NCHW batches (fp32 in
+    [0,1] or uint8) pass through."""
+    if images.dtype == torch.uint8 and images.dim() == 4 and images.shape[-1] == 3 and images.shape[1] != 3:
+        return resize_u8(images, size)
+    return images
+
+
 def linear_qkv(
     a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, batch: int, tokens: int, heads: int, tokens_pad: int,
     q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, q_scale: float, block_n: int = 0, head_dim: int = 0,

@@ -67,6 +67,10 @@ class _BatchSharding:
 
 
 class _Pipelined:
+    def _img_size(self) -> int:
+        fe = getattr(self, "feature_extractor", None)
+        return int((self.model if fe is None else fe).img_size)
+
     """Three-stream batch pipeline shared by the validators: the H2D copy of batch k+1 (copy-in stream) and the D2H
     copy of batch k-1's scores/maps into pinned buffers (copy-out stream) overlap the kernels of batch k (current
     stream).  The reference moves one batch at a time and synchronises 33 times per batch (ValidatorMDN.py:123-168).
@@ -175,7 +179,7 @@ class ValidatorMdn(_Pipelined):
         (host or device, fp32 NCHW in [0,1]).  Body of ValidatorMDN.py:123-162."""
         model = self.gmm_model[0]
         fe = self.feature_extractor
-        images = images.to(self.device, non_blocking=True)
+        images = ops.prepare_images(images.to(self.device, non_blocking=True), self._img_size())
         features = fe(images)
         x = features.patch_embedding
         g = None
@@ -250,7 +254,7 @@ class ValidatorNF(_Pipelined):
 
     def score_batch(self, images: torch.Tensor, batch_index: int = 0):
         """ValidatorNF.py:123-142 → (image_scores [B], anomaly maps [B,1,S,S])."""
-        images = images.to(self.device, non_blocking=True)
+        images = ops.prepare_images(images.to(self.device, non_blocking=True), self._img_size())
         embedding = self.feature_extractor(images, block_index=BLOCK_INDEX_DEIT).patch_embedding
         result = self.nf_model[0].forward_tokens(embedding)
         return result.image_max, result.anomaly_score_map
@@ -285,7 +289,7 @@ class ValidatorRecon(_Pipelined):
 
     def score_batch(self, images: torch.Tensor, batch_index: int = 0):
         """ValidatorRecon.py:107-116 → (image_scores [B], pixel_scores [B,1,S,S], reconstruction)."""
-        images = images.to(self.device, non_blocking=True)
+        images = ops.prepare_images(images.to(self.device, non_blocking=True), self._img_size())
         # uint8 pixels -> the fp32 [0,1] tensor ToTensor produces (the L2 map compares against it)
         images = images.to(torch.float32).div_(255.0) if images.dtype == torch.uint8 else images.to(torch.float32)
         output = self.model(images)
