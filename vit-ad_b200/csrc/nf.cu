@@ -56,24 +56,46 @@ struct EpiNfCouple {
                 x1a[j] = __ldg(xin + static_cast<size_t>(c) * ld + r);
                 x2a[j] = __ldg(xin + static_cast<size_t>(c_half + c) * ld + r);
             }
+            // per-channel constants of the 16 channels: 128-bit uniform loads (the scalar form issued 8 LDG per channel)
+            const int cb = n_tile * kNfHalf + q;
+            float bs[16], bt[16], sc1[16], of1[16], sc2[16], of2[16];
+            int ip1[16], ip2[16];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                ld4(bs + 4 * v, b2p + n_tile * kNfTile + q + 4 * v);
+                ld4(bt + 4 * v, b2p + n_tile * kNfTile + kNfHalf + q + 4 * v);
+                ld4(sc1 + 4 * v, scale + cb + 4 * v);
+                ld4(of1 + 4 * v, offset + cb + 4 * v);
+                ld4(sc2 + 4 * v, scale + c_half + cb + 4 * v);
+                ld4(of2 + 4 * v, offset + c_half + cb + 4 * v);
+                ld4i(ip1 + 4 * v, inv_perm + cb + 4 * v);
+                ld4i(ip2 + 4 * v, inv_perm + c_half + cb + 4 * v);
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const int c = n_tile * kNfHalf + q + j;
-                const float a_s = __uint_as_float(as[j]) + __ldg(b2p + n_tile * kNfTile + q + j);
-                const float a_t = __uint_as_float(at[j]) + __ldg(b2p + n_tile * kNfTile + kNfHalf + q + j);
-                const float sv = clamp * tanhf(a_s);
-                const float x1v = x1a[j];
-                const float x2v = x2a[j];
-                const float y2 = x2v * expf(sv) + a_t;
+                const float a_s = __uint_as_float(as[j]) + bs[j];
+                const float a_t = __uint_as_float(at[j]) + bt[j];
+                // clamp * tanh(a_s) = clamp * (1 - 2 / (1 + e^{2 a_s})), two MUFU (absolute error ~1e-7; e^{2a} = inf / 0
+                // saturate to +-1); exp(s) = 2^{s log2 e}
+                const float e2 = ex2f(a_s * 2.885390081777927f);
+                const float sv = clamp * (1.0f - __fdividef(2.0f, 1.0f + e2));
+                const float y2 = x2a[j] * ex2f(sv * 1.4426950408889634f) + a_t;
                 if (valid) {
-                    xout[static_cast<size_t>(__ldg(inv_perm + c)) * ld + row] = x1v * __ldg(scale + c) + __ldg(offset + c);
-                    xout[static_cast<size_t>(__ldg(inv_perm + c_half + c)) * ld + row] =
-                        y2 * __ldg(scale + c_half + c) + __ldg(offset + c_half + c);
+                    xout[static_cast<size_t>(ip1[j]) * ld + row] = x1a[j] * sc1[j] + of1[j];
+                    xout[static_cast<size_t>(ip2[j]) * ld + row] = y2 * sc2[j] + of2[j];
                 }
                 ssum += sv;
             }
         }
+    }
+    __device__ __forceinline__ static void ld4(float* dst, const float* src) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+        dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;
+    }
+    __device__ __forceinline__ static void ld4i(int* dst, const int* src) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(src));
+        dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;
     }
     __device__ __forceinline__ void tile_end(int, int n_tile, int row) {
         if (row < M) sjac[static_cast<size_t>(n_tile) * ld + row] = ssum;
@@ -83,6 +105,8 @@ struct EpiNfCouple {
 // in [rows][cols] fp32 row-major -> out [cols][ld] (transpose), 32x32 tiles through shared memory.
 __global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                             int rows, int cols, int ld_out) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ float tile[32][33];
     const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -97,6 +121,8 @@ __global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restr
 // the pad_g x pad_g grid goes to row (b, y+1, x+1) of the zero-bordered layout the implicit 3x3 convolution reads.
 __global__ void __launch_bounds__(256) stream_to_operand_kernel(const float* __restrict__ xT, int ld,
                                                                 __half* __restrict__ out, int M, int c1, int pad_g) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ float tile[32][33];
     const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -118,6 +144,8 @@ __global__ void __launch_bounds__(256) stream_to_operand_kernel(const float* __r
 // tap = ky*3+kx.  One thread moves 8 channels (16 bytes).
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const __half* __restrict__ in, __half* __restrict__ out, int M,
                                                         int cw, int g, size_t total) {
+    griddep_launch_dependents();
+    griddep_wait();
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int v_per_tap = cw >> 3;
@@ -135,40 +163,67 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const __half* __restrict
     *reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * 9 * cw + tap * cw + v * 8) = val;
 }
 
-// One block per image: omp[t] = 1 - exp(-0.5*mean_c z^2) (NormalizingFlow.py:134-137) and
-// loss_term[b] = 0.5*sum z^2 - (sum of s partials + logdet_const) (:130-132).
-__global__ void __launch_bounds__(256) nf_finish_kernel(const float* __restrict__ zT, int ld,
-                                                        const float* __restrict__ sjac, int n_partials,
-                                                        float logdet_const, int P, int C, float* __restrict__ omp,
-                                                        float* __restrict__ loss_terms) {
-    __shared__ float red_z[8], red_s[8];
-    const int b = blockIdx.x;
-    float zz_tot = 0.f, s_tot = 0.f;
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
-        const int t = b * P + p;
-        float zz = 0.f;
-        for (int c = 0; c < C; ++c) {
-            const float z = zT[static_cast<size_t>(c) * ld + t];
-            zz = fmaf(z, z, zz);
+// Per token: omp[t] = 1 - exp(-0.5*mean_c z^2) (NormalizingFlow.py:134-137), tok[0][t] = sum_c z^2, tok[1][t] = sum of the
+// log-det partials.  Block = 32 tokens (lane) x 8 channel groups (warp): every load is a coalesced 128-byte row segment,
+// each thread has C/8 independent loads in flight instead of one thread walking all C channels of a token; the 8 partial
+// sums are combined in fixed order (deterministic, independent of the batch size).
+__global__ void __launch_bounds__(256) nf_token_kernel(const float* __restrict__ zT, int ld, const float* __restrict__ sjac,
+                                                       int n_partials, int M, int C, float* __restrict__ omp,
+                                                       float* __restrict__ tok) {
+    griddep_launch_dependents();
+    griddep_wait();
+    __shared__ float red_z[8][32], red_s[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    float zz = 0.f, sv = 0.f;
+    if (t < M) {
+        const int c0 = w * (C / 8), c1 = w == 7 ? C : c0 + C / 8;
+        float z4[4] = {0.f, 0.f, 0.f, 0.f};
+        int c = c0;
+        for (; c + 4 <= c1; c += 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float z = zT[static_cast<size_t>(c + j) * ld + t];
+                z4[j] = fmaf(z, z, z4[j]);
+            }
         }
-        omp[t] = 1.0f - expf(-0.5f * (zz / C));
-        zz_tot += zz;
-        float s = 0.f;
-        for (int k = 0; k < n_partials; ++k) s += sjac[static_cast<size_t>(k) * ld + t];
-        s_tot += s;
+        for (; c < c1; ++c) {
+            const float z = zT[static_cast<size_t>(c) * ld + t];
+            z4[0] = fmaf(z, z, z4[0]);
+        }
+        zz = (z4[0] + z4[1]) + (z4[2] + z4[3]);
+        for (int k = w; k < n_partials; k += 8) sv += sjac[static_cast<size_t>(k) * ld + t];
+    }
+    red_z[w][lane] = zz;
+    red_s[w][lane] = sv;
+    __syncthreads();
+    if (w == 0 && t < M) {
+        float z = 0.f, sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z += red_z[i][lane], sum += red_s[i][lane];
+        omp[t] = 1.0f - expf(-0.5f * (z / C));
+        tok[t] = z;
+        tok[ld + t] = sum;
+    }
+}
+
+// One warp per image: loss_term[b] = 0.5*sum z^2 - (sum of s partials + logdet_const) (NormalizingFlow.py:130-132).
+__global__ void __launch_bounds__(32) nf_image_kernel(const float* __restrict__ tok, int ld, float logdet_const, int P,
+                                                      float* __restrict__ loss_terms) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const int b = blockIdx.x;
+    float z = 0.f, sv = 0.f;
+    for (int p = threadIdx.x; p < P; p += 32) {
+        z += tok[b * P + p];
+        sv += tok[ld + b * P + p];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        zz_tot += __shfl_xor_sync(0xffffffffu, zz_tot, o);
-        s_tot += __shfl_xor_sync(0xffffffffu, s_tot, o);
+        z += __shfl_xor_sync(0xffffffffu, z, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
     }
-    if ((threadIdx.x & 31) == 0) red_z[threadIdx.x >> 5] = zz_tot, red_s[threadIdx.x >> 5] = s_tot;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float z = 0.f, s = 0.f;
-        for (int i = 0; i < (blockDim.x >> 5); ++i) z += red_z[i], s += red_s[i];
-        loss_terms[b] = 0.5f * z - (s + logdet_const);
-    }
+    if (threadIdx.x == 0) loss_terms[b] = 0.5f * z - (sv + logdet_const);
 }
 
 static int launch_couple(const void* a2, const void* w2p, int M, int C, int K2, const EpiNfCouple& epi,
@@ -190,7 +245,7 @@ static int launch_couple(const void* a2, const void* w2p, int M, int C, int K2, 
         const int tiles = ((M + 2 * kBlockM - 1) / (2 * kBlockM)) * n_tiles;
         const int maxc = device_sm_count() / 2;
         const int clusters = tiles < maxc ? tiles : maxc;
-        kern<<<2 * clusters, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, M, n_tiles, K2, epi);
+        VITAD_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), S::kTotalBytes, stream, ta, tb, M, n_tiles, K2, epi));
     } else {
         using S = GemmSmem<kNfTile>;
         rc = make_tmap_f16_2d(&tb, w2p, C, K2, K2, kNfTile);
@@ -203,7 +258,7 @@ static int launch_couple(const void* a2, const void* w2p, int M, int C, int K2, 
         }
         const int tiles = ((M + kBlockM - 1) / kBlockM) * n_tiles;
         const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-        kern<<<grid, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, M, n_tiles, K2, epi);
+        VITAD_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), S::kTotalBytes, stream, ta, tb, M, n_tiles, K2, epi));
     }
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
@@ -212,7 +267,7 @@ static int launch_couple(const void* a2, const void* w2p, int M, int C, int K2, 
 
 namespace {
 struct NfWs {
-    float *xa, *xb, *sjac;
+    float *xa, *xb, *sjac, *tok;
     void *x1h, *x1p, *h, *a2;
     int ld;
     size_t total;
@@ -232,6 +287,7 @@ NfWs carve_nf(const vitad_nf_weights& w, int batch, void* base) {
     s.xa = static_cast<float*>(take(static_cast<size_t>(w.channels) * s.ld * 4));
     s.xb = static_cast<float*>(take(static_cast<size_t>(w.channels) * s.ld * 4));
     s.sjac = static_cast<float*>(take(static_cast<size_t>(w.steps) * (w.channels / kNfTile) * s.ld * 4));
+    s.tok = static_cast<float*>(take(static_cast<size_t>(2) * s.ld * 4));
     s.x1h = take(M * c1 * 2);
     s.x1p = take(static_cast<size_t>(batch) * (w.grid + 2) * (w.grid + 2) * c1 * 2);  // zero-bordered x1 of the 3x3 steps
     s.h = take(M * w.hidden_pad * 2);
@@ -269,7 +325,7 @@ extern "C" int vitad_nf_forward(const vitad_nf_weights* wp, const float* tokens,
     {
         ProfScope prof("nf_transpose", s);
         dim3 grid((M + 31) / 32, (C + 31) / 32);
-        transpose_f32_kernel<<<grid, 256, 0, s>>>(tokens, ws.xa, M, C, ws.ld);
+        VITAD_CUDA_OK(launch_pdl(transpose_f32_kernel, grid, dim3(256), 0, s, tokens, ws.xa, M, C, ws.ld));
         VITAD_CUDA_OK(cudaGetLastError());
         g_launches.fetch_add(1);
     }
@@ -289,8 +345,8 @@ extern "C" int vitad_nf_forward(const vitad_nf_weights* wp, const float* tokens,
         {
             ProfScope prof("nf_operand", s);
             dim3 grid((M + 31) / 32, (c1 + 31) / 32);
-            stream_to_operand_kernel<<<grid, 256, 0, s>>>(xin, ws.ld, static_cast<__half*>(k3 ? ws.x1p : ws.x1h), M, c1,
-                                                          k3 ? w.grid : 0);
+            VITAD_CUDA_OK(launch_pdl(stream_to_operand_kernel, grid, dim3(256), 0, s, static_cast<const float*>(xin), ws.ld,
+                                     static_cast<__half*>(k3 ? ws.x1p : ws.x1h), M, c1, k3 ? w.grid : 0));
             VITAD_CUDA_OK(cudaGetLastError());
             g_launches.fetch_add(1);
         }
@@ -305,8 +361,8 @@ extern "C" int vitad_nf_forward(const vitad_nf_weights* wp, const float* tokens,
         if (st.ksize == 3) {
             ProfScope prof("nf_im2col", s);
             const size_t total = static_cast<size_t>(M) * 9 * (w.hidden_pad / 8);
-            im2col3x3_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
-                static_cast<const __half*>(ws.h), static_cast<__half*>(ws.a2), M, w.hidden_pad, w.grid, total);
+            VITAD_CUDA_OK(launch_pdl(im2col3x3_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s,
+                                     static_cast<const __half*>(ws.h), static_cast<__half*>(ws.a2), M, w.hidden_pad, w.grid, total));
             VITAD_CUDA_OK(cudaGetLastError());
             g_launches.fetch_add(1);
             a2 = ws.a2;
@@ -324,10 +380,12 @@ extern "C" int vitad_nf_forward(const vitad_nf_weights* wp, const float* tokens,
     }
     {
         ProfScope prof("nf_finish", s);
-        nf_finish_kernel<<<batch, 256, 0, s>>>(xin, ws.ld, ws.sjac, w.steps * (C / kNfTile), w.logdet_const, P, C,
-                                               one_minus_prob, loss_terms);
+        VITAD_CUDA_OK(launch_pdl(nf_token_kernel, dim3((M + 31) / 32), dim3(256), 0, s, static_cast<const float*>(xin), ws.ld,
+                                 static_cast<const float*>(ws.sjac), w.steps * (C / kNfTile), M, C, one_minus_prob, ws.tok));
+        VITAD_CUDA_OK(launch_pdl(nf_image_kernel, dim3(batch), dim3(32), 0, s, static_cast<const float*>(ws.tok), ws.ld,
+                                 w.logdet_const, P, loss_terms));
         VITAD_CUDA_OK(cudaGetLastError());
-        g_launches.fetch_add(1);
+        g_launches.fetch_add(2);
     }
     return VITAD_OK;
 }
