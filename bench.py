@@ -369,7 +369,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4 + B * 224 * 224 * 4,
                 "result_interval_ms": {"p50": round(statistics.median(e2e_wall), 3), "max": round(max(e2e_wall), 3)}},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "gmm fused sigma/mu projection + logsumexp (gemm4_tc_kernel<208,1,EpiMdn<104>>, 4-CTA clusters) + feature mean",
+        "roofline": {"kernel": "gmm fused sigma/mu projection + logsumexp (gemm4_tc_kernel<208,1,EpiMdn<104>> on 33 clusters of four + the CTA-pair kernel on the 16 SMs they leave idle) + feature mean",
                      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src + ", sustained bf16/fp16 dense",
                      "flops_per_launch": mdn_flops, "ms_per_launch": mdn_ms,

@@ -45,6 +45,11 @@ void vitad_set_cta_pair(int enable);
 void vitad_set_pdl(int enable);
 /* Fused GMM kernel on clusters of four CTAs sharing the token block by TMA multicast (default on; 0 = CTA pairs). */
 void vitad_set_gmm_cluster4(int enable);
+/* 148 SMs hold 33 clusters of four, so 16 SMs idle under the 4-CTA kernel: the last `features` features of the fused GMM
+ * projection run concurrently on those SMs as the CTA-pair kernel, launched on the same stream as an independent
+ * programmatic dependent of the 4-CTA grid (it starts once that grid is fully resident and waits for it before exiting;
+ * needs vitad_set_pdl(1)).  -1 = balanced split (default, 72 of 768 on a B200), 0 = off. */
+void vitad_set_gmm_split(int features);
 /* Diagnostics: force 8 or 16 epilogue warps in the CTA-pair GEMM kernels (0 = per-epilogue default). */
 void vitad_set_epilogue_warps(int warps);
 /* Optional in-library profiler: CUDA events around every launch site of this library.

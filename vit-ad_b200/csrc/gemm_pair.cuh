@@ -107,7 +107,10 @@ struct PairSmem {
     static_assert(2 * kStages * 8 + 48 <= kBarrierBytes, "barrier area");
 };
 
-template <int BLOCK_N, int SUBTILES, class Epi>
+// kIndependent: the grid does not consume the preceding kernel's results and is launched (programmatic stream
+// serialization) to run BESIDE it: no wait before the main loop, but one before exit, so that this grid's completion still
+// implies the completion of everything before it in the stream (the next kernel only waits for its direct predecessor).
+template <int BLOCK_N, int SUBTILES, class Epi, bool kIndependent = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
                 int num_n_tiles, int K, Epi epi) {
@@ -164,7 +167,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     cluster_sync_all();  // barriers of both CTAs initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
-    griddep_wait();
+    if constexpr (!kIndependent) griddep_wait();
     if (threadIdx.x == 0) VITAD_TL(2);
 
     if (warp == 0) {
@@ -295,6 +298,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     tc_fence_before();
     __syncwarp();
     cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still signal or read it
+    if constexpr (kIndependent) griddep_wait();
     if (threadIdx.x == 0) {
         VITAD_TL(60);
         VITAD_TLG(61);

@@ -78,7 +78,6 @@ gemm4_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int num_k16 = K / 16;
     const int num_kb = (num_k16 + 3) / 4;
 
-    griddep_launch_dependents();
     if (threadIdx.x == 0) {
         VITAD_TL(0);
         VITAD_TLG(1);
@@ -101,6 +100,11 @@ gemm4_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
     griddep_wait();
+    // The dependents are released only now, after this grid's own prerequisites have completed: the kernel launched right
+    // behind this one may be an INDEPENDENT grid (the CTA-pair kernel that takes the last features on the SMs the 33 clusters
+    // of four leave idle, mdn.cu).  It starts once every CTA of this grid is resident and past this point, so it can neither
+    // take SMs away from the clusters nor read operands that are not written yet.
+    griddep_launch_dependents();
     if (threadIdx.x == 0) VITAD_TL(2);
 
     if (warp == 0) {

@@ -23,6 +23,10 @@ namespace vitad {
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_use_pair;
 std::atomic<int> g_gmm_quad{1};  // fused GMM kernel on 4-CTA clusters with A multicast (0: CTA pairs)
+// Features the CTA-pair kernel takes on the SMs the 4-CTA clusters cannot cover (148 SMs hold 33 clusters of four: 16 SMs
+// stay idle), launched right behind the 4-CTA grid as an independent programmatic dependent.  -1: balanced automatically,
+// 0: off, > 0: that many.  Needs programmatic dependent launch (vitad_set_pdl(1), the default).
+std::atomic<int> g_gmm_split{-1};
 
 constexpr float kLog2eF = 1.4426950408889634f;
 constexpr float kLn2F = 0.6931471805599453f;
@@ -496,11 +500,43 @@ static int launch_mdn(const void* xaug, const void* wpk, const float* lp2, const
             max_clusters4 = n;
         }
         const int num_m4 = (M + 2 * kBlockM - 1) / (2 * kBlockM);
-        const int tiles4 = num_m4 * (D / 2);
+        // Side launch: the last Db features go to the CTA-pair kernel on the leftover SMs.  A quad tile (two features) costs
+        // 0.843 of two pair tiles (measured: 1.22 ms on 33 quads vs 1.29 ms on 74 pairs), which balances the two kernels.
+        const int spare_pairs = (device_sm_count() - 4 * max_clusters4) / 2;
+        int Db = g_gmm_split.load();
+        if (Db < 0) {
+            const double ratio = 0.843 * spare_pairs / (2.0 * max_clusters4);
+            Db = static_cast<int>(D * ratio / (1.0 + ratio) + 0.5);
+        }
+        Db &= ~1;
+        if (spare_pairs < 1 || num_m4 < 4 || Db >= D || !pdl_enabled()) Db = 0;
+        const int Dq = D - Db;
+        const int tiles4 = num_m4 * (Dq / 2);
         const int clusters = tiles4 < max_clusters4 ? tiles4 : max_clusters4;
-        VITAD_CUDA_OK(launch_pdl(kern4, dim3(4 * clusters), dim3(kGemmThreads), SP::kTotalBytes, stream, ta64, tb, M, D, kMdnKA, epi));
+        VITAD_CUDA_OK(launch_pdl(kern4, dim3(4 * clusters), dim3(kGemmThreads), SP::kTotalBytes, stream, ta64, tb, M, Dq, kMdnKA, epi));
         VITAD_CUDA_OK(cudaGetLastError());
         g_launches.fetch_add(1);
+        if (Db > 0) {
+            CUtensorMap tb2;
+            const __half* w2 = static_cast<const __half*>(wpk) + static_cast<size_t>(Dq) * NKC * BN * kMdnKA;
+            rc = make_tmap_f16_2d(&tb2, w2, static_cast<uint64_t>(Db) * NKC * BN, kMdnKA, kMdnKA, BN / 2);
+            if (rc) return rc;
+            Epi epi2 = epi;
+            epi2.x = x + Dq;
+            epi2.ll = ll + static_cast<size_t>(Dq) * ldl;
+            // same stream, programmatic launch: starts when every CTA of the 4-CTA grid is resident (gemm_quad.cuh), reads only
+            // what that grid's own prerequisites produced, and waits for that grid before it exits (kIndependent)
+            auto kern2 = gemm2_tc_kernel<BN, NKC, Epi, true>;
+            static bool attr2i_set = false;
+            if (!attr2i_set) {
+                VITAD_CUDA_OK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::kTotalBytes));
+                attr2i_set = true;
+            }
+            VITAD_CUDA_OK(launch_pdl(kern2, dim3(2 * spare_pairs), dim3(kGemmThreads), SP::kTotalBytes, stream, ta, tb2, M, Db, kMdnKA,
+                                     epi2));
+            VITAD_CUDA_OK(cudaGetLastError());
+            g_launches.fetch_add(1);
+        }
         return VITAD_OK;
     }
     if (g_use_pair.load() && M > kBlockM) {
@@ -543,6 +579,7 @@ static int launch_mdn(const void* xaug, const void* wpk, const float* lp2, const
 using namespace vitad;
 
 extern "C" void vitad_set_gmm_cluster4(int enable) { vitad::g_gmm_quad.store(enable ? 1 : 0); }
+extern "C" void vitad_set_gmm_split(int features) { vitad::g_gmm_split.store(features); }
 
 extern "C" int vitad_gmm_plan(int num_gaussians, int* n_kc, int* kc, int* kcv) {
     VITAD_REQUIRE(n_kc && kc && kcv, VITAD_ERR_ARG, "null pointer");

@@ -38,6 +38,10 @@ lib.vitad_set_epilogue_warps.argtypes = [C.c_int]
 lib.vitad_set_epilogue_warps.restype = None
 lib.vitad_set_gmm_cluster4.argtypes = [C.c_int]
 lib.vitad_set_gmm_cluster4.restype = None
+lib.vitad_set_gmm_split.argtypes = [C.c_int]
+lib.vitad_set_gmm_split.restype = None
+if os.environ.get("VITAD_GMM_SPLIT") is not None:  # diagnostics: features given to the side CTA-pair launch (0 = off)
+    lib.vitad_set_gmm_split(int(os.environ["VITAD_GMM_SPLIT"]))
 if os.environ.get("VITAD_GMM_CLUSTER4") == "0":  # diagnostics: fused GMM kernel on CTA pairs
     lib.vitad_set_gmm_cluster4(0)
 if os.environ.get("VITAD_PDL") == "0":  # diagnostics: plain stream order between kernels
