@@ -101,3 +101,30 @@ def test_validator_accepts_decoded_uint8_images():
     b = val.valid_loop_transformer_nf([(torch.from_numpy(imgs), *labels)], keep_origs=False)
     np.testing.assert_array_equal(a["image_scores"], b["image_scores"])
     np.testing.assert_array_equal(a["pixel_scores"], b["pixel_scores"])
+
+
+def test_resize_plan_rejects_bad_arguments():
+    from vitad import _lib
+
+    assert _lib.lib.vitad_resize_ksize(0, 224) == 0 and _lib.lib.vitad_resize_ksize(224, -1) == 0
+    assert _lib.lib.vitad_resize_plan(0, 224, None) < 0
+    assert _lib.lib.vitad_resize_plan(900, 224, None) < 0  # null plan
+
+
+@pytest.mark.gpu
+def test_resize_rejects_bad_arguments_and_handles_one_pixel_rows():
+    from vitad import _lib, ops
+
+    x = torch.zeros(1, 8, 8, 3, dtype=torch.uint8, device="cuda")
+    out = torch.empty(1, 3, 4, 4, dtype=torch.uint8, device="cuda")
+    plan = ops.resize_plan(8, 4).cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    f = _lib.lib.vitad_resize_bilinear_u8
+    assert f(x.data_ptr(), 1, 8, 8, 4, plan.data_ptr(), plan.data_ptr(), None, out.data_ptr(), s) < 0  # null tmp
+    assert f(x.data_ptr(), 0, 8, 8, 4, plan.data_ptr(), plan.data_ptr(), x.data_ptr(), out.data_ptr(), s) < 0  # empty batch
+    with pytest.raises(AssertionError):
+        ops.resize_u8(torch.zeros(1, 3, 8, 8, dtype=torch.float32, device="cuda"), 4)
+    # degenerate geometry: a 1 x 5 image up-scaled to 6 x 6 (every output row reads the single source row)
+    img = np.arange(15, dtype=np.uint8).reshape(1, 5, 3) * 15
+    got = ops.resize_u8(torch.from_numpy(img[None]).cuda(), 6).cpu().numpy()[0].transpose(1, 2, 0)
+    np.testing.assert_array_equal(got, resize_bilinear_u8(img, 6))

@@ -172,3 +172,33 @@ def test_resnet_decoder_cuda_matches_reference_golden():
         got = _module(_decoder_sd()).cuda()(_latents(2).cuda()).cpu().numpy()
     diff = got[:, :, ::4, ::4] - g["recon_sub"]
     assert np.abs(diff).max() <= 2.5e-2 and np.sqrt((diff ** 2).mean()) <= 1.6e-3
+
+
+@pytest.mark.gpu
+def test_c_abi_rejects_bad_decoder_arguments():
+    """Error behaviour of the C entry points: negative status + message, nothing launched, no exception from C."""
+    import ctypes as C
+
+    from vitad import _lib
+
+    dec = _module(_decoder_sd()).cuda()
+    z = _latents(2).cuda()
+    with torch.no_grad():
+        dec(z)
+    w = dec._packed["w"]
+    ws = dec._packed["ws"]
+    out = torch.empty(2, 3, 224, 224, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    f = _lib.lib.vitad_resnet_decoder_forward
+    assert f(C.byref(w), z.data_ptr(), 2, ws.data_ptr(), ws.numel(), None, s) < 0  # null output
+    assert f(C.byref(w), z.data_ptr(), 0, ws.data_ptr(), ws.numel(), out.data_ptr(), s) < 0  # empty batch
+    assert f(C.byref(w), z.data_ptr(), 2, ws.data_ptr(), 1024, out.data_ptr(), s) < 0  # workspace too small
+    assert b"workspace" in _lib.lib.vitad_last_error()
+    assert f(C.byref(w), z.data_ptr(), 2, ws.data_ptr() + 16, ws.numel() - 16, out.data_ptr(), s) < 0  # misaligned workspace
+    bad = _lib.ResnetDecoderWeights.from_buffer_copy(w)
+    bad.blocks[3].cin = 1000  # channels no longer chain
+    assert _lib.lib.vitad_resnet_decoder_workspace_bytes(C.byref(bad), 2) == 0
+    assert f(C.byref(bad), z.data_ptr(), 2, ws.data_ptr(), ws.numel(), out.data_ptr(), s) < 0
+    with pytest.raises(_lib.VitadError):
+        _lib.check(f(C.byref(bad), z.data_ptr(), 2, ws.data_ptr(), ws.numel(), out.data_ptr(), s))
+    torch.cuda.synchronize()
