@@ -19,8 +19,7 @@ def _flow(sd):
     return nf.cuda().eval()
 
 
-@pytest.mark.parametrize("stress", [False, True])
-@pytest.mark.parametrize("B", [1, 3])
+@pytest.mark.parametrize("stress,B", [(False, 1), (True, 1), (False, 3), (True, 3), (True, 32)])
 def test_nf_head_matches_oracle(stress, B):
     from oracle import vitad_oracle as O
     from oracle import weights as W
@@ -63,3 +62,43 @@ def test_nf_validator_matches_reference_golden(tag, stress):
     assert np.abs(res["image_scores"] - ref_s).max() <= 1e-3 * np.abs(ref_s).max(), (res["image_scores"], ref_s)
     assert np.abs(res["pixel_scores"][:, :, ::8, ::8] - ref_m).max() <= 1e-3 * np.abs(ref_m).max()
     np.testing.assert_allclose(res["pixel_scores"].sum(axis=(1, 2, 3)), g[f"{tag}_pixel_scores_sum"], rtol=2e-3)
+
+
+def test_nf_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
+    """north_star's AUROC criterion for the NF head (config 2): ValidatorNF over 24 synthetic MVTec-shaped images, about half of
+    them with pasted anomalies, against the oracle (DeiT block 8 features -> 20-step flow -> amax of the bilinear map)."""
+    from sklearn.metrics import roc_auc_score
+
+    from oracle import vitad_oracle as O
+    from oracle import weights as W
+    from vitad.encoders import EncoderDeit
+    from vitad.synthetic import batches, make_category
+    from vitad.validators import BLOCK_INDEX_DEIT, ValidatorNF
+
+    n = 24
+    images, labels, masks = make_category("cable", n, seed=78)
+    enc_sd = W.make_deit_state_dict(seed=11, stress=True)
+    nf_sd = W.make_nf_state_dict(seed=31, stress=True)
+    with torch.no_grad():
+        tok, _ = O.deit_forward(enc_sd, images, block_index=BLOCK_INDEX_DEIT)
+        _, amap, _, _ = O.nf_forward(nf_sd, O.tokens_to_nchw(tok), flow_steps=20, img_size=224)
+        ref_scores = O.nf_scores(amap).numpy()
+    enc = EncoderDeit(224)
+    enc.load_state_dict(enc_sd)
+    props = {"dataset": "synthetic", "dataclass": "cable", "fp_thres": 0.3}
+    val = ValidatorNF([_flow(nf_sd)], enc, None, props)
+    res = val.valid_loop_transformer_nf(batches(images, labels, masks, batch_size=8))  # NF scores are per-image: any batching
+    noise = 1e-3 * np.abs(ref_scores).max()
+    assert np.abs(res["image_scores"] - ref_scores).max() <= noise
+    assert np.abs(res["pixel_scores"] - amap.numpy()).max() <= 1e-3 * np.abs(amap.numpy()).max()
+    # images whose oracle scores are separated by >= 4x the allowed noise (a near-tie could swap without any kernel error)
+    keep, last = [], -np.inf
+    for i in np.argsort(ref_scores):
+        if ref_scores[i] - last >= 4 * noise:
+            keep.append(i)
+            last = ref_scores[i]
+    keep = np.asarray(sorted(keep))
+    lab = labels.numpy()[keep]
+    assert len(keep) >= 8 and 2 <= lab.sum() <= len(keep) - 2, (len(keep), lab.sum())
+    assert round(roc_auc_score(res["image_labels"][keep], res["image_scores"][keep]), 4) == round(
+        roc_auc_score(lab, ref_scores[keep]), 4)

@@ -18,3 +18,4 @@ timeout 600 ncu --set full --clock-control none --import-source on -k "regex:gem
 fi
 timeout 300 python tools/gpu_diag_configs.py > gpurun_out/other_configs.txt 2>&1; echo "configs rc=$?"
 timeout 300 python tools/gpu_diag_resize.py > gpurun_out/resize_decoder.txt 2>&1; echo "resize rc=$?"
+timeout 600 python tools/sweep.py > gpurun_out/sweep.json 2> gpurun_out/sweep.err; echo "sweep rc=$?"; cut -c1-300 gpurun_out/sweep.json
