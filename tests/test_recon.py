@@ -105,3 +105,39 @@ def test_cnn_decoder_matches_fp32_modules(B):
     assert got.shape == (B, 3, 224, 224)
     err = (got.cpu() - ref).abs().max().item()
     assert err <= 1e-3 * max(ref.abs().max().item(), 1e-3) + 2e-4, (err, ref.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_recon_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
+    """north_star's AUROC criterion for the reconstruction path (config 4, reverse-ResNet decoder): ValidatorRecon over 16
+    synthetic MVTec-shaped images against the oracle (DeiT cls token -> decoder -> per-pixel L2 -> amax)."""
+    from sklearn.metrics import roc_auc_score
+
+    from vitad.model_helper import get_model
+    from vitad.synthetic import batches, make_category
+    from vitad.validators import ValidatorRecon
+
+    n = 16
+    images, labels, masks = make_category("grid", n, seed=79)
+    sd = {("encoder." + k): v for k, v in W.make_deit_state_dict(seed=11, stress=True).items()}
+    sd.update(W.make_resnet_decoder_state_dict(seed=43))
+    with torch.no_grad():
+        _, cls = O.deit_forward(sd, images, prefix="encoder.deit.")
+        ref_scores, ref_maps = O.recon_l2_scores(O.resnet_decoder_forward(sd, cls), images)
+    ref_scores = ref_scores.numpy()
+    props = {"dataset": "synthetic", "dataclass": "grid", "fp_thres": 0.3}
+    val = ValidatorRecon(get_model("ae_deit", 224), None, props, weights_object=sd)
+    res = val.valid_loop_mse(batches(images, labels, masks, batch_size=8))
+    noise = 2e-3 * np.abs(ref_scores).max()  # the decoder's fp16 floor, see test_recon_validator_resnet_matches_reference_golden
+    assert np.abs(res["image_scores"] - ref_scores).max() <= noise
+    assert np.abs(res["pixel_scores"] - ref_maps.numpy()).max() <= 4e-3 * ref_maps.max().item()
+    keep, last = [], -np.inf
+    for i in np.argsort(ref_scores):
+        if ref_scores[i] - last >= 4 * noise:
+            keep.append(i)
+            last = ref_scores[i]
+    keep = np.asarray(sorted(keep))
+    lab = labels.numpy()[keep]
+    assert len(keep) >= 6 and 1 <= lab.sum() <= len(keep) - 1, (len(keep), lab.sum(), np.sort(ref_scores))
+    assert round(roc_auc_score(res["image_labels"][keep], res["image_scores"][keep]), 4) == round(
+        roc_auc_score(lab, ref_scores[keep]), 4)
