@@ -95,7 +95,7 @@ typedef struct vitad_linear_args {
     int m, n, k;
     int lda, ldw;       /* pitches in elements */
     int epilogue;       /* vitad_epilogue */
-    int block_n;        /* tile-width hint: 0 = library default, else 128 or 256 (96: single-CTA kernel only) */
+    int block_n;        /* tile-width hint: 0 = library default, else 128, 192 or 256 (96: single-CTA kernel only) */
     void* out;          /* fp16 or fp32 [M,ldo], see epilogue */
     int ldo;
     const float* resid; /* RESIDUAL_F32: fp32 [M,ldo] (may alias out) */

@@ -18,7 +18,7 @@ def _ref(a, w, b):
     return a.float() @ w.float().t() + b
 
 
-@pytest.mark.parametrize("block_n", [0, 96, 128, 256])
+@pytest.mark.parametrize("block_n", [0, 96, 128, 192, 256])
 @pytest.mark.parametrize(
     "m,n,k",
     [(128, 256, 64), (128, 256, 768), (6336, 768, 768), (6336, 2304, 768), (200, 3072, 784), (77, 512, 3072),

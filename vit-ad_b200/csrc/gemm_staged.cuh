@@ -142,7 +142,7 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     using S = StagedSmem<BLOCK_N, EPI_WARPS>;
     constexpr int kStages = S::kStages;
     static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "8 or 16 epilogue warps");
-    static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N 128 or 256");
+    static_assert(BLOCK_N == 128 || BLOCK_N == 192 || BLOCK_N == 256, "BLOCK_N 128, 192 or 256");
     constexpr uint32_t kTmemCols = tmem_cols_pow2(2 * BLOCK_N);
     constexpr int kPairM = 2 * kBlockM;
 

@@ -16,6 +16,7 @@ namespace vitad {
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_use_pair;
 std::atomic<int> g_epi_warps{0};  // 0 = per-epilogue default, 8 / 16 = forced (diagnostics)
+static double g_cost192 = 1.10;
 
 // Full waves of 256 x bn tiles, then the remaining tiles cut into `split` pieces each (<= one wave of pieces).
 static TileSched make_sched(int m, int n, int bn, int clusters) {
@@ -25,7 +26,10 @@ static TileSched make_sched(int m, int n, int bn, int clusters) {
     const int rest = tiles % clusters;
     s.big_tiles = tiles - rest;
     s.tail_split = 1;
-    while (s.tail_split < 8 && rest * s.tail_split * 2 <= clusters && bn / (s.tail_split * 2) >= 32) s.tail_split *= 2;
+    // a piece is a whole number of 32-column epilogue units
+    while (s.tail_split < 8 && rest * s.tail_split * 2 <= clusters && bn / (s.tail_split * 2) >= 32 &&
+           (bn / (s.tail_split * 2)) % 32 == 0)
+        s.tail_split *= 2;
     s.tail_tiles = rest * s.tail_split;
     s.tail_w = bn / s.tail_split;
     s.conv_kpt = 0;
@@ -227,8 +231,13 @@ static int pick_block_n_single(int m, int n) {
 static int pick_block_n_pair(int m, int n) {
     const int clusters = device_sm_count() / 2;
     const double c256 = sched_cost(make_sched(m, n, 256, clusters), 256, clusters);
-    const double c128 = sched_cost(make_sched(m, n, 128, clusters), 128, clusters) * 1.25;  // 128-wide: more L2 traffic
-    return c128 < c256 ? 128 : 256;
+    const double c192 = sched_cost(make_sched(m, n, 192, clusters), 192, clusters) * g_cost192;  // narrower: more L2 traffic
+    const double c128 = sched_cost(make_sched(m, n, 128, clusters), 128, clusters) * 1.25;
+    int best = 256;
+    double cost = c256;
+    if (c192 < cost) best = 192, cost = c192;
+    if (c128 < cost) best = 128, cost = c128;
+    return best;
 }
 
 }  // namespace vitad
@@ -330,13 +339,15 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
                       a.epilogue == VITAD_EPI_RES16_RELU_F16 || a.epilogue == VITAD_EPI_TANH_PIX4_F32 || a.conv_grid > 0 ||
                       a.out_pad_grid > 0;
     // block_n is a hint: widths the selected kernel does not instantiate fall back to the library's choice
-    const bool hint_ok = pair ? (a.block_n == 128 || a.block_n == 256) : (a.block_n == 96 || a.block_n == 128 || a.block_n == 256);
+    const bool hint_ok = pair ? (a.block_n == 128 || a.block_n == 192 || a.block_n == 256)
+                              : (a.block_n == 96 || a.block_n == 128 || a.block_n == 256);
     const int bn = hint_ok ? a.block_n : (pair ? pick_block_n_pair(a.m, a.n) : pick_block_n_single(a.m, a.n));
     char pname[64];
     snprintf(pname, sizeof(pname), "gemm_epi%d_n%d_k%d_bn%d%s", a.epilogue, a.n, a.k, bn, a.conv_grid > 0 ? "_conv3x3" : "");
     ProfScope prof(pname, s);
     if (pair) {
         if (bn == 256) return dispatch_staged<256>(a, s);
+        if (bn == 192) return dispatch_staged<192>(a, s);
         return dispatch_staged<128>(a, s);
     }
     if (bn == 256) return dispatch_epilogue<256>(a, s);
