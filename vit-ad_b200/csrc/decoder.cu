@@ -14,6 +14,15 @@
 //     and scatters each phase to its output pixel;
 //   * the last layer has 3 output channels: a CUDA-core kernel (1296 FMAs per 2x2 output block) with the folded
 //     BatchNorm and tanh, writing the reconstruction as fp32 NCHW (what the validator returns and the L2-map kernel reads).
+//
+// vitad_resnet_decoder_forward: the reverse-ResNet decoder (DecoderResNetVariableEmbeddingSize, CnnDecoder.py:158-196, over
+// ReverseResNet.py:86-103,169-235; AutoEncoderDeit's default) as one C-ABI call: fc1, fc2, the 1x1 feature replicated to
+// 7x7, 16 Bottleneck blocks, image head.  Every convolution is a tcgen05 GEMM on NHWC fp16 rows (vitad_linear_f16):
+//   conv3 (1x1) bias+ReLU | conv2 (3x3, stride 1) as an implicit convolution over a zero-bordered activation for grids
+//   >= 14 (im2col at 7x7), or the four-phase GEMM above for the stride-2 block of a layer | conv1 + identity + ReLU in one
+//   epilogue, the stride-2 identity path computed on the input grid and added on the even output pixels | the nearest
+//   upsample + 7x7 stride-2 transposed convolution + BatchNorm + tanh head collapsed to one implicit 3x3 convolution that
+//   emits 4x4 pixel blocks.  See include/vitad.h for the packed layouts and DESIGN.md 4.6 for the derivations.
 #include <algorithm>
 #include <atomic>
 

@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(256) gmm_operand_kernel(const float* __restric
 // by the host so that the tokens fill the 148 SMs in ONE balanced wave (M = 6272 -> TPW 11, 143 CTAs): with a fixed
 // 32-token CTA the 196 CTAs left 48 SMs with two CTAs and the rest with one (88 us; this form: see DESIGN.md 4.5).
 constexpr int kPiBK = 32, kPiMaxK = 160;
-template <int TPW, int WARPS>
+// NJ = mixture slots per lane (K <= 32 NJ): 4 for K <= 128 (K = 100: 20 % fewer FMAs and weight loads than 5), 5 up to 160.
+template <int TPW, int WARPS, int NJ>
 __global__ void __launch_bounds__(32 * WARPS) gmm_logpi_kernel(const float* __restrict__ x, int ldx,
                                                                const float* __restrict__ wpi, const float* __restrict__ bpi,
                                                                const float* __restrict__ gumbel, float* __restrict__ lp2,
@@ -207,20 +208,20 @@ __global__ void __launch_bounds__(32 * WARPS) gmm_logpi_kernel(const float* __re
     // broadcasts).  Row pitch 36 floats: 16-byte aligned, the 8 lanes of a quarter-warp land on 8 distinct bank groups.
     constexpr int kPitch = kPiBK + 4;
     __shared__ __align__(16) float xs[BM][kPitch];
-    __shared__ __align__(16) float wsh[kPiMaxK][kPitch];
+    __shared__ __align__(16) float wsh[32 * NJ][kPitch];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int m0 = blockIdx.x * BM;
-    float acc[TPW][5];
+    float acc[TPW][NJ];
 #pragma unroll
     for (int i = 0; i < TPW; ++i)
 #pragma unroll
-        for (int j = 0; j < 5; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
     // global -> register prefetch of the next k-block overlaps the FMAs of the current one
     constexpr int kQ = kPiBK / 4;                  // float4 per staged row
     constexpr int kRowsPerPass = kPiThreads / kQ;  // 16 rows staged per pass
     constexpr int kXPasses = (BM + kRowsPerPass - 1) / kRowsPerPass;
     const int xr = threadIdx.x / kQ, xc = (threadIdx.x % kQ) * 4;
-    float4 px[kXPasses], pw[kPiMaxK / kRowsPerPass];
+    float4 px[kXPasses], pw[32 * NJ / kRowsPerPass];
     auto fetch = [&](int k0) {
 #pragma unroll
         for (int j = 0; j < kXPasses; ++j) {
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(32 * WARPS) gmm_logpi_kernel(const float* __re
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int j = 0; j < kPiMaxK / kRowsPerPass; ++j) {
+        for (int j = 0; j < 32 * NJ / kRowsPerPass; ++j) {
             const int r = xr + kRowsPerPass * j;
             pw[j] = (r < K) ? __ldg(reinterpret_cast<const float4*>(wpi + static_cast<size_t>(r) * D + k0 + xc))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -241,19 +242,19 @@ __global__ void __launch_bounds__(32 * WARPS) gmm_logpi_kernel(const float* __re
         for (int j = 0; j < kXPasses; ++j)
             if (xr + kRowsPerPass * j < BM) *reinterpret_cast<float4*>(&xs[xr + kRowsPerPass * j][xc]) = px[j];
 #pragma unroll
-        for (int j = 0; j < kPiMaxK / kRowsPerPass; ++j) *reinterpret_cast<float4*>(&wsh[xr + kRowsPerPass * j][xc]) = pw[j];
+        for (int j = 0; j < 32 * NJ / kRowsPerPass; ++j) *reinterpret_cast<float4*>(&wsh[xr + kRowsPerPass * j][xc]) = pw[j];
         __syncthreads();
         if (k0 + kPiBK < D) fetch(k0 + kPiBK);
 #pragma unroll
         for (int k = 0; k < kPiBK; k += 4) {
-            float4 wv[5];
+            float4 wv[NJ];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) wv[j] = *reinterpret_cast<const float4*>(&wsh[tx + 32 * j][k]);
+            for (int j = 0; j < NJ; ++j) wv[j] = *reinterpret_cast<const float4*>(&wsh[tx + 32 * j][k]);
 #pragma unroll
             for (int i = 0; i < TPW; ++i) {
                 const float4 xv = *reinterpret_cast<const float4*>(&xs[ty * TPW + i][k]);
 #pragma unroll
-                for (int j = 0; j < 5; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     acc[i][j] = fmaf(xv.x, wv[j].x, acc[i][j]);
                     acc[i][j] = fmaf(xv.y, wv[j].y, acc[i][j]);
                     acc[i][j] = fmaf(xv.z, wv[j].z, acc[i][j]);
@@ -269,19 +270,19 @@ __global__ void __launch_bounds__(32 * WARPS) gmm_logpi_kernel(const float* __re
     for (int i = 0; i < TPW; ++i) {
         const int t = m0 + ty * TPW + i;
         if (t >= M) break;  // warp-uniform
-        float z[5];
+        float z[NJ];
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             const int k = tx + 32 * j;
             z[j] = (k < K) ? acc[i][j] + bpi[k] + gumbel[static_cast<size_t>(t) * K + k] : -INFINITY;
             mx = fmaxf(mx, z[j]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float e[5], sum = 0.f;
+        float e[NJ], sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             e[j] = (tx + 32 * j < K) ? expf(z[j] - mx) : 0.f;
             sum += e[j];
         }
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(32 * WARPS) gmm_logpi_kernel(const float* __re
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         float* dst = lp2 + static_cast<size_t>(t) * ldp;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             const int k = tx + 32 * j;
             if (k < K) {
                 const int kc = k / KCV;
@@ -307,8 +308,12 @@ __global__ void __launch_bounds__(32 * WARPS) gmm_logpi_kernel(const float* __re
 template <int TPW, int WARPS>
 static cudaError_t launch_logpi(cudaStream_t s, const float* x, int ldx, const float* pi_w, const float* pi_b,
                                 const float* gumbel, float* lp2, int tokens, int dim, int K, int n_kc, int kc, int kcv) {
-    return launch_pdl(gmm_logpi_kernel<TPW, WARPS>, dim3((tokens + WARPS * TPW - 1) / (WARPS * TPW)), dim3(32 * WARPS), 0, s,
-                      x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, K, n_kc, kc, kcv);
+    const dim3 grid((tokens + WARPS * TPW - 1) / (WARPS * TPW)), block(32 * WARPS);
+    if (K <= 128)
+        return launch_pdl(gmm_logpi_kernel<TPW, WARPS, 4>, grid, block, 0, s, x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, K, n_kc,
+                          kc, kcv);
+    return launch_pdl(gmm_logpi_kernel<TPW, WARPS, 5>, grid, block, 0, s, x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, K, n_kc, kc,
+                      kcv);
 }
 
 // ---------------------------------------------------------- mixing weights on the tensor cores

@@ -8,8 +8,9 @@
 //   * the activation stream lives channel-major in HBM (xT fp32 [768][tokens]) so the channel permutation is a
 //     ROW permutation of the epilogue's (token-coalesced) stores — the reference spends 4.6 GFLOP/img on a dense
 //     768x768 conv of zeros and ones for it;
-//   * both subnet convolutions are tcgen05 GEMMs over token-major fp16 operands (3x3: im2col rows with zero
-//     padding at the 14x14 borders); conv1 uses the bias+ReLU epilogue, conv2's weight rows are interleaved so one
+//   * both subnet convolutions are tcgen05 GEMMs over token-major fp16 operands; the 3x3 first convolution (384
+//     channels) is an implicit convolution over a zero-bordered operand (vitad_linear_args::conv_grid, no im2col), the
+//     3x3 second one (64 hidden channels) reads im2col rows; conv1 uses the bias+ReLU epilogue, conv2's weight rows are interleaved so one
 //     96-column accumulator tile holds [s(48 channels) | t(48 channels)], and its epilogue (EpiNfCouple) does the
 //     coupling, the global affine, the permuted store and the per-token sum of s;
 //   * log-det partial sums are written per (channel tile, token) and reduced in fixed order (deterministic).
