@@ -120,25 +120,33 @@ __global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restr
 
 // xT [.. >= c1][ld] fp32 -> out fp16 [M][c1] (first c1 channels, token-major GEMM operand).  pad_g > 0: token (b, y, x) of
 // the pad_g x pad_g grid goes to row (b, y+1, x+1) of the zero-bordered layout the implicit 3x3 convolution reads.
+// Block = 32 tokens x 128 channels: 128-byte row segments in, 256 contiguous bytes per token out (a thread packs 16
+// channels into two 16-byte stores; the 32 x 32 tile version wrote 64-byte pieces).
+constexpr int kOpCh = 128;
 __global__ void __launch_bounds__(256) stream_to_operand_kernel(const float* __restrict__ xT, int ld,
                                                                 __half* __restrict__ out, int M, int c1, int pad_g) {
     griddep_launch_dependents();
     griddep_wait();
-    __shared__ float tile[32][33];
-    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    __shared__ float tile[kOpCh][33];
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * kOpCh;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int i = ty; i < 32; i += 8)
-        if (c0 + i < c1 && t0 + tx < M) tile[i][tx] = xT[static_cast<size_t>(c0 + i) * ld + t0 + tx];
+#pragma unroll 4
+    for (int i = ty; i < kOpCh; i += 8)
+        tile[i][tx] = (c0 + i < c1 && t0 + tx < M) ? xT[static_cast<size_t>(c0 + i) * ld + t0 + tx] : 0.f;
     __syncthreads();
-    for (int i = ty; i < 32; i += 8)
-        if (t0 + i < M && c0 + tx < c1) {
-            int row = t0 + i;
-            if (pad_g > 0) {
-                const int x = row % pad_g, t = row / pad_g;
-                row = ((t / pad_g) * (pad_g + 2) + t % pad_g + 1) * (pad_g + 2) + x + 1;
-            }
-            out[static_cast<size_t>(row) * c1 + c0 + tx] = to_h(tile[tx][i]);
-        }
+    const int tl = threadIdx.x >> 3, cg = (threadIdx.x & 7) * 16;  // token of the block, first of this thread's 16 channels
+    if (t0 + tl >= M || c0 + cg >= c1) return;
+    int row = t0 + tl;
+    if (pad_g > 0) {
+        const int x = row % pad_g, t = row / pad_g;
+        row = ((t / pad_g) * (pad_g + 2) + t % pad_g + 1) * (pad_g + 2) + x + 1;
+    }
+    uint32_t u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = pack_h2(tile[cg + 2 * j][tl], tile[cg + 2 * j + 1][tl]);
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * c1 + c0 + cg);
+    dst[0] = make_uint4(u[0], u[1], u[2], u[3]);
+    dst[1] = make_uint4(u[4], u[5], u[6], u[7]);
 }
 
 // 3x3 im2col on a g x g grid per image, zero padding: in fp16 [M][cw] -> out fp16 [M][9*cw], column (tap, c),
@@ -345,7 +353,7 @@ extern "C" int vitad_nf_forward(const vitad_nf_weights* wp, const float* tokens,
         }
         {
             ProfScope prof("nf_operand", s);
-            dim3 grid((M + 31) / 32, (c1 + 31) / 32);
+            dim3 grid((M + 31) / 32, (c1 + kOpCh - 1) / kOpCh);
             VITAD_CUDA_OK(launch_pdl(stream_to_operand_kernel, grid, dim3(256), 0, s, static_cast<const float*>(xin), ws.ld,
                                      static_cast<__half*>(k3 ? ws.x1p : ws.x1h), M, c1, k3 ? w.grid : 0));
             VITAD_CUDA_OK(cudaGetLastError());
