@@ -206,10 +206,33 @@ class ValidatorMdn(_Pipelined):
         return _metrics(result, self.props.get("fp_thres", 0.3), self.dataset_name, on_device)
 
 
+class _Rows:
+    """Result rows appended batch by batch into one geometrically grown array: one copy per batch (from the pinned
+    staging view) instead of a per-batch copy plus a final np.concatenate."""
+
+    def __init__(self):
+        self.buf, self.n = None, 0
+
+    def append(self, a):
+        a = np.asarray(a)
+        k = a.shape[0]
+        if self.buf is None:
+            self.buf = np.empty((max(4 * k, 64),) + a.shape[1:], dtype=a.dtype)
+        elif self.n + k > self.buf.shape[0]:
+            grown = np.empty((max(2 * self.buf.shape[0], self.n + k),) + self.buf.shape[1:], dtype=self.buf.dtype)
+            grown[: self.n] = self.buf[: self.n]
+            self.buf = grown
+        self.buf[self.n: self.n + k] = a
+        self.n += k
+
+    def get(self):
+        return self.buf[: self.n]
+
+
 def _collect(validator, loop_body, dataloader, shard, with_recons=False, keep_origs=True):
     """Shared batch loop: `loop_body(images, batch_index)` → (scores, maps[, recons]) device tensors, run through the
     validator's copy/compute pipeline; returns the reference's result dictionary (fp32 numpy)."""
-    acc = {k: [] for k in ("image_scores", "pixel_scores", "image_labels", "pixel_labels", "origs", "recons")}
+    acc = {k: _Rows() for k in ("image_scores", "pixel_scores", "image_labels", "pixel_labels", "origs", "recons")}
     index, sizes = [], []
 
     def mine():
@@ -218,18 +241,19 @@ def _collect(validator, loop_body, dataloader, shard, with_recons=False, keep_or
                 yield bi, images, (images if keep_origs else None, pixel_labels, image_labels)
 
     with torch.no_grad():
-        for bi, out, (images, pixel_labels, image_labels) in validator._stream_batches(mine(), loop_body):
+        # copy=False: `out` are views of the pinned staging buffers, consumed (copied into the result rows) right here
+        for bi, out, (images, pixel_labels, image_labels) in validator._stream_batches(mine(), loop_body, copy=False):
             acc["image_scores"].append(out[0])
             acc["pixel_scores"].append(out[1])
             if with_recons:
                 acc["recons"].append(out[2])
-            acc["image_labels"].append(np.asarray(image_labels))
-            acc["pixel_labels"].append(np.asarray(pixel_labels))
+            acc["image_labels"].append(image_labels)
+            acc["pixel_labels"].append(pixel_labels)
             if keep_origs:
-                acc["origs"].append(np.asarray(images.cpu() if torch.is_tensor(images) else images))
+                acc["origs"].append(images.cpu() if torch.is_tensor(images) else images)
             index.append(bi)
             sizes.append(int(out[0].shape[0]))
-    res = {k: np.concatenate(v, axis=0) for k, v in acc.items() if v}
+    res = {k: v.get() for k, v in acc.items() if v.n}
     res["batch_index"], res["batch_sizes"] = np.asarray(index), np.asarray(sizes)
     return res
 
