@@ -36,6 +36,12 @@ def test_compute_entry_points_fail_loudly_without_gpu():
     args = _lib.LinearArgs()
     rc = _lib.lib.vitad_linear_f16(C.byref(args), None)
     assert rc == -4 and b"CPU path" in _lib.lib.vitad_last_error()  # VITAD_ERR_ARCH
+    # the entry points added for the reconstruction decoders and the input resize behave the same way
+    buf = (C.c_uint8 * 64)()
+    w = _lib.ResnetDecoderWeights()
+    assert _lib.lib.vitad_resnet_decoder_forward(C.byref(w), buf, 1, buf, 64, buf, None) == -4
+    assert _lib.lib.vitad_cnn_decoder_forward(C.byref(_lib.CnnDecoderWeights()), buf, 1, buf, 64, buf, None) == -4
+    assert _lib.lib.vitad_resize_bilinear_u8(buf, 1, 2, 2, 2, buf, buf, buf, buf, None) == -4
 
 
 def test_modules_refuse_cpu_tensors():
@@ -46,6 +52,12 @@ def test_modules_refuse_cpu_tensors():
         EncoderDeit(224)(torch.rand(1, 3, 224, 224))
     with pytest.raises(RuntimeError, match="no CPU path"):
         GaussianMixtureDensityNetwork(768, 768, 100)(torch.rand(1, 196, 768))
+    from vitad.autoencoders import DecoderResNetVariableEmbeddingSize, DecoderVanillaCNN
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DecoderResNetVariableEmbeddingSize(768)(torch.rand(1, 768))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DecoderVanillaCNN(z_space=768, first_feature_map_size=7)(torch.rand(1, 768))
 
 
 def test_state_dict_layouts_match_reference_keys():
