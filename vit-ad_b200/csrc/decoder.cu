@@ -166,6 +166,27 @@ __global__ void __launch_bounds__(256) dec_im2col3x3_kernel(const __half* __rest
     *reinterpret_cast<uint4*>(out + (t * 9 + tap) * cw + v * 8) = val;
 }
 
+// Zero the one-pixel border of a bordered NHWC activation [B, g+2, g+2, C] (the padding the implicit 3x3 convolution reads).
+// Only the 4g+4 border pixels are touched, and the kernel is a link of the programmatic-launch chain (a cudaMemsetAsync of
+// the whole buffer is not).  One thread clears 8 channels.
+__global__ void __launch_bounds__(256) dec_zero_border_kernel(__half* __restrict__ buf, int g, int c8, size_t total) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int v = static_cast<int>(idx % c8);
+    size_t r = idx / c8;
+    const int P = g + 2, nb = 4 * g + 4;
+    const int k = static_cast<int>(r % nb);
+    const size_t b = r / nb;
+    int y, x;
+    if (k < P) y = 0, x = k;                          // top row
+    else if (k < 2 * P) y = P - 1, x = k - P;         // bottom row
+    else if (k < 2 * P + g) y = k - 2 * P + 1, x = 0; // left column
+    else y = k - 2 * P - g + 1, x = P - 1;            // right column
+    reinterpret_cast<uint4*>(buf)[((b * P + y) * P + x) * c8 + v] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // nn.Upsample(size=g, mode="nearest") of a 1x1 feature map (ReverseResNet.py:135,229): out[(b, p)][c] = in[b][c].
 __global__ void __launch_bounds__(256) dec_replicate_kernel(const __half* __restrict__ in, __half* __restrict__ out, int pix,
                                                             int c8, size_t total) {
@@ -390,7 +411,10 @@ extern "C" int vitad_resnet_decoder_forward(const vitad_resnet_decoder_weights* 
         void* y = ws.x[cur ^ 1];
         // conv3 + bn3 + relu (ReverseResNet.py:89-91)
         if (implicit && (bordered_g != g || bordered_w != b.width)) {
-            VITAD_CUDA_OK(cudaMemsetAsync(ws.h1, 0, static_cast<size_t>(Mp) * b.width * 2, s));
+            const size_t total = static_cast<size_t>(batch) * (4 * g + 4) * (b.width / 8);
+            VITAD_CUDA_OK(launch_pdl(dec_zero_border_kernel, blocks_for(total), dim3(256), 0, s, static_cast<__half*>(ws.h1), g,
+                                     b.width / 8, total));
+            g_launches.fetch_add(1);
             bordered_g = g, bordered_w = b.width;
         }
         if (!implicit) bordered_g = 0;
@@ -435,7 +459,12 @@ extern "C" int vitad_resnet_decoder_forward(const vitad_resnet_decoder_weights* 
         }
         // conv1 + bn1 + identity + relu (:95-101); the last block writes the zero-bordered layout the image head reads
         const int go = b.stride == 2 ? 2 * g : g;
-        if (last) VITAD_CUDA_OK(cudaMemsetAsync(y, 0, static_cast<size_t>(batch) * (go + 2) * (go + 2) * b.cout * 2, s));
+        if (last) {
+            const size_t total = static_cast<size_t>(batch) * (4 * go + 4) * (b.cout / 8);
+            VITAD_CUDA_OK(launch_pdl(dec_zero_border_kernel, blocks_for(total), dim3(256), 0, s, static_cast<__half*>(y), go,
+                                     b.cout / 8, total));
+            g_launches.fetch_add(1);
+        }
         gemm(ws.h2, Mo, b.width, b.w1, b.b1, b.cout, VITAD_EPI_RES16_RELU_F16, y, b.cout);
         a.resid16 = resid, a.ldr = b.cout, a.res_grid = b.stride == 2 ? g : 0, a.out_pad_grid = last ? go : 0;
         if ((rc = vitad_linear_f16(&a, s))) return rc;
