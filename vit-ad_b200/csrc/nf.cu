@@ -41,53 +41,66 @@ struct EpiNfCouple {
 
     __device__ __forceinline__ void tile_begin(int, int, int) { ssum = 0.f; }
     __device__ __forceinline__ void merge(int, float2*) {}
+    // the 2 x 8 stream loads of an 8-channel chunk: rows of the channel-major stream, coalesced over the warp's 32 tokens
+    __device__ __forceinline__ void load_x(int n_tile, int q, int r, float (&x1a)[8], float (&x2a)[8]) const {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = n_tile * kNfHalf + q + j;
+            x1a[j] = __ldg(xin + static_cast<size_t>(c) * ld + r);
+            x2a[j] = __ldg(xin + static_cast<size_t>(c_half + c) * ld + r);
+        }
+    }
+    // one 8-channel chunk: accumulators + constants -> coupling, global affine, permuted stores, sum of s
+    __device__ __forceinline__ void chunk(int n_tile, int q, int row, bool valid, uint32_t taddr, const float (&x1a)[8],
+                                          const float (&x2a)[8]) {
+        uint32_t as[8], at[8];
+        tmem_ld_x8(taddr + q, as);
+        tmem_ld_x8(taddr + kNfHalf + q, at);
+        // per-channel constants: 128-bit uniform loads (the scalar form issued 8 LDG per channel)
+        const int cb = n_tile * kNfHalf + q;
+        float bs[8], bt[8], sc1[8], of1[8], sc2[8], of2[8];
+        int ip1[8], ip2[8];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            ld4(bs + 4 * v, b2p + n_tile * kNfTile + q + 4 * v);
+            ld4(bt + 4 * v, b2p + n_tile * kNfTile + kNfHalf + q + 4 * v);
+            ld4(sc1 + 4 * v, scale + cb + 4 * v);
+            ld4(of1 + 4 * v, offset + cb + 4 * v);
+            ld4(sc2 + 4 * v, scale + c_half + cb + 4 * v);
+            ld4(of2 + 4 * v, offset + c_half + cb + 4 * v);
+            ld4i(ip1 + 4 * v, inv_perm + cb + 4 * v);
+            ld4i(ip2 + 4 * v, inv_perm + c_half + cb + 4 * v);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a_s = __uint_as_float(as[j]) + bs[j];
+            const float a_t = __uint_as_float(at[j]) + bt[j];
+            // clamp * tanh(a_s) = clamp * (1 - 2 / (1 + e^{2 a_s})), two MUFU (absolute error ~1e-7; e^{2a} = inf / 0
+            // saturate to +-1); exp(s) = 2^{s log2 e}
+            const float e2 = ex2f(a_s * 2.885390081777927f);
+            const float sv = clamp * (1.0f - __fdividef(2.0f, 1.0f + e2));
+            const float y2 = x2a[j] * ex2f(sv * 1.4426950408889634f) + a_t;
+            if (valid) {
+                xout[static_cast<size_t>(ip1[j]) * ld + row] = x1a[j] * sc1[j] + of1[j];
+                xout[static_cast<size_t>(ip2[j]) * ld + row] = y2 * sc2[j] + of2[j];
+            }
+            ssum += sv;
+        }
+    }
+    // Six 8-channel chunks, software-pipelined: the stream loads of chunk i+1 are in flight while chunk i is computed (their
+    // L2 latency was the largest stall of this epilogue: 38 % of its warp samples in the ncu source page).  16-channel chunks
+    // with the same pipelining spilled (ptxas keeps this kernel at 168 registers) and ran 35 % slower.
     __device__ __forceinline__ void sub(int, int, int n_tile, int row, uint32_t taddr, int, int) {
+        static_assert(kNfHalf % 8 == 0, "8-channel chunks");
         const bool valid = row < M;
         const int r = valid ? row : 0;
-#pragma unroll 1
-        for (int q = 0; q < kNfHalf; q += 16) {
-            uint32_t as[16], at[16];
-            tmem_ld_x16(taddr + q, as);
-            tmem_ld_x16(taddr + kNfHalf + q, at);
-            // issue all 32 stream loads of this chunk before touching the accumulators (latency overlap)
-            float x1a[16], x2a[16];
+        float xa[2][2][8];
+        load_x(n_tile, 0, r, xa[0][0], xa[0][1]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int c = n_tile * kNfHalf + q + j;
-                x1a[j] = __ldg(xin + static_cast<size_t>(c) * ld + r);
-                x2a[j] = __ldg(xin + static_cast<size_t>(c_half + c) * ld + r);
-            }
-            // per-channel constants of the 16 channels: 128-bit uniform loads (the scalar form issued 8 LDG per channel)
-            const int cb = n_tile * kNfHalf + q;
-            float bs[16], bt[16], sc1[16], of1[16], sc2[16], of2[16];
-            int ip1[16], ip2[16];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                ld4(bs + 4 * v, b2p + n_tile * kNfTile + q + 4 * v);
-                ld4(bt + 4 * v, b2p + n_tile * kNfTile + kNfHalf + q + 4 * v);
-                ld4(sc1 + 4 * v, scale + cb + 4 * v);
-                ld4(of1 + 4 * v, offset + cb + 4 * v);
-                ld4(sc2 + 4 * v, scale + c_half + cb + 4 * v);
-                ld4(of2 + 4 * v, offset + c_half + cb + 4 * v);
-                ld4i(ip1 + 4 * v, inv_perm + cb + 4 * v);
-                ld4i(ip2 + 4 * v, inv_perm + c_half + cb + 4 * v);
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float a_s = __uint_as_float(as[j]) + bs[j];
-                const float a_t = __uint_as_float(at[j]) + bt[j];
-                // clamp * tanh(a_s) = clamp * (1 - 2 / (1 + e^{2 a_s})), two MUFU (absolute error ~1e-7; e^{2a} = inf / 0
-                // saturate to +-1); exp(s) = 2^{s log2 e}
-                const float e2 = ex2f(a_s * 2.885390081777927f);
-                const float sv = clamp * (1.0f - __fdividef(2.0f, 1.0f + e2));
-                const float y2 = x2a[j] * ex2f(sv * 1.4426950408889634f) + a_t;
-                if (valid) {
-                    xout[static_cast<size_t>(ip1[j]) * ld + row] = x1a[j] * sc1[j] + of1[j];
-                    xout[static_cast<size_t>(ip2[j]) * ld + row] = y2 * sc2[j] + of2[j];
-                }
-                ssum += sv;
-            }
+        for (int i = 0; i < kNfHalf / 8; ++i) {
+            if (i + 1 < kNfHalf / 8) load_x(n_tile, 8 * (i + 1), r, xa[(i + 1) & 1][0], xa[(i + 1) & 1][1]);
+            chunk(n_tile, 8 * i, row, valid, taddr, xa[i & 1][0], xa[i & 1][1]);
         }
     }
     __device__ __forceinline__ static void ld4(float* dst, const float* src) {
