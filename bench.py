@@ -1,13 +1,17 @@
 #!/usr/bin/env python
-"""Headline benchmark: images/sec of the vit-ad scoring hot path (DeiT-B encoder + GMM/MDN head with 100
-Gaussians + image scores + 224x224 anomaly maps), 224x224 synthetic images, batch 32 per GPU.
+"""Benchmarks of the vit-ad scoring hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU (oracle port)
+    python bench.py --gpus N --steps K --warmup W                 # headline: DeiT-B + GMM(100) scoring, batch 32 per GPU
+    python bench.py --workload sweep --gpus N --steps K ...        # config 5: 15-category sweep, NCCL gather + AUROC timed
+    python bench.py --impl reference --gpus N --steps K ...        # the reference algorithm on the host CPU
 
-A step = one batch of 32 images through encoder -> head -> scores/maps.  `value` is timed with the inputs
-resident in HBM; `e2e` runs the same step through the validator API from pinned host memory (H2D of the
-images and D2H of scores+maps inside the timed region).  One JSON line on stdout (rank 0).
+Headline (BASELINE.json configs[0]/[1]): a step = one batch of 32 images through encoder -> head -> image scores and
+224x224 anomaly maps; the Gumbel noise of the mixing weights is generated inside the step (the reference draws it in
+every call, MixtureDensityNetwork.py:62).  `value` is timed with the inputs resident in HBM; `e2e` runs the same step
+through the validator API from pinned host memory (H2D of the images and D2H of scores+maps inside the timed region).
+Sweep (configs[4]): a step = one pass over all 15 synthetic MVTecAD-sized categories with both heads, batches dealt
+round-robin over the ranks, the all-gather of scores/maps/labels and the AUROC / PR-AUC computation INSIDE the timed
+region.  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -15,18 +19,30 @@ import argparse
 import json
 import os
 import statistics
+import subprocess
 import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "vit-ad_b200")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+PKG = os.path.join(ROOT, "vit-ad_b200")
 
 METRIC = "images/sec (DeiT enc+GMM score, 224^2, bs32)"
 WORKLOAD = "enc_deit + MDN/GMM head (100 Gaussians) validation scoring, synthetic 224x224 MVTecAD-shaped images, batch 32 per GPU"
+SWEEP_WORKLOAD = ("full 15-category MVTecAD-sized synthetic validation sweep (DeiT + GMM(100) and DeiT + NF(20 steps) heads), "
+                  "batch 32, NCCL gather of scores/maps/labels + AUROC/PR-AUC on the device")
 ENC_GFLOP_PER_IMG = 35.31
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+REFERENCE_ROOT = os.environ.get("VITAD_REFERENCE", "/root/reference")
+NOISE_SEED = 20261018
+
+
+def headline_config(world: int, B: int, K: int) -> dict:
+    """The `config` object, identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "gaussians": K,
+            "weights": "random init of the reference constructors (seeded)",
+            "noise": "Gumbel noise of the mixing weights generated inside every step",
+            "l2": "4 rotating input batches; per-step working set (~0.45 GB of weights) exceeds the 126 MB L2, no flush",
+            "parallelism": f"batch-sharded x{world}, weight replica per rank, no data-path collective"}
 
 
 def load_peaks():
@@ -102,57 +118,127 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_images_per_sec(sample_images: int, steps: int, warmup: int, gaussians: int):
-    """The oracle port of the reference algorithm (oracle/vitad_oracle.py) on all host cores, fp32, no_grad:
-    encoder -> MDN head -> scores/maps as numpy (the span of ValidatorMDN.py:123-168)."""
+def _reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "pipeline"))
+
+
+def cpu_reference_step_fn(batch: int, gaussians: int):
+    """→ (step(), kind).  kind "reference": the reference's OWN classes, imported unchanged from the mounted reference
+    tree (EncoderDeit, GaussianMixtureDensityNetwork, ValidatorMdn.valid_loop_transformer — the span BASELINE.md §3
+    names), with oracle/shims standing in for the un-installable timm/matplotlib packages.  kind "port": the oracle's
+    restatement of the same algorithm (oracle/vitad_oracle.py) when the tree is not on this box (the GPU box).  Both run
+    fp32 on all host cores under no_grad and end with scores/maps as numpy."""
     import torch
 
-    from oracle import vitad_oracle as O
+    for p in (ROOT,):
+        if p not in sys.path:
+            sys.path.insert(0, p)
     from oracle import weights as W
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     enc_sd = W.make_deit_state_dict(seed=11)
     mdn_sd = W.make_mdn_state_dict(seed=21, num_gaussians=gaussians)
-    imgs = W.synthetic_images(seed=1, batch=sample_images)
-    g = O.gumbel_noise((sample_images, 196, gaussians), torch.Generator().manual_seed(7))
+    imgs = W.synthetic_images(seed=1, batch=batch)
+    if _reference_available() and os.environ.get("VITAD_CPU_ARM", "") != "port":
+        try:
+            sys.path.insert(0, REFERENCE_ROOT)
+            sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+            from src.classes.MixtureDensityNetwork import GaussianMixtureDensityNetwork
+            from src.classes.transformer.TransformerEncoder import EncoderDeit
+            from src.pipeline.ValidatorMDN import ValidatorMdn
+
+            assert EncoderDeit.__module__.startswith("src."), "the module overlay must not shadow the reference here"
+            enc = EncoderDeit(img_size=224, requires_grad=True)  # => pretrained=False (TransformerEncoder.py:134-136)
+            enc.load_state_dict(enc_sd, strict=True)
+            enc.eval()
+            mdn = GaussianMixtureDensityNetwork(768, 768, gaussians)
+            props = {"dataset": "synthetic", "dataclass": "bench", "num_gaussians": gaussians, "fp_thres": 0.3}
+            val = ValidatorMdn([mdn], enc, None, props, weights_object=[mdn_sd])
+            val.device = "cpu"
+            labels = (torch.zeros(batch, 1, 224, 224), torch.zeros(batch, dtype=torch.long))
+
+            def step():
+                with torch.no_grad():
+                    r = val.valid_loop_transformer([(imgs, labels[0], labels[1])])
+                return r["image_scores"], r["pixel_scores"]
+
+            return step, "reference", cores
+        except Exception as e:  # fall back to the port, say why
+            print(f"bench.py: reference classes unavailable ({e!r}); timing the oracle port", file=sys.stderr)
+    from oracle import vitad_oracle as O
+
+    gen = torch.Generator().manual_seed(7)
 
     def step():
         with torch.no_grad():
+            g = O.gumbel_noise((batch, 196, gaussians), gen)  # drawn per call, as the reference does
             tok, _ = O.deit_forward(enc_sd, imgs)
             L = O.mdn_patch_loglik(tok, mdn_sd, g)
             s, m = O.mdn_scores(O.mdn_probability_map(L), 224, 16)
         return s.numpy(), m.numpy()
 
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    return sample_images * steps / dt, dt / steps * 1e3, cores
+    return step, "port", cores
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 8
-    ips, ms, cores = cpu_reference_images_per_sec(sample, args.steps, min(args.warmup, 1), args.gaussians)
-    sample_desc = f"{sample} images per step (of the 32-image batch), {args.steps} steps, oracle port, torch fp32, {cores} threads"
+    B, K = args.batch, args.gaussians
+    step, kind, cores = cpu_reference_step_fn(B, K)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    ips, ms = B * args.steps / dt, dt / args.steps * 1e3
+    what = ("the reference's own EncoderDeit + GaussianMixtureDensityNetwork + ValidatorMdn.valid_loop_transformer"
+            if kind == "reference" else "oracle port of the reference algorithm (oracle/vitad_oracle.py)")
+    sample = f"full {B}-image batch per step, {args.steps} steps after {args.warmup} warm-up, {what}, torch fp32, {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample_desc},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample_desc},
+        "config": headline_config(args.gpus, B, K),
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
+def cpu_baseline_leg(B: int, K: int) -> dict:
+    """The reference arm on a bounded sample (1 warm-up + 2 steps of the full batch), in its own process so that the
+    reference's `src` package and this repo's overlay never meet."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--batch", str(B), "--gaussians", str(K)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)["cpu_baseline"]
+    return {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + r.stderr[-300:]}
+
+
 # ------------------------------------------------------------------------------------------- our arm
+def _setup():
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+
+    from vitad.parallel import init_from_env
+
+    rank, world, local = init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    return rank, world, local, torch.device("cuda", local)
+
+
 def run_ours(args):
+    rank, world, local, dev = _setup()
     import torch
     import torch.distributed as dist
 
@@ -160,14 +246,8 @@ def run_ours(args):
     from vitad import _lib, ops
     from vitad.encoders import EncoderDeit
     from vitad.mdn import GaussianMixtureDensityNetwork
-    from vitad.parallel import init_from_env
     from vitad.validators import ValidatorMdn
 
-    rank, world, local = init_from_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     B, K = args.batch, args.gaussians
     NBUF = 4
 
@@ -179,10 +259,8 @@ def run_ours(args):
 
     host_imgs = [W.synthetic_images(seed=100 + rank * NBUF + i, batch=B).pin_memory() for i in range(NBUF)]
     dev_imgs = [h.to(dev) for h in host_imgs]
-    gum = [-torch.empty(B, 196, K, device=dev).exponential_().log() for _ in range(NBUF)]
     props = {"dataset": "synthetic", "dataclass": "bench", "num_gaussians": K, "fp_thres": 0.3}
-    validator = ValidatorMdn([head], enc, None, props, gumbel=lambda bi, shape: gum[bi % NBUF])
-    stream = torch.cuda.current_stream()
+    validator = ValidatorMdn([head], enc, None, props, gumbel_seed=NOISE_SEED)  # noise generated in the kernel per batch
     mdn_events = []
 
     def step_device(i, timed=False):
@@ -192,7 +270,7 @@ def run_ours(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             head.timing_hook = (e0, e1)
             mdn_events.append((e0, e1))
-        prob, scores = head.score(x, gum[i % NBUF])
+        prob, scores = head.score(x, seed=NOISE_SEED, batch_index=i)  # fresh Gumbel noise drawn inside the step
         head.timing_hook = None
         maps, _ = ops.bilinear_up(prob.view(-1, 14, 14), 224, align_corners=True, post_one_minus=True)
         return scores, maps
@@ -259,15 +337,42 @@ def run_ours(args):
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
+        # sustained regime: the same step back to back for >= --sustained-seconds (the power cap pulls the SM clock down
+        # within about a second), with its own clock record and its own timing of the dominant kernel
+        sustained = None
+        if args.sustained_seconds > 0 and world == 1:
+            n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / (ms_total / args.steps)) + 1)
+            sclk = ClockSampler(local)
+            sus_events = []
+            torch.cuda.synchronize()
+            sclk.start()
+            e0.record()
+            for i in range(n_sus):
+                if i % 16 == 0:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    head.timing_hook = (a, b)
+                    sus_events.append((a, b))
+                f = enc(dev_imgs[i % NBUF])
+                prob, _s = head.score(f.patch_embedding, seed=NOISE_SEED, batch_index=i)
+                head.timing_hook = None
+                ops.bilinear_up(prob.view(-1, 14, 14), 224, align_corners=True, post_one_minus=True)
+            e1.record()
+            torch.cuda.synchronize()
+            sclk.stop()
+            ms_sus = e0.elapsed_time(e1)
+            half = sus_events[len(sus_events) // 2:]  # second half: clocks have settled
+            sustained = {"seconds": ms_sus * 1e-3, "steps": n_sus, "value": B * n_sus / (ms_sus * 1e-3),
+                         "ms_per_step": ms_sus / n_sus, "clocks": sclk.summary(),
+                         "gmm_ms_per_launch": statistics.mean(a.elapsed_time(b) for a, b in half)}
+
         # p50 latency of one image (batch 1) through the same device-resident step, synchronising every iteration
         lat_ms = []
         if world == 1:
             one = dev_imgs[0][:1].contiguous()
-            g1 = gum[0][:1].contiguous()
             for it in range(10 + 100):
                 t0 = time.perf_counter()
                 f1 = enc(one)
-                prob1, _s1 = head.score(f1.patch_embedding, g1)
+                prob1, _s1 = head.score(f1.patch_embedding, seed=NOISE_SEED, batch_index=it)
                 ops.bilinear_up(prob1.view(-1, 14, 14), 224, align_corners=True, post_one_minus=True)
                 torch.cuda.synchronize()
                 if it >= 10:
@@ -279,7 +384,7 @@ def run_ours(args):
 
                 def one_step(img):
                     f1 = enc(img)
-                    prob1, s1 = head.score(f1.patch_embedding, g1)
+                    prob1, s1 = head.score(f1.patch_embedding, seed=NOISE_SEED, batch_index=0)
                     m1, _ = ops.bilinear_up(prob1.view(-1, 14, 14), 224, align_corners=True, post_one_minus=True)
                     return s1, m1
 
@@ -317,7 +422,13 @@ def run_ours(args):
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     mdn_flops = 2.0 * (B * 196) * (2 * K * 768) * 768  # unpadded logical dims
     achieved = mdn_flops / (mdn_ms * 1e-3) / 1e12
-    peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
+    peak_burst = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
+    peak_sus = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
+    clk = clocks.summary()
+    # the peak of the regime this measurement ran in: the burst figure while the sampled SM clock stays at (>= 95 % of)
+    # its maximum, the sustained one once the power cap has pulled it down
+    burst_regime = bool(clk["sm_mhz"] and clk["sm_max_mhz"] and clk["sm_mhz"] >= 0.95 * clk["sm_max_mhz"])
+    peak = peak_burst if burst_regime else peak_sus
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
@@ -328,7 +439,7 @@ def run_ours(args):
 
     def site_work(name):
         """(bound, algorithmic work per launch, unit) of a launch site; unpadded logical sizes."""
-        if name.startswith("gemm_epi"):
+        if name.startswith("gemm_epi") or name.startswith("gemm_ln"):
             n, k = int(name.split("_n")[1].split("_")[0]), int(name.split("_k")[1].split("_")[0])
             m = B * 196 if name.startswith("gemm_epi4") else rows_tok
             return "tensor", 2.0 * m * n * k / 1e12, "TFLOP/s"
@@ -360,22 +471,25 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "gaussians": K,
-                   "weights": "random init of the reference constructors (seeded)",
-                   "l2": f"{NBUF} rotating input batches; per-step working set (~0.45 GB of weights) exceeds the 126 MB L2, no flush",
-                   "parallelism": f"batch-sharded x{world}, weight replica per rank, no data-path collective"},
-        "clocks": clocks.summary(),
+        "config": headline_config(world, B, K),
+        "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4 + B * 224 * 224 * 4,
                 "result_interval_ms": {"p50": round(statistics.median(e2e_wall), 3), "max": round(max(e2e_wall), 3)}},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "gmm fused sigma/mu projection + logsumexp (gemm4_tc_kernel<208,1,EpiMdn<104>> on 33 clusters of four + the CTA-pair kernel on the 16 SMs they leave idle) + feature mean",
                      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src + ", sustained bf16/fp16 dense",
+                     "peak_regime": "burst" if burst_regime else "sustained",
+                     "frac_of_burst_peak": achieved / peak_burst, "frac_of_sustained_peak": achieved / peak_sus,
+                     "traffic": traffic, "peak_source": peak_src + ": dense bf16/fp16 cuBLAS, burst "
+                     f"{peak_burst:.0f} / sustained {peak_sus:.0f} TFLOP/s; regime chosen from the SM clock sampled in the timed region",
                      "flops_per_launch": mdn_flops, "ms_per_launch": mdn_ms,
                      "encoder_tflops": ENC_GFLOP_PER_IMG * B * 1e9 / ((ms_step - mdn_ms) * 1e-3) / 1e12},
         "kernels": kernels,
     }
+    if sustained is not None:
+        sustained["gmm_frac_of_sustained_peak"] = mdn_flops / (sustained["gmm_ms_per_launch"] * 1e-3) / 1e12 / peak_sus
+        out["sustained"] = sustained
     if lat_ms:
         out["latency_bs1_ms"] = {"p50": round(statistics.median(lat_ms), 4), "p90": round(sorted(lat_ms)[89], 4),
                                  "iters": len(lat_ms), "how": "host wall clock around one batch-1 step + device synchronize"}
@@ -385,34 +499,119 @@ def run_ours(args):
         if graph_err:
             out["latency_bs1_ms"]["cuda_graph_error"] = graph_err
     if world == 1 and not args.no_cpu_baseline:
-        sample = 8
-        ips, _, cores = cpu_reference_images_per_sec(sample, 2, 1, K)
-        out["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                               "sample": f"{sample} images x 2 steps (1 warm-up) of the same workload, oracle port, torch fp32"}
+        out["cpu_baseline"] = cpu_baseline_leg(B, K)
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------- config 5
+def run_sweep_bench(args):
+    rank, world, local, dev = _setup()
+    import torch
+    import torch.distributed as dist
+
+    from vitad import _lib
+    from vitad.parallel import warm_up
+    from vitad.sweep import build_sweep_models, make_sweep_data, run_sweep
+
+    K = args.gaussians
+    v_gmm, v_nf = build_sweep_models(rank, world, dev, K)
+    host = make_sweep_data(args.categories or None, pin=True)
+    n_images = sum(int(t[0].shape[0]) for t in host.values())
+    # masks as one byte per pixel (what a loader that keeps the PNG's dtype delivers); images fp32 in pinned memory
+    host = {k: (t[0], t[1], (t[2] != 0).to(torch.uint8)) for k, t in host.items()}
+    resident = {k: (t[0].to(dev), t[1], t[2].to(dev)) for k, t in host.items()}
+    warm_up(dev)  # NCCL communicator set-up outside the timed region
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(data, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = run_sweep(v_gmm, v_nf, data, rank, world, batch_size=args.batch)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), last
+
+    W_ = max(args.warmup, 3) if not args.sweep_light_warmup else 1
+    for _ in range(W_):
+        run_sweep(v_gmm, v_nf, resident, rank, world, batch_size=args.batch)
+    clocks = ClockSampler(local)
+    launches0 = _lib.launch_count()
+    clocks.start()
+    ms_total, last = timed(resident, args.steps)
+    clocks.stop()
+    launches = _lib.launch_count() - launches0
+    run_sweep(v_gmm, v_nf, host, rank, world, batch_size=args.batch)
+    ms_e2e, last_e2e = timed(host, args.steps)
+    if rank != 0:
+        return
+    heads = 2
+    scored = heads * n_images
+    img_bytes = n_images * 3 * 224 * 224 * 4
+    mask_bytes = n_images * 224 * 224
+    metrics = last_e2e["metrics"]
+    n_metric_floats = sum(len(v) for v in metrics.values())
+    out = {
+        "metric": "images/sec (15-category sweep: DeiT + GMM/NF scoring, NCCL gather, AUROC)", "value": scored * args.steps / (ms_total * 1e-3),
+        "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W_, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+        "config": {"workload": SWEEP_WORKLOAD, "categories": len(host), "images": n_images, "heads_per_image": heads,
+                   "images_scored_per_step": scored, "batch": args.batch, "gaussians": K,
+                   "timed_region": "scoring of every batch + all_gather of scores/maps/labels per category + image/pixel AUROC, PR-AUC, PRO on the device",
+                   "l2": "1725 distinct images (1.04 GB fp32) per step, far beyond the 126 MB L2",
+                   "parallelism": f"batches dealt round-robin over {world} ranks, weight replica per rank, one all_gather per category and head (async, overlapped with the next category), metrics of category c on rank c % {world}"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": scored * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": heads * (img_bytes + mask_bytes), "d2h_bytes_per_step": 8 * n_metric_floats,
+                "note": "whole job: every image + mask crosses PCIe once per head from pinned host memory (each rank copies its own batches); only metric values come back"},
+        "gpu_launches": int(launches),
+        "metrics_sample": {k: {m: round(v, 4) for m, v in metrics[k].items()} for k in list(metrics)[:4]},
+        "metrics_checksum": round(sum(v for d in metrics.values() for v in d.values()), 6),
+    }
     print(json.dumps(out))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="headline", choices=["headline", "sweep"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--gaussians", type=int, default=100)
+    ap.add_argument("--categories", type=int, default=0, help="sweep: first N categories only (0 = all 15)")
+    ap.add_argument("--sweep-light-warmup", action="store_true", help="sweep: one warm-up pass instead of max(W, 3)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="headline: length of the extra sustained-regime loop (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 50 if args.workload == "headline" and args.impl == "ours" else 5
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_ours(args)
-        try:
-            import torch.distributed as dist
+        return
+    (run_sweep_bench if args.workload == "sweep" else run_ours)(args)
+    try:
+        import torch.distributed as dist
 
-            if dist.is_initialized():
-                dist.destroy_process_group()
-        except Exception:
-            pass
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

@@ -276,6 +276,16 @@ int vitad_gmm_pack_weights(const float* sigma_w, const float* sigma_b, const flo
 int vitad_gmm_make_operand(const float* x, int ldx, void* xaug, int tokens, int dim, void* stream);
 int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, const float* pi_b, const float* gumbel, float* lp2,
                      int tokens, int dim, int num_gaussians, void* stream);
+/* The same with the Gumbel noise generated inside the kernel instead of read from memory.  The reference draws it from
+ * torch's global generator in every call (F.gumbel_softmax, MixtureDensityNetwork.py:62), so its scores depend on the
+ * call order; here element (token t, mixture k) of global batch `batch_index` gets
+ *   g = -log(-log(u)),  u = ((w >> 8) + 0.5) * 2^-24,
+ *   w = word (k/32)%4 of Philox4x32-10(key = seed, counter = (t, k%32, k/128, batch_index)),
+ * a pure function of its arguments: a batch scores the same on whichever rank and in whichever order it runs
+ * (ValidatorMdn, rank/world_size).  vitad_gumbel_noise writes that noise as fp32 [tokens, num_gaussians]. */
+int vitad_gmm_log_pi_seeded(const float* x, int ldx, const float* pi_w, const float* pi_b, uint64_t seed,
+                            uint32_t batch_index, float* lp2, int tokens, int dim, int num_gaussians, void* stream);
+int vitad_gumbel_noise(uint64_t seed, uint32_t batch_index, float* out, int tokens, int num_gaussians, void* stream);
 /* The same on the tensor cores (split-fp16 operands x = xh + xl, W = Wh + Wl): pi_packed fp16 [K, 3*dim] from
  * vitad_gmm_pack_pi (pi.weight fp32 [K, dim]); workspace of vitad_gmm_log_pi_workspace_bytes, 256-byte aligned.
  * 2x faster, but the tensor core's truncating fp32 accumulation is ~5x less accurate than vitad_gmm_log_pi

@@ -193,6 +193,26 @@ def case_gmm_head_k130():
     save("gmm_head_k130_p49", **out)
 
 
+def case_gmm_head_k150():
+    """Head only at the reference's default mixture count (startTraining_mdn.py:37, README `-n 150`) and at the largest
+    count its result tables report (170, csv_results_gmm): B=2, P=49, random unit-variance features."""
+    from src.classes.MixtureDensityNetwork import GaussianMixtureDensityNetwork, get_probability_map, log_likelihood
+
+    out = {}
+    for K in (150, 170):
+        sd = W.make_mdn_state_dict(seed=20 + K, num_gaussians=K, stress=True)
+        mdn = GaussianMixtureDensityNetwork(768, 768, K)
+        mdn.load_state_dict(sd, strict=True)
+        mdn.eval()
+        x = torch.randn(2, 49, 768, generator=torch.Generator().manual_seed(K))
+        with torch.no_grad(), GumbelInjector(seed=900 + K):
+            r = mdn(x)
+            out[f"k{K}_L"] = log_likelihood(x, r.pi, r.sigma, r.mu).mean(2).numpy()
+        with torch.no_grad(), GumbelInjector(seed=900 + K):
+            out[f"k{K}_prob"] = get_probability_map(x, r.pi, r.sigma, r.mu).numpy()
+    save("gmm_head_k150_k170_p49", **out)
+
+
 def case_nf_validator():
     """ValidatorNF.valid_loop_transformer_nf: DeiT (stress) + NormalizingFlow(768,224,196,0.16,20), B=2."""
     from src.classes.NormalizingFlow import NormalizingFlow
@@ -294,6 +314,7 @@ CASES = {
     "esvit_interpolate": case_esvit_interpolate,
     "gmm_validator": case_gmm_validator,
     "gmm_head_k130": case_gmm_head_k130,
+    "gmm_head_k150": case_gmm_head_k150,
     "nf_validator": case_nf_validator,
     "recon_l2": case_recon_l2,
     "recon_validator": case_recon_validator,

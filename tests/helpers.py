@@ -24,3 +24,45 @@ def rel_err(a, b, floor=1e-3):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def assert_rel(got, ref, tol=1e-3, floor_frac=0.05, what=""):
+    """Per-element parity: |got - ref| <= tol * max(|ref|, floor), floor = floor_frac * max|ref| (SURVEY.md §7's
+    `|a-b| <= 1e-3 * max(|b|, floor)`).  The floor exists because the scores have exact zeros — the batch's arg-max patch
+    scores exactly 0 (MixtureDensityNetwork.py:90-95), an anomaly-free pixel of an L2 map can be ~0 — where a relative
+    error is undefined; elements above 5 % of the largest one are held to `tol` relative each."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    floor = floor_frac * np.abs(ref).max()
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), floor)
+    worst = np.unravel_index(np.argmax(err), err.shape) if err.size else ()
+    assert err.size == 0 or err.max() <= tol, f"{what}: max per-element relative error {err.max():.3e} > {tol:g} at {worst} " \
+                                               f"(got {got[worst]:.6g}, ref {ref[worst]:.6g}, floor {floor:.3g})"
+    return float(err.max()) if err.size else 0.0
+
+
+# Fixed synthetic anomaly sets of the AUROC parity tests: one seed per image of vitad.synthetic.make_designed_set, picked by
+# tools/design_anomaly_sets.py so that the ORACLE's image scores of the whole set are pairwise >= 11x the allowed numerical
+# noise (1e-3 of the largest score) apart, with both labels interleaved along the score axis.  The tests assert >= 10x.
+DESIGNED_GMM = [9022, 9102, 9008, 9154, 9125, 9129, 9002, 9047, 9123, 9105, 9018, 9025, 9044, 9153, 9132, 9127, 9113, 9059,
+                9136, 9051, 9128, 9109, 9155, 9054]
+GMM_NOISE_SEED_BASE = 4242  # image with seed s gets gumbel_noise((196, K), seed 4242 + s)
+DESIGNED_NF = [9634, 9580, 9626, 9563, 9562, 9505, 9552, 9522, 9547, 9515]
+NF_TEST_GAIN = 3.0  # synth_weights.make_nf_state_dict(subnet_gain=...): keeps the NF image scores out of saturation
+DESIGNED_RECON = [9869, 9945, 9801, 9901, 9832, 9865, 9806, 9840, 9933, 9812, 9947, 9939, 9888, 9813, 9846, 9885]
+
+
+def assert_designed_separation(ref_scores, labels, factor=10.0):
+    """The whole set is separated: every pair of oracle scores is >= factor x (1e-3 * max score) apart, both labels occur
+    and neither label sits entirely on one side of the score axis (so AUROC is neither 0 nor 1 by construction)."""
+    ref_scores = np.asarray(ref_scores, dtype=np.float64)
+    labels = np.asarray(labels)
+    noise = 1e-3 * np.abs(ref_scores).max()
+    gaps = np.diff(np.sort(ref_scores))
+    assert gaps.min() >= factor * noise, (gaps.min(), factor * noise)
+    order = np.argsort(ref_scores)
+    lab = labels[order]
+    assert 2 <= lab.sum() <= len(lab) - 2
+    assert lab[: len(lab) // 2].sum() > 0 or lab[len(lab) // 2:].sum() < lab.sum(), "labels are not interleaved"
+    return noise

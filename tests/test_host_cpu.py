@@ -117,19 +117,36 @@ n = sum(sizes)
 assert np.array_equal(full["image_scores"], np.arange(n, dtype=np.float32) * 0.5), full["image_scores"]
 assert np.array_equal(full["image_labels"], np.arange(n) % 2)
 assert full["pixel_scores"].shape == (n, 1, 4, 4) and np.array_equal(full["pixel_scores"][:, 0, 0, 0], np.arange(n, dtype=np.float32))
+# the same rows as torch tensors (valid_loop_*(on_device=True)): gathered without a numpy round trip, tensors come back
+rest = {k: (torch.from_numpy(v) if k not in ("batch_index", "batch_sizes") else v) for k, v in res.items()}
+rest["pixel_labels"] = rest["pixel_labels"].to(torch.uint8)
+pend = gather_results(rest, num_batches=len(sizes), device=torch.device("cpu"), async_op=True)
+full_t = pend.result()
+assert torch.is_tensor(full_t["image_scores"]) and full_t["pixel_labels"].dtype == torch.uint8
+assert np.array_equal(full_t["image_scores"].numpy(), full["image_scores"]) and np.array_equal(full_t["pixel_scores"].numpy(), full["pixel_scores"])
+# fewer batches than ranks: the rank without a batch must take part in the collectives with empty payloads (no hang, no raise)
+one = [b for b in range(1) if _BatchSharding(rank, world).mine(b)]
+r1 = {"image_scores": np.arange(3, dtype=np.float32), "pixel_scores": np.ones((3, 1, 4, 4), np.float32), "image_labels": np.array([0, 1, 0]),
+      "pixel_labels": np.zeros((3, 1, 4, 4), np.float32), "batch_index": np.asarray([0]), "batch_sizes": np.asarray([3])} if one else \
+     {"batch_index": np.zeros(0, np.int64), "batch_sizes": np.zeros(0, np.int64)}
+f1 = gather_results(r1, num_batches=1, device=torch.device("cpu"))
+assert np.array_equal(f1["image_scores"], np.arange(3, dtype=np.float32)) and f1["pixel_scores"].shape == (3, 1, 4, 4)
+assert np.array_equal(f1["image_labels"], [0, 1, 0])
 torch.distributed.destroy_process_group()
 print("rank", rank, "ok")
 """
 
 
-def test_batch_sharded_gather_world_size_2_gloo(tmp_path):
+@pytest.mark.parametrize("world", [2, 3])
+def test_batch_sharded_gather_gloo(tmp_path, world):
+    """world 2: the N>1 path; world 3: also ranks that hold nothing (one batch on three ranks)."""
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29531", str(script), ROOT]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(29531 + world), str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.count("ok") == 2
+    assert r.stdout.count("ok") == world
 
 
 @pytest.mark.parametrize("seed,n,ties", [(0, 500, False), (1, 4000, True), (2, 37, True), (3, 20000, True)])
@@ -157,6 +174,56 @@ def test_device_metrics_equal_sklearn(seed, n, ties):
         assert G.calc_threshold(ts, ty, fpr_t) == pytest.approx(thr, abs=0), (fpr_t, thr)
         an = np.where(s > thr, s, 0)
         assert abs(G.roc_auc_score(torch.from_numpy(an), ty) - skm.roc_auc_score(y, an)) < 1e-9
+
+
+@pytest.mark.parametrize("seed,n,levels", [(0, 3000, 6), (1, 3000, 11), (2, 50000, 24), (3, 200, 3), (4, 4000, 64)])
+def test_device_threshold_and_pro_with_collinear_ties(seed, n, levels):
+    """Tie-heavy NON-NEGATIVE scores (few distinct levels, as anomaly maps quantise) whose per-level positive share is
+    constant over runs of levels: roc_curve(drop_intermediate=True) then drops collinear points together with their
+    thresholds, and ValidationHelper.calc_threshold (:70-88) must be reproduced on the kept points only.  Also pins
+    the one-sort derivation of the thresholded-map AUROC (predict_anomaly 'fluently', :91-104) against sklearn."""
+    import torch
+    from sklearn import metrics as skm
+
+    from vitad import gpu_metrics as G
+    from vitad.metrics import calc_threshold as sk_threshold
+
+    rng = np.random.default_rng(seed)
+    # upper half of the levels: the SAME (positives, negatives) count per level -> equal ROC increments -> diff(fps, 2) ==
+    # diff(tps, 2) == 0 at the interior levels of the run; lower half: random counts
+    per = max(4, n // (2 * levels))
+    lev_list, y_list = [], []
+    for v in range(levels):
+        if v >= levels // 2:
+            n_pos, n_neg = per // 4, per - per // 4
+        else:
+            n_pos, n_neg = int(rng.integers(0, per // 8 + 1)), int(rng.integers(1, per))
+        lev_list += [v] * (n_pos + n_neg)
+        y_list += [1.0] * n_pos + [0.0] * n_neg
+    perm = rng.permutation(len(lev_list))
+    lev, y = np.asarray(lev_list)[perm], np.asarray(y_list, np.float32)[perm]
+    s = (lev / levels).astype(np.float32)
+    ts, ty = torch.from_numpy(s), torch.from_numpy(y)
+    fpr, tpr, thr_all = skm.roc_curve(y, s)
+    fpr_full, _, _ = skm.roc_curve(y, s, drop_intermediate=False)
+    assert len(fpr) < len(fpr_full) or levels <= 3, "the case is meant to make drop_intermediate drop points"
+    c = G.Curve(ts, ty)
+    for fpr_t in (0.02, 0.1, 0.3, 0.5, 0.75, 1.0):
+        thr = sk_threshold(s, y, fpr_t)
+        assert G.calc_threshold(ts, ty, fpr_t, c) == pytest.approx(thr, abs=0), (fpr_t, thr)
+        an = np.where(s > thr, s, 0)
+        ref = skm.roc_auc_score(y, an)
+        assert abs(G.thresholded_roc_auc(c, thr) - ref) < 1e-9, (fpr_t, thr)
+        assert abs(G.roc_auc_score(torch.from_numpy(an), ty) - ref) < 1e-9
+    out = G.calc_all_metrics_device({"image_scores": s[:64], "image_labels": np.r_[y[:62], 0, 1], "pixel_scores": s,
+                                     "pixel_labels": y}, fp_thres=0.3, device=torch.device("cpu"))
+    from vitad.metrics import calc_all_metrics
+
+    ref = calc_all_metrics({"image_scores": s[:64], "image_labels": np.r_[y[:62], 0, 1], "pixel_scores": s,
+                            "pixel_labels": y}, fp_thres=0.3)
+    for k, v in ref.items():
+        if isinstance(v, float):
+            assert abs(out[k] - v) < 1e-9, (k, out[k], v)
 
 
 def test_esvit_checkpoint_position_encoding_interpolation():

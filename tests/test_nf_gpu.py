@@ -33,9 +33,11 @@ def test_nf_head_matches_oracle(stress, B):
         r2 = nf(O.tokens_to_nchw(tokens).cuda())  # the reference's NCHW entry point
     torch.cuda.synchronize()
     ref = amap.numpy()
-    assert np.abs(r.anomaly_score_map.cpu().numpy() - ref).max() <= 1e-3 * np.abs(ref).max()
-    assert np.abs(r2.anomaly_score_map.cpu().numpy() - ref).max() <= 1e-3 * np.abs(ref).max()
-    assert np.abs(r.image_max.cpu().numpy() - O.nf_scores(amap).numpy()).max() <= 1e-3 * np.abs(ref).max()
+    from helpers import assert_rel
+
+    assert_rel(r.anomaly_score_map.cpu().numpy(), ref, 1e-3, what="NF map (tokens)")
+    assert_rel(r2.anomaly_score_map.cpu().numpy(), ref, 1e-3, what="NF map (NCHW)")
+    assert_rel(r.image_max.cpu().numpy(), O.nf_scores(amap).numpy(), 1e-3, what="NF image max")
     assert abs(r.loss.item() - loss.item()) <= 2e-3 * abs(loss.item())
 
 
@@ -59,46 +61,42 @@ def test_nf_validator_matches_reference_golden(tag, stress):
     res = val.valid_loop_transformer_nf(batches)
     ref_s, ref_m = g[f"{tag}_image_scores"], g[f"{tag}_pixel_scores_sub"]
     assert res["pixel_scores"].shape == (2, 1, 224, 224)
-    assert np.abs(res["image_scores"] - ref_s).max() <= 1e-3 * np.abs(ref_s).max(), (res["image_scores"], ref_s)
-    assert np.abs(res["pixel_scores"][:, :, ::8, ::8] - ref_m).max() <= 1e-3 * np.abs(ref_m).max()
+    from helpers import assert_rel
+
+    assert_rel(res["image_scores"], ref_s, 1e-3, what="NF image scores")
+    assert_rel(res["pixel_scores"][:, :, ::8, ::8], ref_m, 1e-3, what="NF maps")
     np.testing.assert_allclose(res["pixel_scores"].sum(axis=(1, 2, 3)), g[f"{tag}_pixel_scores_sum"], rtol=2e-3)
 
 
 def test_nf_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
-    """north_star's AUROC criterion for the NF head (config 2): ValidatorNF over 24 synthetic MVTec-shaped images, about half of
-    them with pasted anomalies, against the oracle (DeiT block 8 features -> 20-step flow -> amax of the bilinear map)."""
+    """north_star's AUROC criterion for the NF head (config 2): ValidatorNF over the whole designed set against the oracle
+    (DeiT last-block features -> 20-step flow -> amax of the bilinear map).  NF image scores = max over pixels of
+    1 - exp(-mean_c z^2 / 2) live in a narrow band (random-init flows map every image to similar |z|): the designed set is
+    the 10 images of a 160-image pool whose oracle scores are >= 10x the allowed noise apart (asserted), scored with flow
+    weights whose subnet gain keeps the scores out of saturation."""
     from sklearn.metrics import roc_auc_score
 
+    from helpers import DESIGNED_NF, NF_TEST_GAIN, assert_designed_separation, assert_rel
     from oracle import vitad_oracle as O
     from oracle import weights as W
     from vitad.encoders import EncoderDeit
-    from vitad.synthetic import batches, make_category
+    from vitad.synthetic import batches, make_designed_set
     from vitad.validators import BLOCK_INDEX_DEIT, ValidatorNF
 
-    n = 24
-    images, labels, masks = make_category("cable", n, seed=78)
+    images, labels, masks = make_designed_set(DESIGNED_NF)
     enc_sd = W.make_deit_state_dict(seed=11, stress=True)
-    nf_sd = W.make_nf_state_dict(seed=31, stress=True)
+    nf_sd = W.make_nf_state_dict(seed=31, stress=True, subnet_gain=NF_TEST_GAIN)
     with torch.no_grad():
         tok, _ = O.deit_forward(enc_sd, images, block_index=BLOCK_INDEX_DEIT)
         _, amap, _, _ = O.nf_forward(nf_sd, O.tokens_to_nchw(tok), flow_steps=20, img_size=224)
         ref_scores = O.nf_scores(amap).numpy()
+    assert_designed_separation(ref_scores, labels.numpy(), factor=10.0)
     enc = EncoderDeit(224)
     enc.load_state_dict(enc_sd)
-    props = {"dataset": "synthetic", "dataclass": "cable", "fp_thres": 0.3}
+    props = {"dataset": "synthetic", "dataclass": "designed", "fp_thres": 0.3}
     val = ValidatorNF([_flow(nf_sd)], enc, None, props)
-    res = val.valid_loop_transformer_nf(batches(images, labels, masks, batch_size=8))  # NF scores are per-image: any batching
-    noise = 1e-3 * np.abs(ref_scores).max()
-    assert np.abs(res["image_scores"] - ref_scores).max() <= noise
-    assert np.abs(res["pixel_scores"] - amap.numpy()).max() <= 1e-3 * np.abs(amap.numpy()).max()
-    # images whose oracle scores are separated by >= 4x the allowed noise (a near-tie could swap without any kernel error)
-    keep, last = [], -np.inf
-    for i in np.argsort(ref_scores):
-        if ref_scores[i] - last >= 4 * noise:
-            keep.append(i)
-            last = ref_scores[i]
-    keep = np.asarray(sorted(keep))
-    lab = labels.numpy()[keep]
-    assert len(keep) >= 8 and 2 <= lab.sum() <= len(keep) - 2, (len(keep), lab.sum())
-    assert round(roc_auc_score(res["image_labels"][keep], res["image_scores"][keep]), 4) == round(
-        roc_auc_score(lab, ref_scores[keep]), 4)
+    res = val.valid_loop_transformer_nf(batches(images, labels, masks, batch_size=4))  # NF scores are per-image: any batching
+    assert_rel(res["image_scores"], ref_scores, 1e-3, what="NF image scores")
+    assert_rel(res["pixel_scores"], amap.numpy(), 1e-3, what="NF anomaly maps")
+    assert np.array_equal(np.argsort(ref_scores), np.argsort(res["image_scores"]))
+    assert round(roc_auc_score(res["image_labels"], res["image_scores"]), 4) == round(roc_auc_score(labels.numpy(), ref_scores), 4)

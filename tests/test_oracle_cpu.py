@@ -154,3 +154,35 @@ def test_esvit_oracle_matches_reference_golden(tag, stress):
     np.testing.assert_allclose(tok.numpy()[:, ::3], g[f"{tag}_tokens"], rtol=0, atol=3e-4)
     np.testing.assert_allclose(tok.sum(-1).numpy(), g[f"{tag}_token_sum"], rtol=0, atol=5e-3)
     np.testing.assert_allclose(latent.numpy(), g[f"{tag}_latent"], rtol=0, atol=3e-4)
+
+
+def test_designed_anomaly_sets_are_separated_under_the_oracle():
+    """The fixed sets of the AUROC parity tests (helpers.DESIGNED_*; tools/design_anomaly_sets.py) keep their property on
+    this machine's CPU: the oracle's image scores of the WHOLE set are pairwise >= 10x the allowed numerical noise (1e-3
+    of the largest score) apart, with both labels interleaved.  (The GPU tests assert the same before comparing.)"""
+    from helpers import (DESIGNED_GMM, DESIGNED_NF, DESIGNED_RECON, GMM_NOISE_SEED_BASE, NF_TEST_GAIN,
+                         assert_designed_separation)
+    from oracle import vitad_oracle as O
+    from oracle import weights as W
+    from vitad.synthetic import make_designed_set
+
+    enc_sd = W.make_deit_state_dict(seed=11, stress=True)
+    with torch.no_grad():
+        images, labels, _ = make_designed_set(DESIGNED_GMM)
+        g = torch.stack([O.gumbel_noise((196, 100), torch.Generator().manual_seed(GMM_NOISE_SEED_BASE + s)) for s in DESIGNED_GMM])
+        tok, _ = O.deit_forward(enc_sd, images)
+        s, _ = O.mdn_scores(O.mdn_probability_map(O.mdn_patch_loglik(tok, W.make_mdn_state_dict(21, 100, stress=True), g)), 224, 16)
+        assert_designed_separation(s.numpy(), labels.numpy())
+
+        images, labels, _ = make_designed_set(DESIGNED_NF)
+        tok, _ = O.deit_forward(enc_sd, images, block_index=0)
+        nf_sd = W.make_nf_state_dict(seed=31, stress=True, subnet_gain=NF_TEST_GAIN)
+        _, amap, _, _ = O.nf_forward(nf_sd, O.tokens_to_nchw(tok), flow_steps=20, img_size=224)
+        assert_designed_separation(O.nf_scores(amap).numpy(), labels.numpy())
+
+        images, labels, _ = make_designed_set(DESIGNED_RECON)
+        sd = {("encoder." + k): v for k, v in enc_sd.items()}
+        sd.update(W.make_resnet_decoder_state_dict(seed=43))
+        _, cls = O.deit_forward(sd, images, prefix="encoder.deit.")
+        sc, _ = O.recon_l2_scores(O.resnet_decoder_forward(sd, cls), images)
+        assert_designed_separation(sc.numpy(), labels.numpy())

@@ -405,6 +405,7 @@ extern "C" int vitad_debug_timeline_attention(void* device_buffer) {
 #endif
 
 extern "C" int vitad_attention_f16(const vitad_attention_args* args, void* stream) {
+    VITAD_NVTX("vitad_attention_f16");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(args, VITAD_ERR_ARG, "null args");

@@ -300,6 +300,7 @@ extern "C" size_t vitad_cnn_decoder_workspace_bytes(const vitad_cnn_decoder_weig
 
 extern "C" int vitad_cnn_decoder_forward(const vitad_cnn_decoder_weights* wp, const float* latent, int batch,
                                          void* workspace, size_t workspace_bytes, float* recon, void* stream) {
+    VITAD_NVTX("vitad_cnn_decoder_forward");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(wp && latent && workspace && recon, VITAD_ERR_ARG, "null pointer");
@@ -364,6 +365,7 @@ extern "C" size_t vitad_resnet_decoder_workspace_bytes(const vitad_resnet_decode
 
 extern "C" int vitad_resnet_decoder_forward(const vitad_resnet_decoder_weights* wp, const float* latent, int batch,
                                             void* workspace, size_t workspace_bytes, float* recon, void* stream) {
+    VITAD_NVTX("vitad_resnet_decoder_forward");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(wp && latent && workspace && recon && batch > 0, VITAD_ERR_ARG, "null pointer or empty batch");

@@ -60,6 +60,7 @@ static int deit_forward_impl(const vitad_deit_weights* wp, const void* images, b
 extern "C" int vitad_deit_forward(const vitad_deit_weights* wp, const float* images, int batch, int block_index,
                                   void* workspace, size_t workspace_bytes, float* out_tokens, float* out_cls,
                                   void* out_xaug, int ld_xaug, void* stream) {
+    VITAD_NVTX("vitad_deit_forward");
     return deit_forward_impl(wp, images, false, batch, block_index, workspace, workspace_bytes, out_tokens, out_cls,
                              out_xaug, ld_xaug, stream);
 }
@@ -67,6 +68,7 @@ extern "C" int vitad_deit_forward(const vitad_deit_weights* wp, const float* ima
 extern "C" int vitad_deit_forward_u8(const vitad_deit_weights* wp, const uint8_t* images, int batch, int block_index,
                                      void* workspace, size_t workspace_bytes, float* out_tokens, float* out_cls,
                                      void* out_xaug, int ld_xaug, void* stream) {
+    VITAD_NVTX("vitad_deit_forward_u8");
     return deit_forward_impl(wp, images, true, batch, block_index, workspace, workspace_bytes, out_tokens, out_cls,
                              out_xaug, ld_xaug, stream);
 }

@@ -1,5 +1,6 @@
 #include "host_util.cuh"
 
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 
 #include <atomic>
@@ -164,7 +165,9 @@ struct ProfRec {
 };
 static std::atomic<int> g_prof_on{0};
 static std::vector<ProfRec> g_prof;
-ProfScope::ProfScope(const char* name, cudaStream_t s) : idx(-1), stream(s) {
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
+ProfScope::ProfScope(const char* name, cudaStream_t s) : idx(-1), stream(s), nvtx(name) {
     if (!g_prof_on.load()) return;
     ProfRec r;
     r.name = name;

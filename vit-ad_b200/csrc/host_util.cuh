@@ -66,12 +66,20 @@ int check_device_arch();  // VITAD_OK only on compute capability 10.x
 
 }  // namespace vitad
 
-// ---- optional in-library profiler (CUDA events around every launch site; off by default) ----
+// ---- tracing: NVTX ranges (no-ops unless a tool such as nsys/ncu injects an NVTX library) around every
+// C-ABI entry point (VITAD_NVTX) and every launch site (ProfScope), plus the optional in-library profiler (CUDA events
+// around every launch site; off by default) ----
 namespace vitad {
+struct NvtxRange {
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+};
+#define VITAD_NVTX(name) ::vitad::NvtxRange nvtx_range__(name)
 struct ProfScope {
     ProfScope(const char* name, cudaStream_t stream);
     ~ProfScope();
     int idx;
     cudaStream_t stream;
+    NvtxRange nvtx;
 };
 }  // namespace vitad

@@ -186,6 +186,57 @@ __global__ void __launch_bounds__(256) gmm_operand_kernel(const float* __restric
     *reinterpret_cast<uint2*>(xaug + t * kMdnKA + c) = u;
 }
 
+
+// ------------------------------------------------------------------------ counter-based Gumbel noise
+// The reference draws fresh Gumbel noise in every log_likelihood call (gumbel_softmax, MixtureDensityNetwork.py:62) from
+// torch's global generator, so a score depends on how many draws preceded it.  Here the noise of element (t, k) of
+// global batch `batch_index` is a pure function of (seed, batch_index, t, k): Philox4x32-10 with key = seed and counter =
+// (t, k % 32, (k / 32) / 4, batch_index), word (k / 32) % 4, mapped to g = -log(-log(u)), u = (word >> 8 + 0.5) * 2^-24 in
+// (0, 1).  A sharded run (rank r scores batches r, r + W, ...) therefore reproduces the unsharded scores bit for bit.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ key.x, lo1, hi0 ^ c.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float gumbel_from_word(uint32_t w) {
+    const float u = (static_cast<float>(w >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24: exact, never 0 or 1
+    return -logf(-logf(u));
+}
+struct GumbelKey {
+    uint32_t seed_lo, seed_hi, batch_index;
+};
+// the four noise values of lane tx (mixtures tx + 32 (4 q + w), w = 0..3) of token t
+__device__ __forceinline__ void gumbel4(const GumbelKey& gk, int t, int tx, int q, float (&g)[4]) {
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(t), static_cast<uint32_t>(tx), static_cast<uint32_t>(q),
+                                             gk.batch_index),
+                                  make_uint2(gk.seed_lo, gk.seed_hi));
+    g[0] = gumbel_from_word(r.x);
+    g[1] = gumbel_from_word(r.y);
+    g[2] = gumbel_from_word(r.z);
+    g[3] = gumbel_from_word(r.w);
+}
+// out[t][k] fp32 = the noise the seeded log_pi kernels add (tests, and callers that want to see it)
+__global__ void __launch_bounds__(256) gumbel_fill_kernel(float* __restrict__ out, int M, int K, GumbelKey gk) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int tx = threadIdx.x & 31;
+    if (t >= M) return;
+    for (int q = 0; q * 128 < K; ++q) {
+        float g[4];
+        gumbel4(gk, t, tx, q, g);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int k = tx + 32 * (4 * q + w);
+            if (k < K) out[static_cast<size_t>(t) * K + k] = g[w];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------- mixing weights
 // lp2[t][kmap(k)] = log2( softmax_k(x[t].Wpi[k] + bpi[k] + g[t][k]) + 1e-15 )   — fp32 on CUDA cores: the
 // logits enter every feature's logsumexp with the same sign, so they need better than fp16-GEMM accuracy.
@@ -193,13 +244,15 @@ __global__ void __launch_bounds__(256) gmm_operand_kernel(const float* __restric
 // tx+32*j in registers, so a token's logits stay inside its warp and the softmax needs shuffles only.  TPW is chosen
 // by the host so that the tokens fill the 148 SMs in ONE balanced wave (M = 6272 -> TPW 11, 143 CTAs): with a fixed
 // 32-token CTA the 196 CTAs left 48 SMs with two CTAs and the rest with one (88 us; this form: see DESIGN.md 4.5).
-constexpr int kPiBK = 32, kPiMaxK = 160;
-// NJ = mixture slots per lane (K <= 32 NJ): 4 for K <= 128 (K = 100: 20 % fewer FMAs and weight loads than 5), 5 up to 160.
+constexpr int kPiBK = 32, kPiMaxK = 224;
+// NJ = mixture slots per lane (K <= 32 NJ): 4 for K <= 128 (K = 100: 20 % fewer FMAs and weight loads than 5), 5 / 6 / 7 up to
+// 160 / 192 / 224.  gumbel == nullptr: the noise is generated in place from `gk` (see above).
 template <int TPW, int WARPS, int NJ>
 __global__ void __launch_bounds__(32 * WARPS) gmm_logpi_kernel(const float* __restrict__ x, int ldx,
                                                                const float* __restrict__ wpi, const float* __restrict__ bpi,
-                                                               const float* __restrict__ gumbel, float* __restrict__ lp2,
-                                                               int M, int D, int K, int n_kc, int KC, int KCV) {
+                                                               const float* __restrict__ gumbel, GumbelKey gk,
+                                                               float* __restrict__ lp2, int M, int D, int K, int n_kc, int KC,
+                                                               int KCV) {
     griddep_launch_dependents();
     griddep_wait();
     constexpr int BM = WARPS * TPW;
@@ -272,10 +325,21 @@ __global__ void __launch_bounds__(32 * WARPS) gmm_logpi_kernel(const float* __re
         if (t >= M) break;  // warp-uniform
         float z[NJ];
         float mx = -INFINITY;
+        float gn[(NJ + 3) / 4 * 4];
+        if (gumbel == nullptr) {  // warp-uniform
+#pragma unroll
+            for (int q = 0; q < (NJ + 3) / 4; ++q) {
+                float g4[4];
+                gumbel4(gk, t, tx, q, g4);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) gn[4 * q + w] = g4[w];
+            }
+        }
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const int k = tx + 32 * j;
-            z[j] = (k < K) ? acc[i][j] + bpi[k] + gumbel[static_cast<size_t>(t) * K + k] : -INFINITY;
+            const float g = gumbel != nullptr ? (k < K ? gumbel[static_cast<size_t>(t) * K + k] : 0.f) : gn[j];
+            z[j] = (k < K) ? acc[i][j] + bpi[k] + g : -INFINITY;
             mx = fmaxf(mx, z[j]);
         }
 #pragma unroll
@@ -307,13 +371,17 @@ __global__ void __launch_bounds__(32 * WARPS) gmm_logpi_kernel(const float* __re
 
 template <int TPW, int WARPS>
 static cudaError_t launch_logpi(cudaStream_t s, const float* x, int ldx, const float* pi_w, const float* pi_b,
-                                const float* gumbel, float* lp2, int tokens, int dim, int K, int n_kc, int kc, int kcv) {
+                                const float* gumbel, GumbelKey gk, float* lp2, int tokens, int dim, int K, int n_kc, int kc,
+                                int kcv) {
     const dim3 grid((tokens + WARPS * TPW - 1) / (WARPS * TPW)), block(32 * WARPS);
-    if (K <= 128)
-        return launch_pdl(gmm_logpi_kernel<TPW, WARPS, 4>, grid, block, 0, s, x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, K, n_kc,
-                          kc, kcv);
-    return launch_pdl(gmm_logpi_kernel<TPW, WARPS, 5>, grid, block, 0, s, x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, K, n_kc, kc,
-                      kcv);
+#define VITAD_LOGPI_NJ(NJ)                                                                                                    \
+    return launch_pdl(gmm_logpi_kernel<TPW, WARPS, NJ>, grid, block, 0, s, x, ldx, pi_w, pi_b, gumbel, gk, lp2, tokens, dim, K, \
+                      n_kc, kc, kcv)
+    if (K <= 128) VITAD_LOGPI_NJ(4);
+    if (K <= 160) VITAD_LOGPI_NJ(5);
+    if (K <= 192) VITAD_LOGPI_NJ(6);
+    VITAD_LOGPI_NJ(7);
+#undef VITAD_LOGPI_NJ
 }
 
 // ---------------------------------------------------------- mixing weights on the tensor cores
@@ -588,14 +656,17 @@ extern "C" void vitad_set_gmm_split(int features) { vitad::g_gmm_split.store(fea
 
 extern "C" int vitad_gmm_plan(int num_gaussians, int* n_kc, int* kc, int* kcv) {
     VITAD_REQUIRE(n_kc && kc && kcv, VITAD_ERR_ARG, "null pointer");
-    VITAD_REQUIRE(num_gaussians >= 1 && num_gaussians <= 144, VITAD_ERR_SHAPE,
-                  "num_gaussians=%d unsupported (1..144)", num_gaussians);
+    VITAD_REQUIRE(num_gaussians >= 1 && num_gaussians <= 208, VITAD_ERR_SHAPE,
+                  "num_gaussians=%d unsupported (1..208)", num_gaussians);
     if (num_gaussians <= 104) {  // K = 100: 104 slots (4% padding); the tile is 256 tokens x (104 sigma | 104 mu)
         *n_kc = 1, *kc = 104, *kcv = num_gaussians;
     } else if (num_gaussians <= 112) {
         *n_kc = 1, *kc = 112, *kcv = num_gaussians;
     } else {
-        *n_kc = 2, *kc = 72, *kcv = (num_gaussians + 1) / 2;
+        // two chunks of ceil(K/2) mixtures: 72 slots up to K = 144 (K = 130: 65 valid each), 80 up to 160 (the reference's
+        // default K = 150, startTraining_mdn.py:37: 75 valid), 88 up to 176 (K = 170 of csv_results_gmm), 104 up to 208
+        *n_kc = 2, *kcv = (num_gaussians + 1) / 2;
+        *kc = num_gaussians <= 144 ? 72 : num_gaussians <= 160 ? 80 : num_gaussians <= 176 ? 88 : 104;
     }
     return VITAD_OK;
 }
@@ -608,6 +679,7 @@ extern "C" size_t vitad_gmm_packed_weight_bytes(int dim, int num_gaussians) {
 
 extern "C" int vitad_gmm_pack_weights(const float* sigma_w, const float* sigma_b, const float* mu_w, const float* mu_b,
                                       int dim, int num_gaussians, void* packed, void* stream) {
+    VITAD_NVTX("vitad_gmm_pack_weights");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(sigma_w && sigma_b && mu_w && mu_b && packed, VITAD_ERR_ARG, "null pointer");
@@ -637,12 +709,13 @@ extern "C" int vitad_gmm_make_operand(const float* x, int ldx, void* xaug, int t
     return VITAD_OK;
 }
 
-extern "C" int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, const float* pi_b, const float* gumbel,
-                                float* lp2, int tokens, int dim, int num_gaussians, void* stream) {
+static int gmm_log_pi_impl(const float* x, int ldx, const float* pi_w, const float* pi_b, const float* gumbel, GumbelKey gk,
+                           float* lp2, int tokens, int dim, int num_gaussians, void* stream) {
+    VITAD_NVTX("vitad_gmm_log_pi");
     int rc = check_device_arch();
     if (rc) return rc;
-    VITAD_REQUIRE(x && pi_w && pi_b && gumbel && lp2, VITAD_ERR_ARG, "null pointer");
-    VITAD_REQUIRE(dim % kPiBK == 0 && tokens > 0 && num_gaussians <= kPiMaxK, VITAD_ERR_SHAPE, "dim %% 32 != 0, no tokens or K > 160");
+    VITAD_REQUIRE(x && pi_w && pi_b && lp2, VITAD_ERR_ARG, "null pointer");
+    VITAD_REQUIRE(dim % kPiBK == 0 && tokens > 0 && num_gaussians <= kPiMaxK, VITAD_ERR_SHAPE, "dim %% 32 != 0, no tokens or K > 224");
     VITAD_REQUIRE(ldx % 4 == 0 && aligned16(x) && aligned16(pi_w), VITAD_ERR_ALIGN,
                   "log_pi: x / pi_w must be 16-byte aligned with ldx %% 4 == 0");
     int n_kc, kc, kcv;
@@ -654,7 +727,7 @@ extern "C" int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, cons
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int sms = device_sm_count();
     cudaError_t e;
-#define VITAD_LOGPI(T, W) e = launch_logpi<T, W>(s, x, ldx, pi_w, pi_b, gumbel, lp2, tokens, dim, num_gaussians, n_kc, kc, kcv)
+#define VITAD_LOGPI(T, W) e = launch_logpi<T, W>(s, x, ldx, pi_w, pi_b, gumbel, gk, lp2, tokens, dim, num_gaussians, n_kc, kc, kcv)
     if (tokens <= 8 * sms) {
         const int per_warp = (tokens + 4 * sms - 1) / (4 * sms);
         if (per_warp <= 1) VITAD_LOGPI(1, 4);
@@ -669,6 +742,33 @@ extern "C" int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, cons
     }
 #undef VITAD_LOGPI
     VITAD_CUDA_OK(e);
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
+
+extern "C" int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, const float* pi_b, const float* gumbel,
+                                float* lp2, int tokens, int dim, int num_gaussians, void* stream) {
+    VITAD_REQUIRE(gumbel, VITAD_ERR_ARG, "null gumbel (use vitad_gmm_log_pi_seeded for in-kernel noise)");
+    return gmm_log_pi_impl(x, ldx, pi_w, pi_b, gumbel, GumbelKey{0u, 0u, 0u}, lp2, tokens, dim, num_gaussians, stream);
+}
+
+// Same, with the Gumbel noise generated in the kernel from (seed, batch_index, token, mixture): see gumbel4().
+extern "C" int vitad_gmm_log_pi_seeded(const float* x, int ldx, const float* pi_w, const float* pi_b, uint64_t seed,
+                                       uint32_t batch_index, float* lp2, int tokens, int dim, int num_gaussians,
+                                       void* stream) {
+    const GumbelKey gk{static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), batch_index};
+    return gmm_log_pi_impl(x, ldx, pi_w, pi_b, nullptr, gk, lp2, tokens, dim, num_gaussians, stream);
+}
+
+// out fp32 [tokens, K]: the noise vitad_gmm_log_pi_seeded adds for (seed, batch_index).
+extern "C" int vitad_gumbel_noise(uint64_t seed, uint32_t batch_index, float* out, int tokens, int num_gaussians,
+                                  void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(out && tokens > 0 && num_gaussians > 0 && num_gaussians <= kPiMaxK, VITAD_ERR_ARG, "gumbel_noise args");
+    const GumbelKey gk{static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), batch_index};
+    gumbel_fill_kernel<<<(tokens + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, tokens, num_gaussians, gk);
     VITAD_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1);
     return VITAD_OK;
@@ -702,10 +802,11 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream);
 extern "C" int vitad_gmm_log_pi_tc(const float* x, int ldx, const void* pi_packed, const float* pi_b, const float* gumbel,
                                    float* lp2, int tokens, int dim, int num_gaussians, void* workspace,
                                    size_t workspace_bytes, void* stream) {
+    VITAD_NVTX("vitad_gmm_log_pi_tc");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(x && pi_packed && pi_b && gumbel && lp2 && workspace, VITAD_ERR_ARG, "null pointer");
-    VITAD_REQUIRE(dim % 16 == 0 && tokens > 0 && num_gaussians <= kPiMaxK, VITAD_ERR_SHAPE, "dim %% 16 != 0, no tokens or K > 160");
+    VITAD_REQUIRE(dim % 16 == 0 && tokens > 0 && num_gaussians <= 160, VITAD_ERR_SHAPE, "dim %% 16 != 0, no tokens or K > 160");
     VITAD_REQUIRE(ldx % 4 == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, VITAD_ERR_ALIGN,
                   "log_pi_tc: x 16-byte aligned with ldx %% 4 == 0, workspace 256-byte aligned");
     VITAD_REQUIRE(workspace_bytes >= vitad_gmm_log_pi_workspace_bytes(tokens, dim, num_gaussians), VITAD_ERR_WORKSPACE,
@@ -739,6 +840,7 @@ extern "C" int vitad_gmm_log_pi_tc(const float* x, int ldx, const void* pi_packe
 extern "C" int vitad_gmm_patch_loglik(const void* xaug, const void* packed, const float* lp2, const float* x, int ldx,
                                       float* ll_ws, int ld_ws, float* L, int tokens, int dim, int num_gaussians,
                                       void* stream) {
+    VITAD_NVTX("vitad_gmm_patch_loglik");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(xaug && packed && lp2 && x && ll_ws && L, VITAD_ERR_ARG, "null pointer");
@@ -755,8 +857,14 @@ extern "C" int vitad_gmm_patch_loglik(const void* xaug, const void* packed, cons
             rc = launch_mdn<104, 1>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
         else if (n_kc == 1)
             rc = launch_mdn<112, 1>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
-        else
+        else if (kc == 72)
             rc = launch_mdn<72, 2>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
+        else if (kc == 80)
+            rc = launch_mdn<80, 2>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
+        else if (kc == 88)
+            rc = launch_mdn<88, 2>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
+        else
+            rc = launch_mdn<104, 2>(xaug, packed, lp2, x, ldx, ll_ws, ld_ws, tokens, dim, s);
     }
     if (rc) return rc;
     ProfScope prof2("gmm_mean", s);
@@ -768,6 +876,7 @@ extern "C" int vitad_gmm_patch_loglik(const void* xaug, const void* packed, cons
 
 // L fp32 [batch*patches] -> prob fp32 [batch*patches] (exp(L - max over the whole batch)), scores fp32 [batch].
 extern "C" int vitad_gmm_finish(const float* L, float* prob, float* scores, int batch, int patches, void* stream) {
+    VITAD_NVTX("vitad_gmm_finish");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(L && prob && scores && batch > 0 && patches > 0, VITAD_ERR_ARG, "gmm_finish args");

@@ -330,6 +330,7 @@ extern "C" size_t vitad_nf_workspace_bytes(const vitad_nf_weights* w, int batch)
 
 extern "C" int vitad_nf_forward(const vitad_nf_weights* wp, const float* tokens, int batch, void* workspace,
                                 size_t workspace_bytes, float* one_minus_prob, float* loss_terms, void* stream) {
+    VITAD_NVTX("vitad_nf_forward");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(wp && tokens && workspace && one_minus_prob && loss_terms, VITAD_ERR_ARG, "null pointer");

@@ -122,6 +122,7 @@ extern "C" int vitad_resize_plan(int in_size, int out_size, int32_t* plan) {
 extern "C" int vitad_resize_bilinear_u8(const uint8_t* in, int batch, int height, int width, int out_size,
                                         const int32_t* plan_h, const int32_t* plan_v, uint8_t* tmp, uint8_t* out,
                                         void* stream) {
+    VITAD_NVTX("vitad_resize_bilinear_u8");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(in && out && tmp && plan_h && plan_v, VITAD_ERR_ARG, "null pointer");

@@ -93,6 +93,7 @@ using namespace vitad;
 
 extern "C" int vitad_bilinear_up(const float* in, float* out, float* image_max, int n, int grid_in, int size_out,
                                  int align_corners, int pre_one_minus, int post_one_minus, void* stream) {
+    VITAD_NVTX("vitad_bilinear_up");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(in && out && n > 0 && grid_in > 0, VITAD_ERR_ARG, "bilinear args");
@@ -110,6 +111,7 @@ extern "C" int vitad_bilinear_up(const float* in, float* out, float* image_max, 
 
 extern "C" int vitad_l2_map_score(const float* recon, const float* x, float* map, float* image_max, int n, int channels,
                                   int hw, void* stream) {
+    VITAD_NVTX("vitad_l2_map_score");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(recon && x && map && image_max && n > 0 && channels > 0, VITAD_ERR_ARG, "l2 map args");

@@ -171,6 +171,7 @@ extern "C" size_t vitad_swin_workspace_bytes(const vitad_swin_weights* w, int ba
 extern "C" int vitad_swin_forward(const vitad_swin_weights* wp, const float* images, int batch, void* workspace,
                                   size_t workspace_bytes, float* out_tokens, float* out_latent, void* out_xaug,
                                   int ld_xaug, void* stream) {
+    VITAD_NVTX("vitad_swin_forward");
     int rc = check_device_arch();
     if (rc) return rc;
     VITAD_REQUIRE(wp && images && workspace && out_tokens && wp->stage, VITAD_ERR_ARG, "null pointer");

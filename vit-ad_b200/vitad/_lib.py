@@ -187,6 +187,10 @@ lib.vitad_gmm_make_operand.argtypes = [_vp, _i, _vp, _i, _i, _vp]
 lib.vitad_gmm_make_operand.restype = _i
 lib.vitad_gmm_log_pi.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]
 lib.vitad_gmm_log_pi.restype = _i
+lib.vitad_gmm_log_pi_seeded.argtypes = [_vp, _i, _vp, _vp, C.c_uint64, C.c_uint32, _vp, _i, _i, _i, _vp]
+lib.vitad_gmm_log_pi_seeded.restype = _i
+lib.vitad_gumbel_noise.argtypes = [C.c_uint64, C.c_uint32, _vp, _i, _i, _vp]
+lib.vitad_gumbel_noise.restype = _i
 lib.vitad_gmm_pi_packed_bytes.argtypes = [_i, _i]
 lib.vitad_gmm_pi_packed_bytes.restype = _sz
 lib.vitad_gmm_pack_pi.argtypes = [_vp, _i, _i, _vp, _vp]

@@ -18,7 +18,7 @@ from torch import Tensor, nn
 
 import ctypes as C
 
-from . import _lib, ops
+from . import _lib, custom_ops, ops
 from ._lib import check, lib
 from .encoders import EncoderDeit
 
@@ -62,6 +62,8 @@ class DecoderVanillaCNN(nn.Module):
             layers += [conv, nn.BatchNorm2d(chans[i + 1]), nn.Tanh() if i == 4 else nn.ReLU(inplace=True)]
         self.decoder_cnn = nn.Sequential(*layers)
         self.decoder_cnn.apply(_init)
+        self.out_size = 32 * first_feature_map_size  # five stride-2 transposed convolutions
+        self._handle = custom_ops.register_module(self)
 
     # -- CUDA path ---------------------------------------------------------------------------------
     _packed = None
@@ -130,8 +132,16 @@ class DecoderVanillaCNN(nn.Module):
             raise RuntimeError("DecoderVanillaCNN (vitad): CUDA input required — this implementation has no CPU path")
         if not self.use_linear:
             raise NotImplementedError("vitad DecoderVanillaCNN: only the latent (z_space) form used by AutoEncoderDeit is provided")
-        if self._packed is None or self._packed["device"] != x.device:
+        return torch.ops.vitad.decoder_forward(x, self._handle)
+
+    def _run(self, x):
+        """CUDA implementation of torch.ops.vitad.decoder_forward for this decoder's weights."""
+        from .encoders import _param_key
+
+        key = _param_key(self, x.device)
+        if self._packed is None or self._packed.get("key") != key:
             self._pack(x.device)
+            self._packed["key"] = key
         pk = self._packed
         x = x.to(torch.float32).contiguous()
         B = x.shape[0]
@@ -259,6 +269,8 @@ class DecoderResNetVariableEmbeddingSize(nn.Module):
         hidden = 2 * embedding_size
         self.fc1 = nn.Sequential(nn.Linear(embedding_size, hidden), nn.ReLU(inplace=True))
         self.fc2 = nn.Sequential(nn.Linear(hidden, 2048), nn.ReLU(inplace=True))
+        self.out_size = 224
+        self._handle = custom_ops.register_module(self)
 
     @staticmethod
     def _make_layer(planes, blocks, stride=1, output_padding=1, last_block_dim=0):
@@ -313,8 +325,16 @@ class DecoderResNetVariableEmbeddingSize(nn.Module):
         """latent [B, embedding_size] → reconstruction fp32 [B, 3, 224, 224] (tanh range)."""
         if not x.is_cuda:
             raise RuntimeError("DecoderResNetVariableEmbeddingSize (vitad): CUDA input required — this implementation has no CPU path")
-        if self._packed is None or self._packed["device"] != x.device:
+        return torch.ops.vitad.decoder_forward(x, self._handle)
+
+    def _run(self, x):
+        """CUDA implementation of torch.ops.vitad.decoder_forward for this decoder's weights."""
+        from .encoders import _param_key
+
+        key = _param_key(self, x.device)
+        if self._packed is None or self._packed.get("key") != key:
             self._pack(x.device)
+            self._packed["key"] = key
         pk = self._packed
         x = x.to(torch.float32).contiguous()
         B = x.shape[0]

@@ -12,8 +12,20 @@ from dataclasses import dataclass
 import torch
 from torch import nn
 
-from . import _lib
+from . import _lib, custom_ops
 from ._lib import check, lib
+
+
+def _param_key(module: nn.Module, device) -> tuple:
+    """Identity of the parameter values a packed fp16 copy was made from: device + the sum of the tensors' in-place
+    version counters (optimizer.step(), copy_(), init functions bump them; load_state_dict and .to() reset the cache
+    explicitly).  Writes through `.data` bypass the counter — call `module._packed = None` after such an edit."""
+    v = 0
+    for t in module.parameters():
+        v += t._version
+    for t in module.buffers():
+        v += t._version
+    return (device, v)
 
 
 @dataclass
@@ -117,6 +129,7 @@ class _TimmVitEncoder(TransformerEncoder):
         for p in self._params().parameters():
             p.requires_grad = False
         self._packed = None  # device-side fp16 copies + C structs, rebuilt when parameters change
+        self._handle = custom_ops.register_module(self)
 
     def _params(self) -> _DeitParams:
         return getattr(self, self._ATTR)
@@ -182,8 +195,17 @@ class _TimmVitEncoder(TransformerEncoder):
         block_index = self._block_index(int(block_index))
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.img_size or x.shape[3] != self.img_size:
             raise ValueError(f"expected [B,3,{self.img_size},{self.img_size}] input, got {tuple(x.shape)}")
-        if self._packed is None or self._packed["device"] != x.device:
+        tokens, cls, xaug = torch.ops.vitad.deit_forward(x, self._handle, int(block_index))
+        # fp16 GEMM operand for the MDN head (saves one conversion pass); valid while `tokens` is not modified in place
+        tokens._vitad_xaug = (xaug, tokens._version)
+        return TransformerEncoderOutput(patch_embedding=tokens, latent_space=cls)
+
+    def _run(self, x: torch.Tensor, block_index: int):
+        """CUDA implementation of torch.ops.vitad.deit_forward for this module's weights."""
+        key = _param_key(self, x.device)
+        if self._packed is None or self._packed.get("key") != key:
             self._pack(x.device)
+            self._packed["key"] = key
         pk = self._packed
         # uint8 images (the dataset's native pixels) are taken as they are: the /255 of ToTensor happens in the patch
         # gather; anything else is the reference's fp32 [0,1] tensor
@@ -198,8 +220,7 @@ class _TimmVitEncoder(TransformerEncoder):
         fwd = lib.vitad_deit_forward_u8 if u8 else lib.vitad_deit_forward
         check(fwd(C.byref(pk["w"]), x.data_ptr(), B, int(block_index), ws.data_ptr(), ws.numel(), tokens.data_ptr(),
                   cls.data_ptr(), xaug.data_ptr(), _lib.MDN_KA, torch.cuda.current_stream().cuda_stream))
-        tokens._vitad_xaug = xaug  # fp16 GEMM operand for the MDN head (saves one conversion pass)
-        return TransformerEncoderOutput(patch_embedding=tokens, latent_space=cls)
+        return tokens, cls, xaug
 
 
     def _block_index(self, block_index: int) -> int:
@@ -403,6 +424,7 @@ class EncoderEsVit(TransformerEncoder):
         for p in self.esvit.parameters():
             p.requires_grad = False
         self._packed = None
+        self._handle = custom_ops.register_module(self)
 
     def _apply(self, fn, recurse=True):
         self._packed = None
@@ -483,8 +505,16 @@ class EncoderEsVit(TransformerEncoder):
             raise RuntimeError("EncoderEsVit (vitad): CUDA input required — this implementation has no CPU path")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.img_size or x.shape[3] != self.img_size:
             raise ValueError(f"expected [B,3,{self.img_size},{self.img_size}] input, got {tuple(x.shape)}")
-        if self._packed is None or self._packed["device"] != x.device:
+        tokens, latent, xaug = torch.ops.vitad.swin_forward(x, self._handle)
+        tokens._vitad_xaug = (xaug, tokens._version)
+        return TransformerEncoderOutput(latent_space=latent, patch_embedding=tokens)
+
+    def _run(self, x: torch.Tensor):
+        """CUDA implementation of torch.ops.vitad.swin_forward for this module's weights."""
+        key = _param_key(self, x.device)
+        if self._packed is None or self._packed.get("key") != key:
             self._pack(x.device)
+            self._packed["key"] = key
         pk = self._packed
         if x.dtype == torch.uint8:  # native pixels: the /255 of ToTensor (GeneralDataset.py:46-53)
             x = x.to(torch.float32).div_(255.0)
@@ -500,5 +530,4 @@ class EncoderEsVit(TransformerEncoder):
         check(lib.vitad_swin_forward(C.byref(pk["w"]), x.data_ptr(), B, pk["ws"].data_ptr(), pk["ws"].numel(),
                                      tokens.data_ptr(), latent.data_ptr(), xaug.data_ptr(), _lib.MDN_KA,
                                      torch.cuda.current_stream().cuda_stream))
-        tokens._vitad_xaug = xaug
-        return TransformerEncoderOutput(latent_space=latent, patch_embedding=tokens)
+        return tokens, latent, xaug

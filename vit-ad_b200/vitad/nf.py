@@ -15,7 +15,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import _lib, ops
+from . import _lib, custom_ops, ops
 from ._lib import check, lib
 
 HIDDEN_PAD = 64
@@ -80,6 +80,7 @@ class NormalizingFlow(nn.Module):
         for i in range(flow_steps):
             self.fast_flow_decoder.module_list.append(_Step(num_channels, self.hidden, 1 if i % 2 == 1 else 3))
         self._packed = None
+        self._handle = custom_ops.register_module(self)
 
     def _apply(self, fn, recurse=True):
         self._packed = None
@@ -145,12 +146,25 @@ class NormalizingFlow(nn.Module):
         """tokens: fp32 [B, P, C] patch embedding (the layout the encoder produces)."""
         if not tokens.is_cuda:
             raise RuntimeError("NormalizingFlow (vitad): CUDA input required — no CPU path")
-        if self._packed is None or self._packed["device"] != tokens.device:
-            self._pack(tokens.device)
-        pk = self._packed
         B, P, Cn = tokens.shape
         if P != self.grid * self.grid or Cn != self.num_channels:
             raise ValueError(f"expected [B,{self.grid * self.grid},{self.num_channels}] tokens, got {tuple(tokens.shape)}")
+        omp, loss_terms = torch.ops.vitad.nf_forward(tokens, self._handle)
+        amap, amax = ops.bilinear_up(omp, self.img_size, align_corners=False, want_max=True)
+        out = NormalizingFlowReturn(loss=loss_terms.mean(), anomaly_score_map=amap)
+        out.image_max = amax  # amax(anomaly_score_map, (1,2,3)) computed by the upsample kernel (ValidatorNF.py:137-142)
+        return out
+
+    def _run(self, tokens: torch.Tensor):
+        """CUDA implementation of torch.ops.vitad.nf_forward for this module's weights."""
+        from .encoders import _param_key
+
+        key = _param_key(self, tokens.device)
+        if self._packed is None or self._packed.get("key") != key:
+            self._pack(tokens.device)
+            self._packed["key"] = key
+        pk = self._packed
+        B = tokens.shape[0]
         tokens = tokens.to(torch.float32).contiguous()
         if pk["ws"] is None or pk["ws_batch"] < B:
             nbytes = lib.vitad_nf_workspace_bytes(C.byref(pk["w"]), B)
@@ -159,10 +173,7 @@ class NormalizingFlow(nn.Module):
         loss_terms = torch.empty((B,), device=tokens.device, dtype=torch.float32)
         check(lib.vitad_nf_forward(C.byref(pk["w"]), tokens.data_ptr(), B, pk["ws"].data_ptr(), pk["ws"].numel(),
                                    omp.data_ptr(), loss_terms.data_ptr(), torch.cuda.current_stream().cuda_stream))
-        amap, amax = ops.bilinear_up(omp, self.img_size, align_corners=False, want_max=True)
-        out = NormalizingFlowReturn(loss=loss_terms.mean(), anomaly_score_map=amap)
-        out.image_max = amax  # amax(anomaly_score_map, (1,2,3)) computed by the upsample kernel (ValidatorNF.py:137-142)
-        return out
+        return omp, loss_terms
 
     def forward(self, x: torch.Tensor) -> NormalizingFlowReturn:
         """x: [B, C, h, w] as in the reference (NormalizingFlow.py:118-123)."""

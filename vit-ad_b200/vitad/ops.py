@@ -6,6 +6,7 @@ import ctypes as C
 import torch
 
 from . import _lib
+from . import custom_ops  # noqa: F401  (registers torch.ops.vitad.*)
 from ._lib import check, lib
 
 
@@ -97,8 +98,12 @@ _resize_plans: dict = {}
 def resize_u8(images_hwc: torch.Tensor, size: int) -> torch.Tensor:
     """transforms.Resize((size, size)) of the reference's loader (GeneralDataset.py:38-59) on the device, bit-identical
     to Pillow: uint8 [B, H, W, 3] (decoded images, HWC) → uint8 [B, 3, size, size] (planar; feed it to the encoders'
-    uint8 path, which folds ToTensor's /255 into the patch gather)."""
+    uint8 path, which folds ToTensor's /255 into the patch gather).  = torch.ops.vitad.resize_u8."""
     _need_cuda(images_hwc)
+    return torch.ops.vitad.resize_u8(images_hwc, size)
+
+
+def _resize_u8(images_hwc: torch.Tensor, size: int) -> torch.Tensor:
     assert images_hwc.dtype == torch.uint8 and images_hwc.dim() == 4 and images_hwc.shape[3] == 3
     images_hwc = images_hwc.contiguous()
     b, h, w, _ = images_hwc.shape
@@ -198,19 +203,30 @@ def attention(q, k, vt, tokens, windows=1, bias=None, region=None, win2tok=None)
 
 # ------------------------------------------------------------------------------------- score maps
 def bilinear_up(x, size, align_corners, pre_one_minus=False, post_one_minus=False, want_max=False):
-    """x fp32 [N,g,g] -> ([N,1,size,size], per-image max or None)."""
+    """x fp32 [N,g,g] -> ([N,1,size,size], per-image max or None).  = torch.ops.vitad.bilinear_up."""
     _need_cuda(x)
+    out, mx = torch.ops.vitad.bilinear_up(x, int(size), bool(align_corners), bool(pre_one_minus), bool(post_one_minus),
+                                          bool(want_max))
+    return out, (mx if want_max else None)
+
+
+def _bilinear_up(x, size, align_corners, pre_one_minus, post_one_minus, want_max):
+    x = x.to(torch.float32).contiguous()
     n, g, _ = x.shape
     out = torch.empty((n, 1, size, size), device=x.device, dtype=torch.float32)
     mx = torch.empty((n,), device=x.device, dtype=torch.float32) if want_max else None
     check(lib.vitad_bilinear_up(x.data_ptr(), out.data_ptr(), _ptr(mx), n, g, size, int(align_corners),
                                 int(pre_one_minus), int(post_one_minus), _stream()))
-    return out, mx
+    return out, (mx if mx is not None else torch.empty((0,), device=x.device, dtype=torch.float32))
 
 
 def l2_map_score(recon, x):
-    """mean_c (recon - x)^2 -> ([N,1,H,W] map, [N] per-image max)."""
+    """mean_c (recon - x)^2 -> ([N,1,H,W] map, [N] per-image max).  = torch.ops.vitad.l2_map_score."""
     _need_cuda(recon, x)
+    return torch.ops.vitad.l2_map_score(recon, x)
+
+
+def _l2_map_score(recon, x):
     n, c, h, w = x.shape
     recon, x = recon.contiguous(), x.contiguous()
     amap = torch.empty((n, 1, h, w), device=x.device, dtype=torch.float32)

@@ -1,7 +1,10 @@
 """Multi-GPU plumbing of the scoring path: one process per GPU (torchrun), a weight replica per rank,
 whole batches dealt round-robin (validators.py), and ONE exchange step — gathering per-image scores, maps
 and labels on every rank for AUROC / PR-AUC.  The reference is single-process; this is new.
-Works with the nccl backend on GPUs and with gloo on CPU (used by the world_size-2 tests).
+Works with the nccl backend on GPUs and with gloo on CPU (used by the world_size-2/3 tests).
+
+Every rank takes part in the same sequence of collectives whatever it holds: a rank that scored nothing (fewer
+batches than ranks — a small category on 8 GPUs) contributes empty payloads instead of raising while its peers wait.
 """
 from __future__ import annotations
 
@@ -10,6 +13,9 @@ import os
 import numpy as np
 import torch
 import torch.distributed as dist
+
+PAYLOAD = (("image_scores", torch.float32), ("pixel_scores", torch.float32), ("image_labels", torch.int64),
+           ("pixel_labels", None))  # pixel_labels keeps the dtype the ranks hold (fp32 from the loader, uint8 on-device rows)
 
 
 def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
@@ -30,49 +36,123 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     return rank, world, local
 
 
-def gather_results(result: dict, num_batches: int, device: torch.device | None = None) -> dict:
-    """All-gather the per-rank validator dicts (keys image_scores, pixel_scores, image_labels, pixel_labels,
-    batch_index [, origs]) and restore the original batch order.  Ranks may hold different numbers of images
-    (short tail batches): payloads are padded to the per-rank maximum for equal-count all_gather_into_tensor.
-    """
+def warm_up(device: torch.device | None = None) -> None:
+    """One tiny all_gather so that communicator set-up (NCCL: hundreds of ms) does not land in a timed gather."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return result
+        return
+    device = _default_device() if device is None else device
+    t = torch.zeros(8, device=device)
+    out = torch.empty(8 * dist.get_world_size(), device=device)
+    dist.all_gather_into_tensor(out, t)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+
+
+def _default_device() -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def _as_tensor(a, device, dtype=None) -> torch.Tensor:
+    t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(device=device, dtype=dtype if dtype is not None else t.dtype, non_blocking=True)
+
+
+class PendingGather:
+    """Handle of a gather in flight (gather_results(..., async_op=True)): .result() waits for the collectives on the
+    calling stream and stitches the global batch order back."""
+
+    def __init__(self, finish):
+        self._finish = finish
+
+    def result(self) -> dict:
+        return self._finish()
+
+
+def gather_results(result: dict, num_batches: int, device: torch.device | None = None, async_op: bool = False,
+                   as_numpy: bool | None = None):
+    """All-gather the per-rank validator dicts (keys image_scores, pixel_scores, image_labels, pixel_labels,
+    batch_index, batch_sizes) and restore the original batch order.  Ranks may hold different numbers of images
+    (short tail batches) or none at all: payloads are padded to the per-rank maximum for equal-count
+    all_gather_into_tensor.
+
+    Values may be numpy arrays (valid_loop_*) or torch tensors on `device` (valid_loop_*(on_device=True)); tensors that
+    already live on the device are gathered in place — no host round trip.  Returns numpy arrays when the input held
+    numpy arrays, device tensors otherwise (`as_numpy` overrides).  async_op=True returns a PendingGather after
+    enqueueing the payload collectives, so the caller can score the next category while NVLink moves this one."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return PendingGather(lambda: result) if async_op else result
     world = dist.get_world_size()
     if device is None:
-        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    counts_local = np.asarray(result.get("batch_sizes", []), dtype=np.int64)
-    if counts_local.size == 0:  # derive from batch_index: caller did not record sizes -> equal split unknown
-        raise ValueError("gather_results needs result['batch_sizes'] (images per scored batch)")
-    n_local = int(counts_local.sum())
-    meta = torch.tensor([n_local, len(counts_local)], device=device, dtype=torch.int64)
-    metas = torch.empty(world * 2, device=device, dtype=torch.int64)
+        device = _default_device()
+    if as_numpy is None:
+        as_numpy = not any(torch.is_tensor(result.get(k)) for k, _ in PAYLOAD)
+    if "batch_sizes" not in result or "batch_index" not in result:
+        raise ValueError("gather_results needs result['batch_index'] and result['batch_sizes'] (images per scored batch)")
+    counts_local = np.asarray(result["batch_sizes"], dtype=np.int64).reshape(-1)
+    bidx_local = np.asarray(result["batch_index"], dtype=np.int64).reshape(-1)
+    n_local, b_local = int(counts_local.sum()), int(counts_local.size)
+
+    # -- metadata: image / batch counts, trailing map shape and label dtype of every rank (empty ranks send zeros)
+    ps = result.get("pixel_scores")
+    map_shape = tuple(int(v) for v in ps.shape[1:]) if ps is not None and n_local > 0 else (0, 0, 0)
+    if len(map_shape) != 3:
+        raise ValueError(f"pixel_scores must be [n, 1, S, S], got trailing shape {map_shape}")
+    pl = result.get("pixel_labels")
+    pl_is_u8 = int(n_local > 0 and pl is not None and (pl.dtype in (torch.uint8, np.uint8, torch.bool, np.bool_)))
+    meta = torch.tensor([n_local, b_local, *map_shape, pl_is_u8], dtype=torch.int64).to(device)
+    metas = torch.empty(world * meta.numel(), device=device, dtype=torch.int64)
     dist.all_gather_into_tensor(metas, meta)
-    metas = metas.view(world, 2).cpu().numpy()
+    metas = metas.view(world, -1).cpu().numpy()
     n_max, b_max = int(metas[:, 0].max()), int(metas[:, 1].max())
+    if n_max == 0:
+        raise ValueError("gather_results: no rank holds any result")
+    holder = int(np.argmax(metas[:, 0] > 0))
+    map_shape = tuple(int(v) for v in metas[holder, 2:5])
+    pl_dtype = torch.uint8 if int(metas[holder, 5]) else torch.float32
+    trailing = {"image_scores": (), "pixel_scores": map_shape, "image_labels": (), "pixel_labels": map_shape}
 
-    def gather(arr: np.ndarray, pad_to: int, dtype: torch.dtype) -> list[np.ndarray]:
-        t = torch.zeros((pad_to,) + arr.shape[1:], device=device, dtype=dtype)
-        t[: arr.shape[0]] = torch.as_tensor(arr, dtype=dtype).to(device)
-        out = torch.empty((world * pad_to,) + arr.shape[1:], device=device, dtype=dtype)
-        dist.all_gather_into_tensor(out, t.contiguous())
-        return list(out.view((world, pad_to) + arr.shape[1:]).cpu().numpy())
+    # -- payloads: padded to n_max rows, gathered on the device
+    works, gathered = [], {}
 
-    per_rank = {}
-    for key, dtype in (("image_scores", torch.float32), ("pixel_scores", torch.float32),
-                       ("image_labels", torch.int64), ("pixel_labels", torch.float32)):
-        per_rank[key] = gather(np.asarray(result[key]), n_max, dtype)
-    bidx = gather(np.asarray(result["batch_index"], dtype=np.int64), b_max, torch.int64)
-    bsz = gather(counts_local, b_max, torch.int64)
+    def gather(name, local, pad_to, dtype, trail):
+        t = torch.zeros((pad_to,) + trail, device=device, dtype=dtype)
+        if local is not None and pad_to > 0 and (local.shape[0] if hasattr(local, "shape") else len(local)) > 0:
+            src = _as_tensor(local, device, dtype)
+            t[: src.shape[0]] = src.reshape((src.shape[0],) + trail)
+        out = torch.empty((world * pad_to,) + trail, device=device, dtype=dtype)
+        w = dist.all_gather_into_tensor(out, t, async_op=True)
+        works.append(w)
+        gathered[name] = out.view((world, pad_to) + trail)
 
-    # stitch back in global batch order
-    pieces = {k: [None] * num_batches for k in per_rank}
-    for r in range(world):
-        off = 0
-        for j in range(int(metas[r, 1])):
-            b, n = int(bidx[r][j]), int(bsz[r][j])
-            for k in per_rank:
-                pieces[k][b] = per_rank[k][r][off : off + n]
-            off += n
-    merged = {k: np.concatenate([p for p in v if p is not None], axis=0) for k, v in pieces.items()}
-    merged["batch_index"] = np.arange(num_batches)
-    return merged
+    for key, dtype in PAYLOAD:
+        gather(key, result.get(key) if n_local > 0 else None, n_max, dtype if dtype is not None else pl_dtype, trailing[key])
+    gather("batch_index", bidx_local, b_max, torch.int64, ())
+    gather("batch_sizes", counts_local, b_max, torch.int64, ())
+
+    def finish():
+        for w in works:
+            w.wait()
+        bidx = gathered["batch_index"].cpu().numpy()
+        bsz = gathered["batch_sizes"].cpu().numpy()
+        # row of the flattened [world * n_max] gather buffers for every image, in global batch order
+        rows = [None] * num_batches
+        for r in range(world):
+            off = 0
+            for j in range(int(metas[r, 1])):
+                b, n = int(bidx[r, j]), int(bsz[r, j])
+                if not (0 <= b < num_batches) or rows[b] is not None:
+                    raise ValueError(f"gather_results: batch {b} reported twice or outside [0, {num_batches})")
+                rows[b] = np.arange(r * n_max + off, r * n_max + off + n, dtype=np.int64)
+                off += n
+        present = [b for b in range(num_batches) if rows[b] is not None]
+        order = torch.from_numpy(np.concatenate([rows[b] for b in present])).to(device)
+        merged = {}
+        for key, _ in PAYLOAD:
+            flat = gathered[key].reshape((world * n_max,) + trailing[key])
+            t = flat.index_select(0, order)
+            merged[key] = t.cpu().numpy() if as_numpy else t
+        merged["batch_index"] = np.asarray(present, dtype=np.int64)
+        merged["batch_sizes"] = np.asarray([len(rows[b]) for b in present], dtype=np.int64)
+        return merged
+
+    return PendingGather(finish) if async_op else finish()

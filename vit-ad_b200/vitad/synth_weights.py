@@ -152,8 +152,10 @@ def make_mdn_state_dict(seed: int, num_gaussians: int, dim: int = 768, stress: b
 
 
 def make_nf_state_dict(seed: int, channels: int = 768, grid: int = 14, hidden_ratio: float = 0.16,
-                       flow_steps: int = 20, stress: bool = False) -> dict:
-    """NormalizingFlow.__init__ (NormalizingFlow.py:28-116) with FrEIA AllInOneBlock defaults."""
+                       flow_steps: int = 20, stress: bool = False, subnet_gain: float = 4.0) -> dict:
+    """NormalizingFlow.__init__ (NormalizingFlow.py:28-116) with FrEIA AllInOneBlock defaults.  `stress`: random global
+    affine + the coupling subnets' output layer scaled by `subnet_gain` (the default init leaves the flow near identity;
+    4 drives the image scores towards saturation, ~2 keeps them mid-range where they separate images best)."""
     g = torch.Generator().manual_seed(seed)
     rng = np.random.RandomState(seed)
     c2 = channels // 2
@@ -179,7 +181,7 @@ def make_nf_state_dict(seed: int, channels: int = 768, grid: int = 14, hidden_ra
         sd[p + "subnet.2.weight"] = _kaiming_uniform(g, (2 * c2, hidden, k, k), hidden * k * k)
         sd[p + "subnet.2.bias"] = _kaiming_uniform(g, (2 * c2,), hidden * k * k)
         if stress:
-            sd[p + "subnet.2.weight"] *= 4.0
+            sd[p + "subnet.2.weight"] *= subnet_gain
     return sd
 
 

@@ -32,6 +32,38 @@ def make_category(name: str, n_images: int, seed: int, size: int = 224, anomaly_
     return images, labels, masks
 
 
+def make_diverse_image(seed: int, size: int = 224):
+    """One image of a deliberately heterogeneous family (texture block size, noise share, contrast and brightness all
+    drawn from the seed; anomalous images get 1-3 pasted flat patches of 16-64 px): with random-init weights the image
+    scores of a homogeneous family cluster within a few 1e-3 of each other, this family spreads them.
+    → image [1,3,S,S] fp32 in [0,1], label [1] int64, mask [1,1,S,S] fp32."""
+    g = torch.Generator().manual_seed(int(seed))
+    blk = (2, 4, 8, 16, 32)[int(torch.randint(0, 5, (1,), generator=g))]
+    base = torch.rand(1, 3, size // blk, size // blk, generator=g)
+    base = base.repeat_interleave(blk, dim=2).repeat_interleave(blk, dim=3)
+    alpha = 0.05 + 0.9 * float(torch.rand(1, generator=g))        # noise share
+    contrast = 0.2 + 0.8 * float(torch.rand(1, generator=g))
+    bright = 0.5 + 0.3 * (float(torch.rand(1, generator=g)) - 0.5)
+    img = (1 - alpha) * base + alpha * torch.rand(1, 3, size, size, generator=g)
+    img = ((img - 0.5) * contrast + bright).clamp(0, 1)
+    label = (torch.rand(1, generator=g) < 0.5).long()
+    mask = torch.zeros(1, 1, size, size)
+    if label[0]:
+        for _ in range(int(torch.randint(1, 4, (1,), generator=g))):
+            ps = int(torch.randint(16, 65, (1,), generator=g))
+            y, x = (int(v) for v in torch.randint(0, size - ps, (2,), generator=g))
+            img[0, :, y:y + ps, x:x + ps] = (torch.rand(3, 1, 1, generator=g) > 0.5).float()
+            mask[0, :, y:y + ps, x:x + ps] = 1.0
+    return img, label, mask
+
+
+def make_designed_set(seeds, size: int = 224):
+    """A fixed anomaly set given as one seed per image (tools/design_anomaly_sets.py picks the seeds so that the oracle's
+    image scores of the whole set are pairwise well separated): image i = make_diverse_image(seeds[i])."""
+    parts = [make_diverse_image(int(s), size=size) for s in seeds]
+    return (torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]), torch.cat([p[2] for p in parts]))
+
+
 def batches(images, labels, masks, batch_size: int = 32):
     """The reference DataLoader: shuffle=False, no drop_last (GeneralDataLoader.py:152-156) → short tail batch."""
     return [(images[s:s + batch_size], masks[s:s + batch_size], labels[s:s + batch_size])

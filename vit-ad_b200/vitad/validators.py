@@ -54,6 +54,23 @@ def _metrics(result: dict, fp_thres: float, dataset_name: str, on_device: bool) 
     return calc_all_metrics(result, fp_thres=fp_thres, dataset_name=dataset_name)
 
 
+def _shared_seed() -> int:
+    """One fresh 62-bit seed from torch's CPU generator (follows torch.manual_seed); with torch.distributed
+    initialised every rank takes rank 0's, so all shards of one validation draw the same noise field."""
+    seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            t = seed.to(dev)
+            dist.broadcast(t, src=0)
+            seed = t.cpu()
+    except ImportError:  # pragma: no cover
+        pass
+    return int(seed.item())
+
+
 class _BatchSharding:
     """Batch-granular round-robin sharding: batch i belongs to rank i % world_size."""
 
@@ -78,10 +95,12 @@ class _Pipelined:
 
     DEPTH = 2  # batches in flight
 
-    def _stream_batches(self, batches: Iterable, compute: Callable, copy: bool = True):
+    def _stream_batches(self, batches: Iterable, compute: Callable, copy: bool = True, to_host: bool = True):
         """`batches` yields (batch_index, host_or_device_images, extra).  `compute(images_dev, batch_index)` returns a
         tuple of device tensors.  Yields (batch_index, tuple of host numpy arrays, extra) in input order.  With
-        copy=False the arrays are views of the pinned staging buffers, valid until the next item is requested."""
+        copy=False the arrays are views of the pinned staging buffers, valid until the next item is requested.
+        to_host=False: no D2H at all — yields the device tensors `compute` returned, without synchronising (the H2D
+        prefetch of the next batch still overlaps); for callers that keep working on the device (gather + metrics)."""
         dev = self.device
         main = torch.cuda.current_stream(dev)
         if not hasattr(self, "_s_in"):
@@ -121,6 +140,9 @@ class _Pipelined:
             ev_c.record(main)
             nxt = next(it, None)  # enqueue the next batch's H2D while this batch computes
             staged = stage_in(nxt) if nxt is not None else None
+            if not to_host:
+                yield bi, tuple(outs), extra
+                continue
             slot = self._free_slots.pop(0)
             s_out.wait_event(ev_c)
             host = []
@@ -161,7 +183,7 @@ class ValidatorMdn(_Pipelined):
 
     def __init__(self, gmm_model: list, feature_extractor, dataloader, props: dict, weights_object: list | None = None,
                  weights_base_path: str = "", weights_name: list | str = "", rank: int = 0, world_size: int = 1,
-                 gumbel: Callable[[int, tuple], torch.Tensor] | None = None):
+                 gumbel: Callable[[int, tuple], torch.Tensor] | None = None, gumbel_seed: int | None = None):
         self.gmm_model = gmm_model
         self.feature_extractor = feature_extractor
         self.dataloader = dataloader
@@ -170,7 +192,13 @@ class ValidatorMdn(_Pipelined):
         self.props = props
         self.device = _require_cuda()
         self.shard = _BatchSharding(rank, world_size)
-        self.gumbel = gumbel  # (batch_index, shape) -> noise tensor; None = draw on the device like the reference
+        # Gumbel noise of the mixing weights (the reference draws it from torch's global generator in every call,
+        # MixtureDensityNetwork.py:62).  `gumbel`: (batch_index, shape) -> explicit noise tensor (parity tests).  Otherwise the
+        # kernel generates it from (gumbel_seed, GLOBAL batch index, token, mixture): batch i scores the same on whichever
+        # rank it lands, so a sharded sweep reproduces the unsharded scores bit for bit.  gumbel_seed=None draws one seed
+        # per validator from torch's CPU generator (rank 0's, when torch.distributed is up).
+        self.gumbel = gumbel
+        self.gumbel_seed = _shared_seed() if gumbel_seed is None else int(gumbel_seed)
         _load_weights(self.gmm_model, weights_object, weights_base_path, weights_name)
 
     # -- one batch: host images in, host scores/maps out -------------------------------------------
@@ -185,24 +213,31 @@ class ValidatorMdn(_Pipelined):
         g = None
         if self.gumbel is not None:
             g = self.gumbel(batch_index, (x.shape[0], x.shape[1], model.num_gaussians)).to(self.device, non_blocking=True)
-        prob, image_scores = model.score(x, g)
+        prob, image_scores = model.score(x, g, seed=self.gumbel_seed, batch_index=batch_index)
         grid = int(fe.img_size / fe.patch_size)
         pixel_scores, _ = ops.bilinear_up(prob.view(-1, grid, grid), fe.img_size, align_corners=True,
                                           post_one_minus=True)
         return image_scores, pixel_scores
 
-    def valid_loop_transformer(self, dataloader: Iterable, keep_origs: bool = True) -> dict:
+    def valid_loop_transformer(self, dataloader: Iterable, keep_origs: bool = True, on_device: bool = False) -> dict:
         """ValidatorMDN.py:104-183.  `keep_origs=False` drops the copy of the input images from the result (the
-        reference returns them for its plots)."""
+        reference returns them for its plots).  `on_device=True`: the result rows stay on the GPU as torch tensors
+        (no per-batch D2H; feed them to parallel.gather_results / gpu_metrics.calc_all_metrics_device)."""
+        _reject_cnn_encoder(self.feature_extractor, "ValidatorMdn", "valid_loop_resnet (ValidatorMDN.py:185-273)")
         _place(self.gmm_model[0], self.device)
         _place(self.feature_extractor, self.device)
-        return _collect(self, self.score_batch, dataloader, self.shard, keep_origs=keep_origs)
+        return _collect(self, self.score_batch, dataloader, self.shard, keep_origs=keep_origs, on_device=on_device)
+
+    def valid_loop_resnet(self, dataloader: Iterable, *a, **kw) -> dict:
+        """ValidatorMDN.py:185-273 serves the CNN encoders (ResNet / EfficientNet feature pyramids), which are outside this
+        implementation's scope (transformer encoders only)."""
+        raise NotImplementedError(_CNN_MSG.format(cls="ValidatorMdn", what="valid_loop_resnet (ValidatorMDN.py:185-273)"))
 
     def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True, on_device: bool = True) -> dict:
         """ValidatorMDN.py:71-102 without the W&B / matplotlib side effects: returns the metric dict
         (`on_device`: sort-based metrics on the GPU, vitad.gpu_metrics; False: the reference's sklearn calls)."""
         loader = self.dataloader.get_dataloader(centering=centering)
-        result = self.valid_loop_transformer(loader)
+        result = self.valid_loop_transformer(loader, keep_origs=False, on_device=on_device)
         return _metrics(result, self.props.get("fp_thres", 0.3), self.dataset_name, on_device)
 
 
@@ -229,10 +264,24 @@ class _Rows:
         return self.buf[: self.n]
 
 
-def _collect(validator, loop_body, dataloader, shard, with_recons=False, keep_origs=True):
+_CNN_MSG = ("{cls}: {what} needs a CNN feature extractor (ResNet / EfficientNet), which the B200 scoring path does not "
+            "provide — it covers the transformer encoders (enc_deit, enc_vit, enc_esvit; SURVEY.md §8).  Use the "
+            "reference's PyTorch validator for CNN encoders.")
+
+
+def _reject_cnn_encoder(fe, cls: str, what: str) -> None:
+    """The reference dispatches on the encoder type (ValidatorMDN.py:80-92, ValidatorNF.py:73-84); an encoder that is not
+    one of this package's transformer encoders gets a clear error instead of an AttributeError deep in the loop."""
+    from .encoders import TransformerEncoder
+
+    if not isinstance(fe, TransformerEncoder):
+        raise NotImplementedError(_CNN_MSG.format(cls=cls, what=what) + f"  (got {type(fe).__name__})")
+
+
+def _collect(validator, loop_body, dataloader, shard, with_recons=False, keep_origs=True, on_device=False):
     """Shared batch loop: `loop_body(images, batch_index)` → (scores, maps[, recons]) device tensors, run through the
-    validator's copy/compute pipeline; returns the reference's result dictionary (fp32 numpy)."""
-    acc = {k: _Rows() for k in ("image_scores", "pixel_scores", "image_labels", "pixel_labels", "origs", "recons")}
+    validator's copy/compute pipeline; returns the reference's result dictionary (fp32 numpy; torch tensors on the
+    validator's device with on_device=True — labels as int64 / uint8)."""
     index, sizes = [], []
 
     def mine():
@@ -240,6 +289,34 @@ def _collect(validator, loop_body, dataloader, shard, with_recons=False, keep_or
             if shard.mine(bi):
                 yield bi, images, (images if keep_origs else None, pixel_labels, image_labels)
 
+    if on_device:
+        dev = validator.device
+        rows = {k: [] for k in ("image_scores", "pixel_scores", "image_labels", "pixel_labels", "origs", "recons")}
+        with torch.no_grad():
+            for bi, out, (images, pixel_labels, image_labels) in validator._stream_batches(mine(), loop_body, to_host=False):
+                rows["image_scores"].append(out[0])
+                rows["pixel_scores"].append(out[1])
+                if with_recons:
+                    rows["recons"].append(out[2])
+                rows["image_labels"].append(torch.as_tensor(image_labels).reshape(-1).to(torch.int64))
+                rows["pixel_labels"].append(torch.as_tensor(pixel_labels))
+                if keep_origs:
+                    rows["origs"].append(torch.as_tensor(images))
+                index.append(bi)
+                sizes.append(int(out[0].shape[0]))
+            res = {}
+            for k, v in rows.items():
+                if not v:
+                    continue
+                if k == "pixel_labels":  # masks are 0/1: one byte per pixel crosses PCIe / NVLink instead of four
+                    t = torch.cat([(p != 0).to(torch.uint8) for p in v])
+                else:
+                    t = torch.cat(v)
+                res[k] = t.to(dev, non_blocking=True)
+        res["batch_index"], res["batch_sizes"] = np.asarray(index, dtype=np.int64), np.asarray(sizes, dtype=np.int64)
+        return res
+
+    acc = {k: _Rows() for k in ("image_scores", "pixel_scores", "image_labels", "pixel_labels", "origs", "recons")}
     with torch.no_grad():
         # copy=False: `out` are views of the pinned staging buffers, consumed (copied into the result rows) right here
         for bi, out, (images, pixel_labels, image_labels) in validator._stream_batches(mine(), loop_body, copy=False):
@@ -254,7 +331,7 @@ def _collect(validator, loop_body, dataloader, shard, with_recons=False, keep_or
             index.append(bi)
             sizes.append(int(out[0].shape[0]))
     res = {k: v.get() for k, v in acc.items() if v.n}
-    res["batch_index"], res["batch_sizes"] = np.asarray(index), np.asarray(sizes)
+    res["batch_index"], res["batch_sizes"] = np.asarray(index, dtype=np.int64), np.asarray(sizes, dtype=np.int64)
     return res
 
 
@@ -283,13 +360,19 @@ class ValidatorNF(_Pipelined):
         result = self.nf_model[0].forward_tokens(embedding)
         return result.image_max, result.anomaly_score_map
 
-    def valid_loop_transformer_nf(self, dataloader: Iterable, keep_origs: bool = True) -> dict:
+    def valid_loop_transformer_nf(self, dataloader: Iterable, keep_origs: bool = True, on_device: bool = False) -> dict:
+        _reject_cnn_encoder(self.feature_extractor, "ValidatorNF", "valid_loop_cnn_nf (ValidatorNF.py:166-219)")
         _place(self.nf_model[0], self.device)
         _place(self.feature_extractor, self.device)
-        return _collect(self, self.score_batch, dataloader, self.shard, keep_origs=keep_origs)
+        return _collect(self, self.score_batch, dataloader, self.shard, keep_origs=keep_origs, on_device=on_device)
+
+    def valid_loop_cnn_nf(self, dataloader: Iterable, *a, **kw) -> dict:
+        """ValidatorNF.py:166-219 serves the CNN encoders; outside this implementation's scope."""
+        raise NotImplementedError(_CNN_MSG.format(cls="ValidatorNF", what="valid_loop_cnn_nf (ValidatorNF.py:166-219)"))
 
     def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True, on_device: bool = True) -> dict:
-        result = self.valid_loop_transformer_nf(self.dataloader.get_dataloader(centering=centering))
+        result = self.valid_loop_transformer_nf(self.dataloader.get_dataloader(centering=centering), keep_origs=False,
+                                                on_device=on_device)
         return _metrics(result, self.props.get("fp_thres", 0.3), self.dataset_name, on_device)
 
 
@@ -320,10 +403,12 @@ class ValidatorRecon(_Pipelined):
         amap, score = self.model.anomaly_map_and_score(output.reconstruction, images)
         return score, amap, output.reconstruction
 
-    def valid_loop_mse(self, dataloader: Iterable, keep_origs: bool = True) -> dict:
+    def valid_loop_mse(self, dataloader: Iterable, keep_origs: bool = True, on_device: bool = False) -> dict:
         _place(self.model, self.device)
-        return _collect(self, self.score_batch, dataloader, self.shard, with_recons=True, keep_origs=keep_origs)
+        return _collect(self, self.score_batch, dataloader, self.shard, with_recons=True, keep_origs=keep_origs,
+                        on_device=on_device)
 
     def calc_all_metrics(self, centering: bool = False, new_wandb_run: bool = True, on_device: bool = True) -> dict:
-        result = self.valid_loop_mse(self.dataloader.get_dataloader(centering=centering))
+        result = self.valid_loop_mse(self.dataloader.get_dataloader(centering=centering), keep_origs=False,
+                                     on_device=on_device)
         return _metrics(result, self.props.get("fp_thres", 0.3), self.dataset_name, on_device)
