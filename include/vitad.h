@@ -123,6 +123,15 @@ typedef struct vitad_linear_args {
      * ones are written as plain pixel rows.  out_pad_grid = g > 0 (BIAS_*_F16, RES16_RELU_F16): the GEMM's m = B*g*g
      * plain pixel rows are written into such a zero-bordered layout (the caller zeroes the border once). */
     int conv_grid, out_pad_grid;
+    /* Split-fp16 operands: fp32-grade products on the fp16 tensor cores (used by the reverse-ResNet decoder, whose 53
+     * chained layers otherwise leave 2e-3 on the L2 map).  A value v is stored as hi = fp16(v), lo = fp16(v - hi).
+     * split_c = C > 0 (C % 64 == 0): every tap of `a` holds [hi (C) | lo (C)] columns and every tap of `w`
+     * [w_hi (C) | w_hi (C) | w_lo (C)], k = taps * 3 * C; the K loop pairs them as hi*w_hi + lo*w_hi + hi*w_lo (each
+     * product exact in the fp32 accumulator; the dropped lo*w_lo term is 2^-22 relative).
+     * a_taps > 1: `a` is an explicit im2col layout of that many taps (columns tap-major); taps = 9 with conv_grid.
+     * split_out = 1 (BIAS_F16, BIAS_RELU_F16, CONVT_RELU_F16, RES16_RELU_F16): the epilogue writes [hi (N) | lo (N)]
+     * rows (ldo >= 2N; per pixel for CONVT), and RES16 reads its residual in the same form (ldr >= 2N). */
+    int split_c, a_taps, split_out;
 } vitad_linear_args;
 
 int vitad_linear_f16(const vitad_linear_args* args, void* stream);
@@ -437,6 +446,11 @@ typedef struct vitad_resnet_decoder_weights {
     vitad_resnet_block blocks[VITAD_RESNET_MAX_BLOCKS];
     const void* last_w;
     const float* last_b;
+    /* 1: split-fp16 arithmetic (vitad_linear_args.split_c): every packed weight matrix holds [w_hi | w_hi | w_lo] per tap
+     * (3x the columns listed above), activations travel as [hi | lo] pairs, all channel counts % 64 == 0.  3x the tensor
+     * work for fp32-grade products: the 53 chained layers otherwise leave ~2e-3 of the maximum on the L2 anomaly map,
+     * outside the 1e-3 the reference's fp32 decoder meets.  0: plain fp16 operands. */
+    int split;
 } vitad_resnet_decoder_weights;
 size_t vitad_resnet_decoder_workspace_bytes(const vitad_resnet_decoder_weights* w, int batch);
 int vitad_resnet_decoder_forward(const vitad_resnet_decoder_weights* w, const float* latent, int batch, void* workspace,

@@ -104,7 +104,7 @@ def _run_deit(sd, images, block_index=0):
     with torch.no_grad():
         o = enc(images.cuda(), block_index=block_index)
     torch.cuda.synchronize()
-    return o.patch_embedding.cpu(), o.latent_space.cpu(), o.patch_embedding._vitad_xaug.cpu()
+    return o.patch_embedding.cpu(), o.latent_space.cpu(), o.patch_embedding._vitad_xaug[0].cpu()
 
 
 @pytest.mark.parametrize("tag,stress", [("default", False), ("stress", True)])

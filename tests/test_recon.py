@@ -57,18 +57,18 @@ def test_recon_validator_matches_reference_golden():
     assert res["pixel_scores"].shape == (2, 1, 224, 224) and res["recons"].shape == (2, 3, 224, 224)
     # the cls token comes from the fp16-operand encoder; the decoder amplifies it through 7 layers
     assert np.abs(res["recons"][:, :, ::8, ::8] - g["recons_sub"]).max() <= 2e-3
-    from helpers import assert_rel
+    from helpers import MAP_FLOOR, assert_rel
 
     assert_rel(res["image_scores"], g["image_scores"], 1e-3, what="recon (small decoder) image scores")
-    assert_rel(res["pixel_scores"][:, :, ::8, ::8], g["pixel_scores_sub"], 1e-3, what="recon (small decoder) L2 maps")
+    assert_rel(res["pixel_scores"][:, :, ::8, ::8], g["pixel_scores_sub"], 1e-3, floor_frac=MAP_FLOOR, what="recon (small decoder) L2 maps")
 
 
 @pytest.mark.gpu
 def test_recon_validator_resnet_matches_reference_golden():
     """get_model('ae_deit') (DeiT + reverse-ResNet decoder) through ValidatorRecon.valid_loop_mse against the reference's
-    own run (oracle/make_golden.py case_recon_validator_resnet).  53 fp16-operand GEMM layers sit between the cls token
-    and the image: the measured (and CPU-emulated, tests/test_resnet_decoder.py) rounding floor of the per-pixel map is
-    ~2e-3 of its maximum on these stress weights; bf16 operands, the precision north_star names, would be 8x worse."""
+    own run (oracle/make_golden.py case_recon_validator_resnet).  53 GEMM layers sit between the cls token and the image;
+    the decoder runs them in split-fp16 arithmetic (tests/test_resnet_decoder.py), so what is left is the encoder's
+    fp16-operand error on the cls token, amplified through the decoder."""
     from vitad.model_helper import get_model
     from vitad.validators import ValidatorRecon
 
@@ -82,9 +82,12 @@ def test_recon_validator_resnet_matches_reference_golden():
     val = ValidatorRecon(model, None, props, weights_object=sd)
     res = val.valid_loop_mse(batches)
     assert res["pixel_scores"].shape == (2, 1, 224, 224) and res["recons"].shape == (2, 3, 224, 224)
-    assert np.abs(res["recons"][:, :, ::8, ::8] - g["recons_sub"]).max() <= 2.5e-2
-    assert np.abs(res["image_scores"] - g["image_scores"]).max() <= 2e-3 * np.abs(g["image_scores"]).max()
-    assert np.abs(res["pixel_scores"][:, :, ::8, ::8] - g["pixel_scores_sub"]).max() <= 4e-3 * g["pixel_scores_sub"].max()
+    from helpers import MAP_FLOOR, assert_rel
+
+    assert np.abs(res["recons"][:, :, ::8, ::8] - g["recons_sub"]).max() <= 2e-3
+    assert_rel(res["image_scores"], g["image_scores"], 1e-3, what="recon (reverse-ResNet decoder) image scores")
+    assert_rel(res["pixel_scores"][:, :, ::8, ::8], g["pixel_scores_sub"], 1e-3, floor_frac=MAP_FLOOR,
+               what="recon (reverse-ResNet decoder) L2 maps")
     np.testing.assert_allclose(res["pixel_scores"].sum(axis=(1, 2, 3)), g["pixel_scores_sum"], rtol=1e-3)
 
 
@@ -116,7 +119,7 @@ def test_recon_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
     token -> decoder -> per-pixel L2 -> amax)."""
     from sklearn.metrics import roc_auc_score
 
-    from helpers import DESIGNED_RECON, assert_designed_separation, assert_rel
+    from helpers import DESIGNED_RECON, MAP_FLOOR, assert_designed_separation, assert_rel
     from vitad.model_helper import get_model
     from vitad.synthetic import batches, make_designed_set
     from vitad.validators import ValidatorRecon
@@ -133,6 +136,6 @@ def test_recon_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
     val = ValidatorRecon(get_model("ae_deit", 224), None, props, weights_object=sd)
     res = val.valid_loop_mse(batches(images, labels, masks, batch_size=8))
     assert_rel(res["image_scores"], ref_scores, 1e-3, what="recon image scores")
-    assert_rel(res["pixel_scores"], ref_maps.numpy(), 1e-3, what="recon L2 maps")
+    assert_rel(res["pixel_scores"], ref_maps.numpy(), 1e-3, floor_frac=MAP_FLOOR, what="recon L2 maps")
     assert np.array_equal(np.argsort(ref_scores), np.argsort(res["image_scores"]))
     assert round(roc_auc_score(res["image_labels"], res["image_scores"]), 4) == round(roc_auc_score(labels.numpy(), ref_scores), 4)

@@ -38,7 +38,7 @@ with torch.no_grad():
     print(f"full path B={B}: {t_full:.3f} ms -> {B/t_full*1e3:.0f} img/s; launches/iter ~ {(_lib.launch_count())}")
     # kernel-level breakdown with events around pieces of the head
     M = B*196
-    xf = x.reshape(M, 768); xaug = x._vitad_xaug
+    xf = x.reshape(M, 768); xaug = x._vitad_xaug[0]
     n_kc, kc, _ = _lib.gmm_plan(K)
     lp2 = torch.empty(M, n_kc*kc, device="cuda"); g2 = gn.reshape(M, K).contiguous()
     pk = head._packed

@@ -46,6 +46,24 @@ __global__ void __launch_bounds__(256) cast_f16_kernel(const float* __restrict__
     reinterpret_cast<uint2*>(y)[i] = u;
 }
 
+// y[r] = [hi (cols) | lo (cols)] of x[r] (split-fp16 operand form, gemm_staged.cuh: split_h4); one thread = 4 columns
+__global__ void __launch_bounds__(256) cast_split_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int cols,
+                                                              size_t n4) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const int per_row = cols >> 2;
+    const size_t r = i / per_row;
+    const int c = static_cast<int>(i - r * per_row) << 2;
+    uint2 hi, lo;
+    split_h4(v.x, v.y, v.z, v.w, hi, lo);
+    __half* dst = y + r * (2 * static_cast<size_t>(cols)) + c;
+    *reinterpret_cast<uint2*>(dst) = hi;
+    *reinterpret_cast<uint2*>(dst + cols) = lo;
+}
+
 // A[(b,i,j)][(di,dj,c)] = in[b, i+di, j+dj, c] (NHWC fp16, C channels per pixel), zero outside the Wg x Wg grid.
 // One thread moves 8 channels (16 bytes).
 __global__ void __launch_bounds__(256) im2col2x2_kernel(const __half* __restrict__ in, __half* __restrict__ a, int Wg,
@@ -237,6 +255,7 @@ struct ResWs {
     size_t total;
 };
 ResWs carve_resnet(const vitad_resnet_decoder_weights& w, int batch, void* base) {
+    const size_t S = w.split ? 2 : 1;  // split-fp16 activations: [hi | lo] per pixel
     size_t x_el = static_cast<size_t>(batch) * w.grid0 * w.grid0 * w.feat, h1_el = 0, col_el = 64, h2_el = 0, up_el = 0;
     int g = w.grid0;
     for (int i = 0; i < w.n_blocks; ++i) {
@@ -258,15 +277,15 @@ ResWs carve_resnet(const vitad_resnet_decoder_weights& w, int batch, void* base)
     x_el = std::max(x_el, static_cast<size_t>(batch) * (g + 2) * (g + 2) * w.last_c);  // the image head reads a bordered map
     Carve c{static_cast<uint8_t*>(base)};
     ResWs s;
-    s.lat = c.take(static_cast<size_t>(batch) * w.latent * 2);
-    s.h = c.take(static_cast<size_t>(batch) * w.hidden * 2);
-    s.f = c.take(static_cast<size_t>(batch) * w.feat * 2);
-    s.x[0] = c.take(x_el * 2);
-    s.x[1] = c.take(x_el * 2);
-    s.h1 = c.take(h1_el * 2);
-    s.col = c.take(col_el * 2);
-    s.h2 = c.take(h2_el * 2);
-    s.up = c.take(up_el * 2);
+    s.lat = c.take(static_cast<size_t>(batch) * w.latent * 2 * S);
+    s.h = c.take(static_cast<size_t>(batch) * w.hidden * 2 * S);
+    s.f = c.take(static_cast<size_t>(batch) * w.feat * 2 * S);
+    s.x[0] = c.take(x_el * 2 * S);
+    s.x[1] = c.take(x_el * 2 * S);
+    s.h1 = c.take(h1_el * 2 * S);
+    s.col = c.take(col_el * 2 * S);
+    s.h2 = c.take(h2_el * 2 * S);
+    s.up = c.take(up_el * 2 * S);
     s.total = c.used;
     return s;
 }
@@ -286,6 +305,13 @@ int check_resnet(const vitad_resnet_decoder_weights& w) {
         cin = b.cout;
     }
     VITAD_REQUIRE(cin == w.last_c, VITAD_ERR_SHAPE, "the last block must end in %d channels", w.last_c);
+    if (w.split) {
+        VITAD_REQUIRE(w.split == 1 && w.latent % 64 == 0 && w.hidden % 64 == 0 && w.feat % 64 == 0, VITAD_ERR_SHAPE,
+                      "split-fp16 decoder: every channel count must be a multiple of 64");
+        for (int i = 0; i < w.n_blocks; ++i)
+            VITAD_REQUIRE(w.blocks[i].cin % 64 == 0 && w.blocks[i].width % 64 == 0 && w.blocks[i].cout % 64 == 0,
+                          VITAD_ERR_SHAPE, "split-fp16 decoder: block %d channels must be multiples of 64", i);
+    }
     return VITAD_OK;
 }
 }  // namespace
@@ -377,28 +403,40 @@ extern "C" int vitad_resnet_decoder_forward(const vitad_resnet_decoder_weights* 
     VITAD_REQUIRE(workspace_bytes >= ws.total, VITAD_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, ws.total);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     auto blocks_for = [](size_t n) { return dim3(static_cast<unsigned>((n + 255) / 256)); };
+    // Split-fp16 mode (w.split): activations are [hi | lo] pairs (S = 2 halves per pixel), packed weights hold
+    // [w_hi | w_hi | w_lo] per tap (KM = 3), every GEMM runs the three exact partial products (include/vitad.h: split_c).
+    const int S = w.split ? 2 : 1, KM = w.split ? 3 : 1;
     {
         ProfScope prof("dec_cast", s);
         const size_t n4 = static_cast<size_t>(batch) * w.latent / 4;
-        VITAD_CUDA_OK(launch_pdl(cast_f16_kernel, blocks_for(n4), dim3(256), 0, s, latent, static_cast<__half*>(ws.lat), n4));
+        if (w.split)
+            VITAD_CUDA_OK(launch_pdl(cast_split_f16_kernel, blocks_for(n4), dim3(256), 0, s, latent, static_cast<__half*>(ws.lat),
+                                     w.latent, n4));
+        else
+            VITAD_CUDA_OK(launch_pdl(cast_f16_kernel, blocks_for(n4), dim3(256), 0, s, latent, static_cast<__half*>(ws.lat), n4));
         g_launches.fetch_add(1);
     }
     vitad_linear_args a;
-    auto gemm = [&](const void* A, int M, int K, const void* W, const float* bias, int N, int epi, void* out, int ldo) {
+    // A: `taps` taps of C channels each (S halves per tap); W: [N, taps * KM * C]; out: N channels (S halves)
+    auto gemm = [&](const void* A, int M, int C, int taps, const void* W, const float* bias, int N, int epi, void* out, int ldo) {
         memset(&a, 0, sizeof(a));
-        a.a = A, a.w = W, a.bias = bias, a.m = M, a.n = N, a.k = K, a.lda = K, a.ldw = K, a.epilogue = epi, a.out = out, a.ldo = ldo;
+        a.a = A, a.w = W, a.bias = bias, a.m = M, a.n = N, a.k = taps * KM * C, a.lda = taps * S * C, a.ldw = taps * KM * C;
+        a.epilogue = epi, a.out = out, a.ldo = ldo;
+        a.a_taps = taps > 1 ? taps : 0;
+        a.split_c = w.split ? C : 0;
+        a.split_out = w.split;
     };
     // fc1, fc2 (CnnDecoder.py:171-179, 185-186)
-    gemm(ws.lat, batch, w.latent, w.fc1_w, w.fc1_b, w.hidden, VITAD_EPI_BIAS_RELU_F16, ws.h, w.hidden);
+    gemm(ws.lat, batch, w.latent, 1, w.fc1_w, w.fc1_b, w.hidden, VITAD_EPI_BIAS_RELU_F16, ws.h, S * w.hidden);
     if ((rc = vitad_linear_f16(&a, s))) return rc;
-    gemm(ws.h, batch, w.hidden, w.fc2_w, w.fc2_b, w.feat, VITAD_EPI_BIAS_RELU_F16, ws.f, w.feat);
+    gemm(ws.h, batch, w.hidden, 1, w.fc2_w, w.fc2_b, w.feat, VITAD_EPI_BIAS_RELU_F16, ws.f, S * w.feat);
     if ((rc = vitad_linear_f16(&a, s))) return rc;
     int g = w.grid0;
     {
         ProfScope prof("dec_replicate", s);
-        const size_t total = static_cast<size_t>(batch) * g * g * (w.feat / 8);
+        const size_t total = static_cast<size_t>(batch) * g * g * (S * w.feat / 8);
         VITAD_CUDA_OK(launch_pdl(dec_replicate_kernel, blocks_for(total), dim3(256), 0, s, static_cast<const __half*>(ws.f),
-                                 static_cast<__half*>(ws.x[0]), g * g, w.feat / 8, total));
+                                 static_cast<__half*>(ws.x[0]), g * g, S * w.feat / 8, total));
         g_launches.fetch_add(1);
     }
     int cur = 0;
@@ -413,41 +451,41 @@ extern "C" int vitad_resnet_decoder_forward(const vitad_resnet_decoder_weights* 
         void* y = ws.x[cur ^ 1];
         // conv3 + bn3 + relu (ReverseResNet.py:89-91)
         if (implicit && (bordered_g != g || bordered_w != b.width)) {
-            const size_t total = static_cast<size_t>(batch) * (4 * g + 4) * (b.width / 8);
+            const size_t total = static_cast<size_t>(batch) * (4 * g + 4) * (S * b.width / 8);
             VITAD_CUDA_OK(launch_pdl(dec_zero_border_kernel, blocks_for(total), dim3(256), 0, s, static_cast<__half*>(ws.h1), g,
-                                     b.width / 8, total));
+                                     S * b.width / 8, total));
             g_launches.fetch_add(1);
             bordered_g = g, bordered_w = b.width;
         }
         if (!implicit) bordered_g = 0;
-        gemm(x, M, b.cin, b.w3, b.b3, b.width, VITAD_EPI_BIAS_RELU_F16, ws.h1, b.width);
+        gemm(x, M, b.cin, 1, b.w3, b.b3, b.width, VITAD_EPI_BIAS_RELU_F16, ws.h1, S * b.width);
         a.out_pad_grid = implicit ? g : 0;
         if ((rc = vitad_linear_f16(&a, s))) return rc;
         // conv2 + bn2 + relu (:92-94)
         int Mo = M;
         if (implicit) {
-            gemm(ws.h1, Mp, 9 * b.width, b.w2, b.b2, b.width, VITAD_EPI_BIAS_RELU_F16, ws.h2, b.width);
-            a.lda = b.width, a.conv_grid = g;
+            gemm(ws.h1, Mp, b.width, 9, b.w2, b.b2, b.width, VITAD_EPI_BIAS_RELU_F16, ws.h2, S * b.width);
+            a.lda = S * b.width, a.conv_grid = g, a.a_taps = 0;
             if ((rc = vitad_linear_f16(&a, s))) return rc;
         } else if (b.stride == 1) {
             {
                 ProfScope prof("dec_im2col3", s);
-                const size_t total = static_cast<size_t>(M) * 9 * (b.width / 8);
+                const size_t total = static_cast<size_t>(M) * 9 * (S * b.width / 8);
                 VITAD_CUDA_OK(launch_pdl(dec_im2col3x3_kernel, blocks_for(total), dim3(256), 0, s,
-                                         static_cast<const __half*>(ws.h1), static_cast<__half*>(ws.col), b.width, g, total));
+                                         static_cast<const __half*>(ws.h1), static_cast<__half*>(ws.col), S * b.width, g, total));
                 g_launches.fetch_add(1);
             }
-            gemm(ws.col, M, 9 * b.width, b.w2, b.b2, b.width, VITAD_EPI_BIAS_RELU_F16, ws.h2, b.width);
+            gemm(ws.col, M, b.width, 9, b.w2, b.b2, b.width, VITAD_EPI_BIAS_RELU_F16, ws.h2, S * b.width);
             if ((rc = vitad_linear_f16(&a, s))) return rc;
         } else {
             {
                 ProfScope prof("dec_im2col", s);
-                const size_t total8 = static_cast<size_t>(M) * 4 * (b.width / 8);
+                const size_t total8 = static_cast<size_t>(M) * 4 * (S * b.width / 8);
                 VITAD_CUDA_OK(launch_pdl(im2col2x2_kernel, blocks_for(total8), dim3(256), 0, s,
-                                         static_cast<const __half*>(ws.h1), static_cast<__half*>(ws.col), g, b.width, total8));
+                                         static_cast<const __half*>(ws.h1), static_cast<__half*>(ws.col), g, S * b.width, total8));
                 g_launches.fetch_add(1);
             }
-            gemm(ws.col, M, 4 * b.width, b.w2, b.b2, 4 * b.width, VITAD_EPI_CONVT_RELU_F16, ws.h2, 2 * b.width);
+            gemm(ws.col, M, b.width, 4, b.w2, b.b2, 4 * b.width, VITAD_EPI_CONVT_RELU_F16, ws.h2, S * 2 * b.width);
             a.convt_w = g;
             if ((rc = vitad_linear_f16(&a, s))) return rc;
             Mo = 4 * M;
@@ -455,27 +493,27 @@ extern "C" int vitad_resnet_decoder_forward(const vitad_resnet_decoder_weights* 
         // identity path (:98-99, 186-196): a 1x1 transposed convolution on the input grid, or the block input itself
         const void* resid = x;
         if (b.wup) {
-            gemm(x, M, b.cin, b.wup, b.bup, b.cout, VITAD_EPI_BIAS_F16, ws.up, b.cout);
+            gemm(x, M, b.cin, 1, b.wup, b.bup, b.cout, VITAD_EPI_BIAS_F16, ws.up, S * b.cout);
             if ((rc = vitad_linear_f16(&a, s))) return rc;
             resid = ws.up;
         }
         // conv1 + bn1 + identity + relu (:95-101); the last block writes the zero-bordered layout the image head reads
         const int go = b.stride == 2 ? 2 * g : g;
         if (last) {
-            const size_t total = static_cast<size_t>(batch) * (4 * go + 4) * (b.cout / 8);
+            const size_t total = static_cast<size_t>(batch) * (4 * go + 4) * (S * b.cout / 8);
             VITAD_CUDA_OK(launch_pdl(dec_zero_border_kernel, blocks_for(total), dim3(256), 0, s, static_cast<__half*>(y), go,
-                                     b.cout / 8, total));
+                                     S * b.cout / 8, total));
             g_launches.fetch_add(1);
         }
-        gemm(ws.h2, Mo, b.width, b.w1, b.b1, b.cout, VITAD_EPI_RES16_RELU_F16, y, b.cout);
-        a.resid16 = resid, a.ldr = b.cout, a.res_grid = b.stride == 2 ? g : 0, a.out_pad_grid = last ? go : 0;
+        gemm(ws.h2, Mo, b.width, 1, b.w1, b.b1, b.cout, VITAD_EPI_RES16_RELU_F16, y, S * b.cout);
+        a.resid16 = resid, a.ldr = S * b.cout, a.res_grid = b.stride == 2 ? g : 0, a.out_pad_grid = last ? go : 0;
         if ((rc = vitad_linear_f16(&a, s))) return rc;
         cur ^= 1;
         g = go;
     }
     // image head (CnnDecoder.py:189-194) as an implicit 3x3 convolution producing 4x4 pixel blocks
-    gemm(ws.x[cur], batch * (g + 2) * (g + 2), 9 * w.last_c, w.last_w, w.last_b, 64, VITAD_EPI_TANH_PIX4_F32, recon, 0);
-    a.lda = w.last_c, a.conv_grid = g;
+    gemm(ws.x[cur], batch * (g + 2) * (g + 2), w.last_c, 9, w.last_w, w.last_b, 64, VITAD_EPI_TANH_PIX4_F32, recon, 0);
+    a.lda = S * w.last_c, a.conv_grid = g, a.a_taps = 0, a.split_out = 0;
     a.convt_w = g;
     return vitad_linear_f16(&a, s);
 }

@@ -23,10 +23,17 @@ struct TileSched {
     int tail_tiles;  // = (tiles cut) * tail_split
     int tail_split;  // pieces per cut tile (1, 2, 4, 8)
     int tail_w;      // BLOCK_N / tail_split (multiple of 32)
-    // implicit 3x3 convolution (conv_kpt > 0): A is a zero-bordered NHWC activation [B*(g+2)*(g+2), C]; the K loop walks
-    // 9 taps x conv_kpt = C/64 k-blocks, tap (ty, tx) reads the A rows shifted by (ty-1)*conv_pitch + (tx-1), conv_pitch =
+    // implicit 3x3 convolution (conv_pitch > 0): A is a zero-bordered NHWC activation [B*(g+2)*(g+2), C]; the K loop walks
+    // 9 taps x kpt k-blocks, tap (ty, tx) reads the A rows shifted by (ty-1)*conv_pitch + (tx-1), conv_pitch =
     // g+2 (rows outside the tensor are zero-filled by TMA and only reach border rows, which the epilogue drops)
-    int conv_kpt, conv_pitch;
+    int conv_pitch;
+    // Tapped / split A operand (kpt > 0): the K loop walks taps x kpt k-blocks; tap t reads A columns from t * tap_cols
+    // (explicit im2col layouts; 0 for the row-shifted taps of the implicit convolution above, which sets conv_pitch too).
+    // split_kb > 0 — split-fp16 operands: A rows hold [hi (C) | lo (C)] per tap, W rows [w_hi | w_hi | w_lo] per tap
+    // (C = 64 * split_kb), so kpt = 3 * split_kb and the three segments of a tap read A's hi, lo, hi columns:
+    // hi*w_hi + lo*w_hi + hi*w_lo, every fp16 x fp16 product exact in the fp32 accumulator (fp32-grade products on the fp16
+    // tensor cores; the dropped lo*w_lo term is 2^-22 relative).
+    int kpt, tap_cols, split_kb;
 };
 
 template <int BLOCK_N, int EPI_WARPS>
@@ -205,10 +212,15 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             const uint32_t tx = 2u * static_cast<uint32_t>(S::kABytes + (t.w >> 1) * (kBlockK * 2));
             for (int kb = 0; kb < num_kb; ++kb) {
                 int a_k = kb * kBlockK, a_row = row0;
-                if (sched.conv_kpt > 0) {
-                    const int tap = kb / sched.conv_kpt;
-                    a_k = (kb - tap * sched.conv_kpt) * kBlockK;
-                    a_row = row0 + (tap / 3 - 1) * sched.conv_pitch + (tap % 3 - 1);
+                if (sched.kpt > 0) {
+                    const int tap = kb / sched.kpt;
+                    int r = kb - tap * sched.kpt;
+                    if (sched.split_kb > 0) {  // segments hi, lo, hi of this tap
+                        const int seg = r / sched.split_kb;
+                        r = r - seg * sched.split_kb + (seg == 1 ? sched.split_kb : 0);
+                    }
+                    a_k = tap * sched.tap_cols + r * kBlockK;
+                    if (sched.conv_pitch > 0) a_row = row0 + (tap / 3 - 1) * sched.conv_pitch + (tap % 3 - 1);
                 }
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
@@ -338,6 +350,7 @@ struct SEpiBiasH {
     const float* bias;
     __half* out;
     int ldo, M, N;
+    int split;  // 1: out rows are [hi (N) | lo (N)] (split-fp16 activations, see split_h4)
     __device__ __forceinline__ RowCtx row_ctx(int) const { return RowCtx{0, 0}; }
     __device__ __forceinline__ bool direct(int) const { return false; }
     __device__ __forceinline__ void direct_unit(int, RowCtx, int, const uint32_t (&)[32]) const {}
@@ -350,16 +363,22 @@ struct SEpiBiasH {
     }
     __device__ __forceinline__ void store(int row, RowCtx, int col, float4 a, Pre, ColC b) const {
         if (row < M && col < N) {
-            uint2 u;
-            u.x = pack_h2(act(a.x + b.x), act(a.y + b.y));
-            u.y = pack_h2(act(a.z + b.z), act(a.w + b.w));
-            *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * ldo + col) = u;
+            __half* dst = out + static_cast<size_t>(row) * ldo + col;
+            uint2 u, lo;
+            if (split) {
+                split_h4(act(a.x + b.x), act(a.y + b.y), act(a.z + b.z), act(a.w + b.w), u, lo);
+                *reinterpret_cast<uint2*>(dst + N) = lo;
+            } else {
+                u.x = pack_h2(act(a.x + b.x), act(a.y + b.y));
+                u.y = pack_h2(act(a.z + b.z), act(a.w + b.w));
+            }
+            *reinterpret_cast<uint2*>(dst) = u;
         }
     }
 };
 
 // Pixel-row maps between the plain NHWC layout [B, g, g] and the zero-bordered one [B, g+2, g+2] that the implicit 3x3
-// convolution reads (TileSched::conv_kpt).  -1: the row has no image (out of range, or a border row).
+// convolution reads (TileSched::conv_pitch).  -1: the row has no image (out of range, or a border row).
 __device__ __forceinline__ int row_plain_to_padded(int row, int g) {
     const int x = row % g;
     const int t = row / g;
@@ -389,6 +408,7 @@ struct SEpiBiasHMap {
     const float* bias;
     __half* out;
     int ldo, M, N, mode, g;
+    int split;  // 1: out rows are [hi (N) | lo (N)]
     __device__ __forceinline__ RowCtx row_ctx(int row) const {
         if (row >= M) return RowCtx{0, -1};
         const int r = mode == 1 ? row_plain_to_padded(row, g) : row_padded_to_plain(row, g);
@@ -402,10 +422,17 @@ struct SEpiBiasHMap {
     }
     __device__ __forceinline__ void store(int, RowCtx ctx, int col, float4 a, Pre, ColC b) const {
         if (ctx.b < 0 || col >= N) return;
-        uint2 u;
-        u.x = pack_h2(SEpiBiasH<ACT>::act(a.x + b.x), SEpiBiasH<ACT>::act(a.y + b.y));
-        u.y = pack_h2(SEpiBiasH<ACT>::act(a.z + b.z), SEpiBiasH<ACT>::act(a.w + b.w));
-        *reinterpret_cast<uint2*>(out + static_cast<size_t>(ctx.a) * ldo + col) = u;
+        __half* dst = out + static_cast<size_t>(ctx.a) * ldo + col;
+        uint2 u, lo;
+        if (split) {
+            split_h4(SEpiBiasH<ACT>::act(a.x + b.x), SEpiBiasH<ACT>::act(a.y + b.y), SEpiBiasH<ACT>::act(a.z + b.z),
+                     SEpiBiasH<ACT>::act(a.w + b.w), u, lo);
+            *reinterpret_cast<uint2*>(dst + N) = lo;
+        } else {
+            u.x = pack_h2(SEpiBiasH<ACT>::act(a.x + b.x), SEpiBiasH<ACT>::act(a.y + b.y));
+            u.y = pack_h2(SEpiBiasH<ACT>::act(a.z + b.z), SEpiBiasH<ACT>::act(a.w + b.w));
+        }
+        *reinterpret_cast<uint2*>(dst) = u;
     }
 };
 
@@ -575,6 +602,7 @@ struct SEpiConvT {
     const float* bias;  // [N] = per (phase, channel), BN folded
     __half* out;        // NHWC fp16 [B, 2Wg, 2Wg, Cp]
     int M, N, Wg;       // N = 4*Cp
+    int split;          // 1: every output pixel holds [hi (Cp) | lo (Cp)] channels
     __device__ __forceinline__ RowCtx row_ctx(int row) const {
         if (row >= M) return RowCtx{0, -1};
         return RowCtx{2 * row - (row % Wg), 0};
@@ -590,6 +618,17 @@ struct SEpiConvT {
         const int half_n = N >> 1;  // 2*Cp
         const int pa = col >= half_n ? 1 : 0;
         const int cc = col - pa * half_n;
+        if (split) {
+            // output "row" (b, y, j) = two adjacent pixels of 2*Cp channels each ([hi | lo]); cc = c*Cp + co
+            const int Cp = N >> 2;
+            const int pc = cc >= Cp ? 1 : 0;
+            __half* dst = out + (static_cast<size_t>(ctx.a) + pa * Wg) * (2 * half_n) + pc * (2 * Cp) + (cc - pc * Cp);
+            uint2 u, lo;
+            split_h4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f), u, lo);
+            *reinterpret_cast<uint2*>(dst) = u;
+            *reinterpret_cast<uint2*>(dst + Cp) = lo;
+            return;
+        }
         uint2 u;
         u.x = pack_h2(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f));
         u.y = pack_h2(fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
@@ -604,13 +643,14 @@ struct SEpiConvT {
 struct SEpiResReluH {
     static constexpr bool kRowCtx = true;
     static constexpr int kDefaultEpiWarps = 16;  // output-bound (small K): measured 0.995 -> 0.886 ms on the reverse-ResNet decoder
-    using Pre = uint2;
+    using Pre = uint4;  // residual hi quad (.x, .y) and, in split mode, lo quad (.z, .w)
     using ColC = float4;
     const float* bias;
     const __half* resid;
     __half* out;
     int ldo, ldr, M, N, rg;
     int pad_g;  // > 0: output rows go to the zero-bordered layout [B, pad_g+2, pad_g+2] (feeds an implicit 3x3 convolution)
+    int split;  // 1: residual and output rows are [hi (N) | lo (N)]: the identity stream keeps ~22 mantissa bits
     // ctx.a = residual row (-1: none), ctx.b = output row (-1 when out of range)
     __device__ __forceinline__ RowCtx row_ctx(int row) const {
         if (row >= M) return RowCtx{-1, -1};
@@ -627,20 +667,39 @@ struct SEpiResReluH {
     __device__ __forceinline__ bool direct(int) const { return false; }
     __device__ __forceinline__ void direct_unit(int, RowCtx, int, const uint32_t (&)[32]) const {}
     __device__ __forceinline__ Pre prefetch(int, RowCtx ctx, int col) const {
-        return (ctx.a >= 0 && col < N) ? *reinterpret_cast<const uint2*>(resid + static_cast<size_t>(ctx.a) * ldr + col)
-                                       : make_uint2(0u, 0u);
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        if (ctx.a >= 0 && col < N) {
+            const __half* src = resid + static_cast<size_t>(ctx.a) * ldr + col;
+            const uint2 hi = *reinterpret_cast<const uint2*>(src);
+            r.x = hi.x, r.y = hi.y;
+            if (split) {
+                const uint2 lo = *reinterpret_cast<const uint2*>(src + N);
+                r.z = lo.x, r.w = lo.y;
+            }
+        }
+        return r;
     }
     __device__ __forceinline__ ColC col_const(int col) const {
         return col < N ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __device__ __forceinline__ void store(int, RowCtx ctx, int col, float4 a, Pre r, ColC b) const {
         if (ctx.b < 0 || col >= N) return;
-        const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
-        const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
-        uint2 u;
-        u.x = pack_h2(fmaxf(a.x + b.x + r0.x, 0.f), fmaxf(a.y + b.y + r0.y, 0.f));
-        u.y = pack_h2(fmaxf(a.z + b.z + r1.x, 0.f), fmaxf(a.w + b.w + r1.y, 0.f));
-        *reinterpret_cast<uint2*>(out + static_cast<size_t>(ctx.b) * ldo + col) = u;
+        float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+        float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        __half* dst = out + static_cast<size_t>(ctx.b) * ldo + col;
+        uint2 u, lo;
+        if (split) {
+            const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&r.z));
+            const float2 l1 = __half22float2(*reinterpret_cast<const __half2*>(&r.w));
+            r0.x += l0.x, r0.y += l0.y, r1.x += l1.x, r1.y += l1.y;
+            split_h4(fmaxf(a.x + b.x + r0.x, 0.f), fmaxf(a.y + b.y + r0.y, 0.f), fmaxf(a.z + b.z + r1.x, 0.f),
+                     fmaxf(a.w + b.w + r1.y, 0.f), u, lo);
+            *reinterpret_cast<uint2*>(dst + N) = lo;
+        } else {
+            u.x = pack_h2(fmaxf(a.x + b.x + r0.x, 0.f), fmaxf(a.y + b.y + r0.y, 0.f));
+            u.y = pack_h2(fmaxf(a.z + b.z + r1.x, 0.f), fmaxf(a.w + b.w + r1.y, 0.f));
+        }
+        *reinterpret_cast<uint2*>(dst) = u;
     }
 };
 

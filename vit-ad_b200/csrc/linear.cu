@@ -32,8 +32,10 @@ static TileSched make_sched(int m, int n, int bn, int clusters) {
         s.tail_split *= 2;
     s.tail_tiles = rest * s.tail_split;
     s.tail_w = bn / s.tail_split;
-    s.conv_kpt = 0;
     s.conv_pitch = 0;
+    s.kpt = 0;
+    s.tap_cols = 0;
+    s.split_kb = 0;
     return s;
 }
 // Relative cost of a schedule in units of "one 256 x 256 tile": a cut piece still streams the whole 256-row A block,
@@ -51,10 +53,17 @@ static int launch_gemm_staged_w(const vitad_linear_args& a, const Epi& epi, cuda
     using S = StagedSmem<BLOCK_N, EPI_WARPS>;
     const int max_clusters = device_sm_count() / 2;
     TileSched sched = make_sched(a.m, a.n, BLOCK_N, max_clusters);
-    const int a_cols = a.conv_grid > 0 ? a.k / 9 : a.k;
-    if (a.conv_grid > 0) {
-        sched.conv_kpt = a_cols / kBlockK;
-        sched.conv_pitch = a.conv_grid + 2;
+    // A's width and the K walk (TileSched): plain | implicit 3x3 convolution (row-shifted taps) | explicit im2col taps,
+    // each optionally with split-fp16 operands (A rows [hi | lo] per tap, W rows [w_hi | w_hi | w_lo] per tap)
+    const int taps = a.conv_grid > 0 ? 9 : (a.a_taps > 0 ? a.a_taps : 1);
+    const int per_tap_k = a.k / taps;                                   // W columns per tap
+    const int per_tap_a = a.split_c > 0 ? 2 * a.split_c : per_tap_k;    // A columns per tap
+    const int a_cols = a.conv_grid > 0 ? per_tap_a : taps * per_tap_a;
+    if (a.conv_grid > 0 || a.split_c > 0 || taps > 1) {
+        sched.kpt = per_tap_k / kBlockK;
+        sched.tap_cols = a.conv_grid > 0 ? 0 : per_tap_a;
+        sched.split_kb = a.split_c > 0 ? a.split_c / kBlockK : 0;
+        sched.conv_pitch = a.conv_grid > 0 ? a.conv_grid + 2 : 0;
     }
     CUtensorMap ta, tb, tbt;
     int rc = make_tmap_f16_2d(&ta, a.a, a.m, a_cols, a.lda, kBlockM);
@@ -93,16 +102,16 @@ static int dispatch_staged(const vitad_linear_args& a, cudaStream_t stream) {
             if (a.conv_grid > 0 || a.out_pad_grid > 0)
                 return launch_gemm_staged<BLOCK_N>(a, SEpiBiasHMap<0>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n,
                                                                      a.conv_grid > 0 ? 2 : 1,
-                                                                     a.conv_grid > 0 ? a.conv_grid : a.out_pad_grid}, stream);
-            return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<0>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n}, stream);
+                                                                     a.conv_grid > 0 ? a.conv_grid : a.out_pad_grid, a.split_out}, stream);
+            return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<0>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n, a.split_out}, stream);
         case VITAD_EPI_BIAS_GELU_F16:
-            return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<1>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n}, stream);
+            return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<1>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n, 0}, stream);
         case VITAD_EPI_BIAS_RELU_F16:
             if (a.conv_grid > 0 || a.out_pad_grid > 0)
                 return launch_gemm_staged<BLOCK_N>(a, SEpiBiasHMap<2>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n,
                                                                      a.conv_grid > 0 ? 2 : 1,
-                                                                     a.conv_grid > 0 ? a.conv_grid : a.out_pad_grid}, stream);
-            return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<2>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n}, stream);
+                                                                     a.conv_grid > 0 ? a.conv_grid : a.out_pad_grid, a.split_out}, stream);
+            return launch_gemm_staged<BLOCK_N>(a, SEpiBiasH<2>{a.bias, static_cast<__half*>(a.out), a.ldo, a.m, a.n, a.split_out}, stream);
         case VITAD_EPI_RESIDUAL_F32:
             return launch_gemm_staged<BLOCK_N>(a, SEpiResidualF32{a.bias, a.resid, static_cast<float*>(a.out), a.ldo, a.m, a.n},
                                                stream);
@@ -120,11 +129,11 @@ static int dispatch_staged(const vitad_linear_args& a, cudaStream_t stream) {
         case VITAD_EPI_F32:
             return launch_gemm_staged<BLOCK_N>(a, SEpiBiasF32{a.bias, static_cast<float*>(a.out), a.ldo, a.m, a.n}, stream);
         case VITAD_EPI_CONVT_RELU_F16:
-            return launch_gemm_staged<BLOCK_N>(a, SEpiConvT{a.bias, static_cast<__half*>(a.out), a.m, a.n, a.convt_w}, stream);
+            return launch_gemm_staged<BLOCK_N>(a, SEpiConvT{a.bias, static_cast<__half*>(a.out), a.m, a.n, a.convt_w, a.split_out}, stream);
         case VITAD_EPI_RES16_RELU_F16:
             return launch_gemm_staged<BLOCK_N>(a, SEpiResReluH{a.bias, static_cast<const __half*>(a.resid16),
                                                                static_cast<__half*>(a.out), a.ldo, a.ldr, a.m, a.n, a.res_grid,
-                                                               a.out_pad_grid},
+                                                               a.out_pad_grid, a.split_out},
                                                stream);
         case VITAD_EPI_TANH_PIX4_F32:
             return launch_gemm_staged<BLOCK_N>(a, SEpiTanhPix4{a.bias, static_cast<float*>(a.out), a.m, a.convt_w, a.conv_grid > 0 ? 1 : 0},
@@ -265,6 +274,17 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
     VITAD_REQUIRE(a.k % 16 == 0, VITAD_ERR_SHAPE, "K=%d must be a multiple of 16", a.k);
     VITAD_REQUIRE(a.conv_grid >= 0 && a.out_pad_grid >= 0 && !(a.conv_grid > 0 && a.out_pad_grid > 0), VITAD_ERR_ARG,
                   "conv_grid / out_pad_grid: at most one, non-negative");
+    VITAD_REQUIRE(a.split_c >= 0 && a.a_taps >= 0 && (a.split_out == 0 || a.split_out == 1), VITAD_ERR_ARG,
+                  "split_c / a_taps / split_out out of range");
+    const int taps_chk = a.conv_grid > 0 ? 9 : (a.a_taps > 0 ? a.a_taps : 1);
+    if (a.split_c > 0 || a.a_taps > 1)
+        VITAD_REQUIRE((a.split_c == 0 || (a.split_c % kBlockK == 0 && a.k == taps_chk * 3 * a.split_c)) &&
+                          (a.a_taps <= 1 || (a.conv_grid == 0 && a.k % (a.a_taps * kBlockK) == 0)),
+                      VITAD_ERR_SHAPE, "split operands: K = taps * 3 * split_c with split_c %% 64 == 0; im2col taps: K %% (taps*64) == 0");
+    if (a.split_out)
+        VITAD_REQUIRE(a.epilogue == VITAD_EPI_BIAS_F16 || a.epilogue == VITAD_EPI_BIAS_RELU_F16 ||
+                          a.epilogue == VITAD_EPI_CONVT_RELU_F16 || a.epilogue == VITAD_EPI_RES16_RELU_F16,
+                      VITAD_ERR_ARG, "split_out: bias / ReLU / conv-transpose / residual fp16 epilogues only");
     if (a.conv_grid > 0) {
         const int P = a.conv_grid + 2;
         VITAD_REQUIRE(a.k % (9 * kBlockK) == 0 && a.m % (P * P) == 0 &&
@@ -279,8 +299,10 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
                           (a.epilogue == VITAD_EPI_BIAS_F16 || a.epilogue == VITAD_EPI_BIAS_RELU_F16 ||
                            a.epilogue == VITAD_EPI_RES16_RELU_F16),
                       VITAD_ERR_SHAPE, "out_pad_grid: M = B*g*g and a bias/ReLU/residual fp16 epilogue");
-    VITAD_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0 && a.lda >= (a.conv_grid > 0 ? a.k / 9 : a.k) && a.ldw >= a.k, VITAD_ERR_ALIGN,
-                  "pitches must be >= K and multiples of 8 elements (lda=%d ldw=%d)", a.lda, a.ldw);
+    const int a_width = (a.conv_grid > 0 ? 1 : taps_chk) * (a.split_c > 0 ? 2 * a.split_c : a.k / taps_chk);
+    VITAD_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0 && a.lda >= a_width && a.ldw >= a.k, VITAD_ERR_ALIGN,
+                  "pitches must cover the operands and be multiples of 8 elements (lda=%d >= %d, ldw=%d >= %d)", a.lda, a_width,
+                  a.ldw, a.k);
     if (a.epilogue == VITAD_EPI_F32) {
         VITAD_REQUIRE(a.out && a.ldo >= a.n, VITAD_ERR_ARG, "bad fp32 output");
     } else {
@@ -291,8 +313,8 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
         case VITAD_EPI_BIAS_F16:
         case VITAD_EPI_BIAS_GELU_F16:
         case VITAD_EPI_BIAS_RELU_F16:
-            VITAD_REQUIRE(a.out && aligned16(a.out) && a.ldo % 8 == 0 && a.ldo >= a.n, VITAD_ERR_ALIGN,
-                          "fp16 output must be 16-byte aligned with pitch %% 8 == 0");
+            VITAD_REQUIRE(a.out && aligned16(a.out) && a.ldo % 8 == 0 && a.ldo >= (a.split_out ? 2 : 1) * a.n, VITAD_ERR_ALIGN,
+                          "fp16 output must be 16-byte aligned with pitch %% 8 == 0 (and >= 2N with split_out)");
             break;
         case VITAD_EPI_RESIDUAL_F32:
             VITAD_REQUIRE(a.out && a.resid && aligned16(a.out) && aligned16(a.resid) && a.ldo % 4 == 0 &&
@@ -315,8 +337,9 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
                           VITAD_ERR_SHAPE, "conv-transpose epilogue needs N = 4*Cp with Cp %% 32 == 0 and M = B*Wg*Wg");
             break;
         case VITAD_EPI_RES16_RELU_F16:
-            VITAD_REQUIRE(a.out && a.resid16 && aligned16(a.out) && aligned16(a.resid16) && a.ldo % 8 == 0 && a.ldo >= a.n &&
-                              a.ldr % 8 == 0 && a.ldr >= a.n && a.res_grid >= 0 &&
+            VITAD_REQUIRE(a.out && a.resid16 && aligned16(a.out) && aligned16(a.resid16) && a.ldo % 8 == 0 &&
+                              a.ldo >= (a.split_out ? 2 : 1) * a.n && a.ldr % 8 == 0 && a.ldr >= (a.split_out ? 2 : 1) * a.n &&
+                              a.res_grid >= 0 &&
                               (a.res_grid == 0 || a.m % (4 * a.res_grid * a.res_grid) == 0),
                           VITAD_ERR_ALIGN, "fp16 residual epilogue: aligned out/resid16, pitches %% 8, M = B*(2*res_grid)^2");
             break;
@@ -337,13 +360,14 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
     // the conv-transpose scatter exists only as a staged epilogue of the CTA-pair kernel (which handles any M)
     const bool pair = (g_use_pair.load() && a.m > kBlockM) || a.epilogue == VITAD_EPI_CONVT_RELU_F16 ||
                       a.epilogue == VITAD_EPI_RES16_RELU_F16 || a.epilogue == VITAD_EPI_TANH_PIX4_F32 || a.conv_grid > 0 ||
-                      a.out_pad_grid > 0;
+                      a.out_pad_grid > 0 || a.split_c > 0 || a.a_taps > 1 || a.split_out;
     // block_n is a hint: widths the selected kernel does not instantiate fall back to the library's choice
     const bool hint_ok = pair ? (a.block_n == 128 || a.block_n == 192 || a.block_n == 256)
                               : (a.block_n == 96 || a.block_n == 128 || a.block_n == 256);
     const int bn = hint_ok ? a.block_n : (pair ? pick_block_n_pair(a.m, a.n) : pick_block_n_single(a.m, a.n));
     char pname[64];
-    snprintf(pname, sizeof(pname), "gemm_epi%d_n%d_k%d_bn%d%s", a.epilogue, a.n, a.k, bn, a.conv_grid > 0 ? "_conv3x3" : "");
+    snprintf(pname, sizeof(pname), "gemm_epi%d_n%d_k%d_bn%d%s%s", a.epilogue, a.n, a.k, bn, a.conv_grid > 0 ? "_conv3x3" : "",
+             a.split_c > 0 ? "_split" : "");
     ProfScope prof(pname, s);
     if (pair) {
         if (bn == 256) return dispatch_staged<256>(a, s);

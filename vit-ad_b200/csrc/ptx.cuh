@@ -217,4 +217,15 @@ __device__ __forceinline__ __half to_h(float x) {
     return __half(h);
 }
 
+// Split-fp16 storage of an activation: v ~= hi + lo with hi = fp16(v), lo = fp16(v - hi) (2^-22 relative).  Four values ->
+// the packed hi and lo quads of a [hi | lo] row.
+__device__ __forceinline__ void split_h4(float x, float y, float z, float w, uint2& hi, uint2& lo) {
+    hi.x = pack_h2(x, y);
+    hi.y = pack_h2(z, w);
+    const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x));
+    const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+    lo.x = pack_h2(x - h0.x, y - h0.y);
+    lo.y = pack_h2(z - h1.x, w - h1.y);
+}
+
 }  // namespace vitad

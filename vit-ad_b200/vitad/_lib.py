@@ -94,6 +94,9 @@ class LinearArgs(C.Structure):
         ("res_grid", C.c_int),
         ("conv_grid", C.c_int),
         ("out_pad_grid", C.c_int),
+        ("split_c", C.c_int),
+        ("a_taps", C.c_int),
+        ("split_out", C.c_int),
     ]
 
 
@@ -249,7 +252,7 @@ class ResnetBlock(C.Structure):
 class ResnetDecoderWeights(C.Structure):
     _fields_ = [("latent", _i), ("hidden", _i), ("feat", _i), ("grid0", _i), ("n_blocks", _i), ("last_c", _i),
                 ("fc1_w", _vp), ("fc1_b", _vp), ("fc2_w", _vp), ("fc2_b", _vp), ("blocks", ResnetBlock * RESNET_MAX_BLOCKS),
-                ("last_w", _vp), ("last_b", _vp)]
+                ("last_w", _vp), ("last_b", _vp), ("split", _i)]
 
 
 lib.vitad_resnet_decoder_workspace_bytes.argtypes = [C.POINTER(ResnetDecoderWeights), _i]
