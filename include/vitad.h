@@ -136,6 +136,36 @@ typedef struct vitad_linear_args {
 
 int vitad_linear_f16(const vitad_linear_args* args, void* stream);
 
+/* Residual projection + LayerNorm in one kernel (N = 768), the tail of both halves of a timm Block
+ * (`x = x + drop_path(attn(norm1(x)))` / `x = x + drop_path(mlp(norm2(x)))` followed by the next norm; call sites
+ * TransformerEncoder.py:150-165):
+ *     x[r,:] += a[r,:] . w^T + bias          fp32 [m, 768] residual stream, in place (pitch 768)
+ *     h[r,:]  = LayerNorm(x[r,:]) * gamma + beta   fp16 [m, ldh]
+ * a fp16 [m, k] (pitch lda), w fp16 [768, k] (pitch ldw), k % 64 == 0.  A cluster of four CTAs owns 256 rows over all
+ * 768 columns, so the row statistics never leave the chip (csrc/gemm_ln.cuh). */
+typedef struct vitad_linear_ln_args {
+    const void* a;
+    const void* w;
+    const float* bias;
+    int m, k, lda, ldw;
+    float* x;
+    const float* gamma;
+    const float* beta;
+    float eps;
+    void* h;
+    int ldh;
+} vitad_linear_ln_args;
+int vitad_linear_resid_ln_f16(const vitad_linear_ln_args* args, void* stream);
+/* Encoder forward: fuse each block's two LayerNorms into the preceding residual GEMMs when the batch has enough rows
+ * to fill the 4-CTA clusters (default 1; 0 = always the separate vitad_linear_f16(RESIDUAL_F32) +
+ * vitad_layernorm768_tree launches — the results are bit-identical either way). */
+void vitad_set_fused_ln(int enable);
+/* LayerNorm over C = 768 (x fp32 [rows, ldx] -> out fp16 [rows, ldh]) with exactly the arithmetic of the LayerNorm half of
+ * vitad_linear_resid_ln_f16 (csrc/ln_tree.cuh): bit-identical rows, so the encoder can pick the fused kernel or the
+ * separate launches by row count without changing a result. */
+int vitad_layernorm768_tree(const float* x, const float* weight, const float* bias, void* out_f16, int rows, int ldx,
+                            int ldh, float eps, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Row-wise encoder kernels (HBM-bound).
  * vitad_layernorm: nn.LayerNorm over the last dim (timm Block.norm1/norm2 and VisionTransformer.norm,

@@ -15,7 +15,7 @@ def test_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
     asserted): per-element 1e-3 parity of scores and maps, identical score order, image AUROC identical to 4 decimals."""
     from sklearn.metrics import roc_auc_score
 
-    from helpers import DESIGNED_GMM, GMM_NOISE_SEED_BASE, MAP_FLOOR, assert_designed_separation, assert_rel
+    from helpers import DESIGNED_GMM, GMM_NOISE_SEED_BASE, assert_designed_separation, assert_map_parity, assert_rel
     from oracle import vitad_oracle as O
     from oracle import weights as W
     from vitad.encoders import EncoderDeit
@@ -44,7 +44,7 @@ def test_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
     res = val.valid_loop_transformer(batches(images, labels, masks, batch_size=n))
 
     assert_rel(res["image_scores"], ref_scores, 1e-3, what="image scores")
-    assert_rel(res["pixel_scores"], ref_maps, 1e-3, floor_frac=MAP_FLOOR, what="anomaly maps")
+    assert_map_parity(res["pixel_scores"], ref_maps, what="anomaly maps")
     lab = labels.numpy()
     auroc_ref = roc_auc_score(lab, ref_scores)
     auroc = roc_auc_score(res["image_labels"], res["image_scores"])

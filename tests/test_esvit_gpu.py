@@ -81,7 +81,7 @@ def test_esvit_gmm130_scores_match_oracle():
         tok, _ = O.swin_forward(enc_sd, imgs)
         rs, rm = O.mdn_scores(O.mdn_probability_map(O.mdn_patch_loglik(tok, mdn_sd, gn)), 224, 32)
     torch.cuda.synchronize()
-    from helpers import MAP_FLOOR, assert_rel
+    from helpers import assert_map_parity, assert_rel
 
     assert_rel(scores.cpu().numpy(), rs.numpy(), 1e-3, what="EsViT + GMM image scores")
-    assert_rel(maps.cpu().numpy(), rm.numpy(), 1e-3, floor_frac=MAP_FLOOR, what="EsViT + GMM maps")
+    assert_map_parity(maps.cpu().numpy(), rm.numpy(), what="EsViT + GMM maps")

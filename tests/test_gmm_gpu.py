@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import MAP_FLOOR, assert_rel, golden, gumbel
+from helpers import assert_map_parity, assert_rel, golden, gumbel
 
 pytestmark = pytest.mark.gpu
 
@@ -187,7 +187,7 @@ def test_gmm_validator_path_matches_reference_golden(tag, stress):
     scores, maps = torch.cat(scores).numpy(), torch.cat(maps).numpy()
     ref_s, ref_m = g[f"{tag}_image_scores"], g[f"{tag}_pixel_scores_sub"]
     assert_rel(scores, ref_s, 1e-3, what="image scores")
-    assert_rel(maps[:, :, ::8, ::8], ref_m, 1e-3, floor_frac=MAP_FLOOR, what="anomaly maps")
+    assert_map_parity(maps[:, :, ::8, ::8], ref_m, what="anomaly maps")
     np.testing.assert_allclose(maps.sum(axis=(1, 2, 3)), g[f"{tag}_pixel_scores_sum"], rtol=2e-3)
 
 

@@ -164,3 +164,87 @@ def test_out_pad_grid_scatters_into_the_bordered_layout():
     ref = ops.pad_pixels(_ref(a, w, b).relu().half(), B, g)
     assert (out.float() - ref.float()).abs().max().item() <= 2e-3 * ref.float().abs().max().item()
     assert torch.equal(out.view(B, g + 2, g + 2, n)[:, 0], torch.zeros_like(out.view(B, g + 2, g + 2, n)[:, 0]))
+
+
+@pytest.mark.parametrize("M,K", [(1, 768), (100, 768), (256, 3072), (300, 768), (1000, 3072), (6336, 768), (6336, 3072), (8500, 768)])
+def test_residual_gemm_layernorm_fused_matches_torch(M, K):
+    """vitad_linear_resid_ln_f16 (csrc/gemm_ln.cuh): x += a @ w.T + bias in place (fp32), h = LayerNorm(x) (fp16) — against
+    torch on the same fp16-rounded operands; rows beyond M in the last 256-row block must not be touched; 8500 rows need
+    more clusters than one wave holds.  The separate launches (residual GEMM epilogue + vitad_layernorm768_tree) produce
+    the same bits, and a row's bits do not depend on the rows around it."""
+    import ctypes as C
+
+    from vitad import _lib, ops
+
+    g = torch.Generator().manual_seed(M + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).half().cuda()
+    w = (torch.randn(768, K, generator=g) * (K ** -0.5)).half().cuda()
+    bias = (torch.randn(768, generator=g) * 0.1).cuda()
+    gamma = (1.0 + 0.2 * torch.randn(768, generator=g)).cuda()
+    beta = (0.1 * torch.randn(768, generator=g)).cuda()
+    x0 = (torch.randn(M, 768, generator=g) * 2.0 + 0.3).cuda()
+    pad = 40  # guard rows behind the tensors: a kernel that writes past M corrupts them
+    xbuf = torch.full((M + pad, 768), 7.0, device="cuda")
+    xbuf[:M] = x0
+    hbuf = torch.full((M + pad, 768), 3.0, device="cuda", dtype=torch.float16)
+    args = _lib.LinearLnArgs()
+    args.a, args.w, args.bias, args.m, args.k, args.lda, args.ldw = a.data_ptr(), w.data_ptr(), bias.data_ptr(), M, K, K, K
+    args.x, args.gamma, args.beta, args.eps, args.h, args.ldh = xbuf.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-6, hbuf.data_ptr(), 768
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib.vitad_linear_resid_ln_f16(C.byref(args), s))
+    torch.cuda.synchronize()
+    ref_x = x0.double() + a.double() @ w.double().t() + bias.double()
+    ref_h = torch.nn.functional.layer_norm(ref_x, (768,), gamma.double(), beta.double(), 1e-6)
+    assert torch.equal(xbuf[M:], torch.full((pad, 768), 7.0, device="cuda")) and torch.equal(
+        hbuf[M:], torch.full((pad, 768), 3.0, device="cuda", dtype=torch.float16))
+    ex = (xbuf[:M].double() - ref_x).abs().max().item()
+    eh = (hbuf[:M].double() - ref_h).abs().max().item()
+    assert ex <= 2e-5 * max(1.0, ref_x.abs().max().item()), ex  # fp32 accumulation of exact fp16 products
+    assert eh <= 2e-3 * max(1.0, ref_h.abs().max().item()), eh  # fp16 output rounding (2^-11 relative)
+    # the separate launches: residual-GEMM epilogue, then the standalone LayerNorm with the same expression tree
+    x_sep = x0.clone()
+    ops.linear(a, w, bias, _lib.EPI_RESIDUAL_F32, out=x_sep, resid=x_sep)
+    h_sep = torch.empty(M, 768, device="cuda", dtype=torch.float16)
+    _lib.check(_lib.lib.vitad_layernorm768_tree(x_sep.data_ptr(), gamma.data_ptr(), beta.data_ptr(), h_sep.data_ptr(), M, 768, 768,
+                                                1e-6, s))
+    torch.cuda.synchronize()
+    assert torch.equal(x_sep, xbuf[:M]), (x_sep - xbuf[:M]).abs().max().item()
+    assert torch.equal(h_sep, hbuf[:M]), (h_sep.float() - hbuf[:M].float()).abs().max().item()
+    if M == 300:  # the same rows inside a larger problem give the same bits (batch invariance)
+        x2 = torch.empty(M + 512, 768, device="cuda")
+        x2[:M] = x0
+        x2[M:] = 1.0
+        a2 = torch.zeros(M + 512, K, device="cuda", dtype=torch.float16)
+        a2[:M] = a
+        h2 = torch.empty(M + 512, 768, device="cuda", dtype=torch.float16)
+        args2 = _lib.LinearLnArgs.from_buffer_copy(args)
+        args2.a, args2.m, args2.x, args2.h = a2.data_ptr(), M + 512, x2.data_ptr(), h2.data_ptr()
+        _lib.check(_lib.lib.vitad_linear_resid_ln_f16(C.byref(args2), s))
+        torch.cuda.synchronize()
+        assert torch.equal(x2[:M], xbuf[:M]) and torch.equal(h2[:M], hbuf[:M])
+
+
+def test_fused_and_unfused_encoder_are_bit_identical():
+    """vitad_set_fused_ln(0) keeps the separate residual-GEMM + LayerNorm launches at every batch size; with fusion on, the
+    encoder switches to the fused kernel from 4096 token rows (batch 21).  Both forms evaluate the same expression tree
+    (csrc/ln_tree.cuh): the whole forward is bit-identical, at a batch on either side of the switch."""
+    from oracle import weights as W
+    from vitad import _lib
+    from vitad.encoders import EncoderDeit
+
+    enc = EncoderDeit(224)
+    enc.load_state_dict(W.make_deit_state_dict(seed=11, stress=True))
+    enc = enc.cuda().eval()
+    for B in (24, 5):
+        imgs = W.synthetic_images(seed=3, batch=B).cuda()
+        with torch.no_grad():
+            fused = enc(imgs)
+            _lib.lib.vitad_set_fused_ln(0)
+            try:
+                plain = enc(imgs)
+            finally:
+                _lib.lib.vitad_set_fused_ln(1)
+        torch.cuda.synchronize()
+        assert torch.equal(fused.patch_embedding, plain.patch_embedding), B
+        assert torch.equal(fused.latent_space, plain.latent_space)
+        assert torch.isfinite(fused.patch_embedding).all()

@@ -33,10 +33,10 @@ def test_nf_head_matches_oracle(stress, B):
         r2 = nf(O.tokens_to_nchw(tokens).cuda())  # the reference's NCHW entry point
     torch.cuda.synchronize()
     ref = amap.numpy()
-    from helpers import MAP_FLOOR, assert_rel
+    from helpers import assert_map_parity, assert_rel
 
-    assert_rel(r.anomaly_score_map.cpu().numpy(), ref, 1e-3, floor_frac=MAP_FLOOR, what="NF map (tokens)")
-    assert_rel(r2.anomaly_score_map.cpu().numpy(), ref, 1e-3, floor_frac=MAP_FLOOR, what="NF map (NCHW)")
+    assert_map_parity(r.anomaly_score_map.cpu().numpy(), ref, what="NF map (tokens)")
+    assert_map_parity(r2.anomaly_score_map.cpu().numpy(), ref, what="NF map (NCHW)")
     assert_rel(r.image_max.cpu().numpy(), O.nf_scores(amap).numpy(), 1e-3, what="NF image max")
     assert abs(r.loss.item() - loss.item()) <= 2e-3 * abs(loss.item())
 
@@ -61,10 +61,10 @@ def test_nf_validator_matches_reference_golden(tag, stress):
     res = val.valid_loop_transformer_nf(batches)
     ref_s, ref_m = g[f"{tag}_image_scores"], g[f"{tag}_pixel_scores_sub"]
     assert res["pixel_scores"].shape == (2, 1, 224, 224)
-    from helpers import MAP_FLOOR, assert_rel
+    from helpers import assert_map_parity, assert_rel
 
     assert_rel(res["image_scores"], ref_s, 1e-3, what="NF image scores")
-    assert_rel(res["pixel_scores"][:, :, ::8, ::8], ref_m, 1e-3, floor_frac=MAP_FLOOR, what="NF maps")
+    assert_map_parity(res["pixel_scores"][:, :, ::8, ::8], ref_m, what="NF maps")
     np.testing.assert_allclose(res["pixel_scores"].sum(axis=(1, 2, 3)), g[f"{tag}_pixel_scores_sum"], rtol=2e-3)
 
 
@@ -76,7 +76,7 @@ def test_nf_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
     weights whose subnet gain keeps the scores out of saturation."""
     from sklearn.metrics import roc_auc_score
 
-    from helpers import DESIGNED_NF, NF_TEST_GAIN, MAP_FLOOR, assert_designed_separation, assert_rel
+    from helpers import DESIGNED_NF, NF_TEST_GAIN, assert_designed_separation, assert_map_parity, assert_rel
     from oracle import vitad_oracle as O
     from oracle import weights as W
     from vitad.encoders import EncoderDeit
@@ -97,6 +97,6 @@ def test_nf_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
     val = ValidatorNF([_flow(nf_sd)], enc, None, props)
     res = val.valid_loop_transformer_nf(batches(images, labels, masks, batch_size=4))  # NF scores are per-image: any batching
     assert_rel(res["image_scores"], ref_scores, 1e-3, what="NF image scores")
-    assert_rel(res["pixel_scores"], amap.numpy(), 1e-3, floor_frac=MAP_FLOOR, what="NF anomaly maps")
+    assert_map_parity(res["pixel_scores"], amap.numpy(), what="NF anomaly maps")
     assert np.array_equal(np.argsort(ref_scores), np.argsort(res["image_scores"]))
     assert round(roc_auc_score(res["image_labels"], res["image_scores"]), 4) == round(roc_auc_score(labels.numpy(), ref_scores), 4)

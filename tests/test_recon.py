@@ -57,10 +57,10 @@ def test_recon_validator_matches_reference_golden():
     assert res["pixel_scores"].shape == (2, 1, 224, 224) and res["recons"].shape == (2, 3, 224, 224)
     # the cls token comes from the fp16-operand encoder; the decoder amplifies it through 7 layers
     assert np.abs(res["recons"][:, :, ::8, ::8] - g["recons_sub"]).max() <= 2e-3
-    from helpers import MAP_FLOOR, assert_rel
+    from helpers import assert_map_parity, assert_rel
 
     assert_rel(res["image_scores"], g["image_scores"], 1e-3, what="recon (small decoder) image scores")
-    assert_rel(res["pixel_scores"][:, :, ::8, ::8], g["pixel_scores_sub"], 1e-3, floor_frac=MAP_FLOOR, what="recon (small decoder) L2 maps")
+    assert_map_parity(res["pixel_scores"][:, :, ::8, ::8], g["pixel_scores_sub"], what="recon (small decoder) L2 maps")
 
 
 @pytest.mark.gpu
@@ -82,12 +82,11 @@ def test_recon_validator_resnet_matches_reference_golden():
     val = ValidatorRecon(model, None, props, weights_object=sd)
     res = val.valid_loop_mse(batches)
     assert res["pixel_scores"].shape == (2, 1, 224, 224) and res["recons"].shape == (2, 3, 224, 224)
-    from helpers import MAP_FLOOR, assert_rel
+    from helpers import assert_map_parity, assert_rel
 
     assert np.abs(res["recons"][:, :, ::8, ::8] - g["recons_sub"]).max() <= 2e-3
     assert_rel(res["image_scores"], g["image_scores"], 1e-3, what="recon (reverse-ResNet decoder) image scores")
-    assert_rel(res["pixel_scores"][:, :, ::8, ::8], g["pixel_scores_sub"], 1e-3, floor_frac=MAP_FLOOR,
-               what="recon (reverse-ResNet decoder) L2 maps")
+    assert_map_parity(res["pixel_scores"][:, :, ::8, ::8], g["pixel_scores_sub"], what="recon (reverse-ResNet decoder) L2 maps")
     np.testing.assert_allclose(res["pixel_scores"].sum(axis=(1, 2, 3)), g["pixel_scores_sum"], rtol=1e-3)
 
 
@@ -119,7 +118,7 @@ def test_recon_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
     token -> decoder -> per-pixel L2 -> amax)."""
     from sklearn.metrics import roc_auc_score
 
-    from helpers import DESIGNED_RECON, MAP_FLOOR, assert_designed_separation, assert_rel
+    from helpers import DESIGNED_RECON, assert_designed_separation, assert_map_parity, assert_rel
     from vitad.model_helper import get_model
     from vitad.synthetic import batches, make_designed_set
     from vitad.validators import ValidatorRecon
@@ -136,6 +135,6 @@ def test_recon_image_auroc_identical_to_4_decimals_on_synthetic_anomaly_set():
     val = ValidatorRecon(get_model("ae_deit", 224), None, props, weights_object=sd)
     res = val.valid_loop_mse(batches(images, labels, masks, batch_size=8))
     assert_rel(res["image_scores"], ref_scores, 1e-3, what="recon image scores")
-    assert_rel(res["pixel_scores"], ref_maps.numpy(), 1e-3, floor_frac=MAP_FLOOR, what="recon L2 maps")
+    assert_map_parity(res["pixel_scores"], ref_maps.numpy(), what="recon L2 maps")
     assert np.array_equal(np.argsort(ref_scores), np.argsort(res["image_scores"]))
     assert round(roc_auc_score(res["image_labels"], res["image_scores"]), 4) == round(roc_auc_score(labels.numpy(), ref_scores), 4)

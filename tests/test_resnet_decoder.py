@@ -124,7 +124,7 @@ def _check_against_oracle(got, ref, plain_fp16=False):
     of exactly those rounding points: emulate_packed(half=True); weights and activations contribute equally, no single
     stage dominates), which is why the decoder runs the split-fp16 arithmetic by default (emulate_packed(split=True):
     max 1.1e-5).  plain_fp16=True keeps the old floor bounds for the optional fast mode."""
-    from helpers import MAP_FLOOR, assert_rel
+    from helpers import assert_map_parity, assert_rel
 
     diff = got - ref
     x = torch.rand(ref.shape, generator=torch.Generator().manual_seed(5))
@@ -138,7 +138,7 @@ def _check_against_oracle(got, ref, plain_fp16=False):
         return
     assert diff.abs().max().item() <= 1e-3, diff.abs().max().item()
     assert diff.pow(2).mean().sqrt().item() <= 1e-4, diff.pow(2).mean().sqrt().item()
-    assert_rel(amap_got.numpy(), amap_ref.numpy(), 1e-3, floor_frac=MAP_FLOOR, what="L2 map")
+    assert_map_parity(amap_got.numpy(), amap_ref.numpy(), what="L2 map")
     assert_rel(s_got.numpy(), s_ref.numpy(), 1e-3, what="image score")
 
 

@@ -2,11 +2,20 @@
 // (EncoderDeit.forward, src/classes/transformer/TransformerEncoder.py:145-173; timm 0.6.13
 // VisionTransformerDistilled.forward_features).  Per block: LayerNorm -> QKV GEMM (head-major epilogue)
 // -> fused attention -> proj GEMM (+residual) -> LayerNorm -> fc1 GEMM (+GELU) -> fc2 GEMM (+residual).
-// The residual stream stays fp32 in HBM; GEMM operands are fp16.
+// The residual stream stays fp32 in HBM; GEMM operands are fp16.  In the standard forward (block_index 0) both
+// LayerNorms of a block run inside the residual GEMM that produces their input (vitad_linear_resid_ln_f16, gemm_ln.cuh):
+// proj also emits norm2(x), fc2 also emits the NEXT block's norm1(x) — 26 LayerNorm launches become 3.
+#include <atomic>
+
 #include "host_util.cuh"
+
+namespace vitad {
+extern std::atomic<int> g_fused_ln;  // gemm_ln.cu: residual GEMM + LayerNorm in one kernel (default on)
+}
 
 extern "C" int vitad_layernorm(const float*, const float*, const float*, void*, float*, int, int, int, int, int, int,
                                int, int, float, int, void*);
+extern "C" int vitad_layernorm768_tree(const float*, const float*, const float*, void*, int, int, int, float, void*);
 extern "C" int vitad_patchify(const float*, void*, int, int, int, int, void*);
 extern "C" int vitad_patchify_u8(const uint8_t*, void*, int, int, int, int, void*);
 extern "C" int vitad_prefix_tokens(const float*, const float*, float*, int, int, int, int, void*);
@@ -112,10 +121,20 @@ static int deit_forward_impl(const vitad_deit_weights* wp, const void* images, b
     if ((rc = vitad_prefix_tokens(w.prefix_tokens, w.pos, ws.x, batch, w.prefix, T, C, s))) return rc;
 
     const int last = block_index != 0 ? block_index : w.depth - 1;
+    // block_index != 0 re-normalises the stream after every block (below), which breaks the fc2 -> next norm1 chain
+    // The fused kernel runs one 4-CTA cluster per 256 rows: it pays once the batch fills most of the 33 cluster slots
+    // (batch 32: 25 clusters); below that the separate launches spread the same work over more SMs (batch 1: 0.73 vs
+    // 0.95 ms per image).  Both forms compute every row with the same arithmetic (ln_tree.cuh), bit for bit.
+    const bool fused = vitad::g_fused_ln.load() != 0 && block_index == 0 && C == 768 && rows >= 16 * 256;
+    auto block_norm = [&](const float* gw, const float* gb) {  // a block's norm1 / norm2 as its own launch
+        return C == 768 ? vitad_layernorm768_tree(ws.x, gw, gb, ws.h, rows, C, C, 1e-6f, s)
+                        : vitad_layernorm(ws.x, gw, gb, ws.h, nullptr, rows, C, C, C, 0, rows, rows, 0, 1e-6f, 0, s);
+    };
+    vitad_linear_ln_args f;
     for (int i = 0; i <= last; ++i) {
         const vitad_deit_layer& L = w.layers[i];
-        if ((rc = vitad_layernorm(ws.x, L.ln1_w, L.ln1_b, ws.h, nullptr, rows, C, C, C, 0, rows, rows, 0, 1e-6f, 0, s)))
-            return rc;
+        if (!fused || i == 0)
+            if ((rc = block_norm(L.ln1_w, L.ln1_b))) return rc;
         memset(&a, 0, sizeof(a));
         a.a = ws.h, a.w = L.qkv_w, a.bias = L.qkv_b, a.m = rows, a.n = 3 * C, a.k = C, a.lda = C, a.ldw = C;
         a.epilogue = VITAD_EPI_QKV, a.q = ws.q, a.kmat = ws.k, a.vt = ws.vt;
@@ -127,16 +146,33 @@ static int deit_forward_impl(const vitad_deit_weights* wp, const void* images, b
         at.batch_windows = batch, at.heads = w.heads, at.tokens = T, at.tokens_pad = kTokPad;
         at.head_dim = C / w.heads, at.windows = 1;
         if ((rc = vitad_attention_f16(&at, s))) return rc;
-        memset(&a, 0, sizeof(a));
-        a.a = ws.h, a.w = L.proj_w, a.bias = L.proj_b, a.m = rows, a.n = C, a.k = C, a.lda = C, a.ldw = C;
-        a.epilogue = VITAD_EPI_RESIDUAL_F32, a.out = ws.x, a.resid = ws.x, a.ldo = C;
-        if ((rc = vitad_linear_f16(&a, s))) return rc;
-        if ((rc = vitad_layernorm(ws.x, L.ln2_w, L.ln2_b, ws.h, nullptr, rows, C, C, C, 0, rows, rows, 0, 1e-6f, 0, s)))
-            return rc;
+        if (fused) {
+            // x += proj(attention) + bias;  h = norm2(x).  In place on ws.h: a cluster reads its 256 rows of the attention
+            // output through the whole K loop before its epilogue overwrites the same rows with the normalised stream
+            memset(&f, 0, sizeof(f));
+            f.a = ws.h, f.w = L.proj_w, f.bias = L.proj_b, f.m = rows, f.k = C, f.lda = C, f.ldw = C;
+            f.x = ws.x, f.gamma = L.ln2_w, f.beta = L.ln2_b, f.eps = 1e-6f, f.h = ws.h, f.ldh = C;
+            if ((rc = vitad_linear_resid_ln_f16(&f, s))) return rc;
+        } else {
+            memset(&a, 0, sizeof(a));
+            a.a = ws.h, a.w = L.proj_w, a.bias = L.proj_b, a.m = rows, a.n = C, a.k = C, a.lda = C, a.ldw = C;
+            a.epilogue = VITAD_EPI_RESIDUAL_F32, a.out = ws.x, a.resid = ws.x, a.ldo = C;
+            if ((rc = vitad_linear_f16(&a, s))) return rc;
+            if ((rc = block_norm(L.ln2_w, L.ln2_b))) return rc;
+        }
         memset(&a, 0, sizeof(a));
         a.a = ws.h, a.w = L.fc1_w, a.bias = L.fc1_b, a.m = rows, a.n = w.hidden, a.k = C, a.lda = C, a.ldw = C;
         a.epilogue = VITAD_EPI_BIAS_GELU_F16, a.out = ws.mlp, a.ldo = w.hidden;
         if ((rc = vitad_linear_f16(&a, s))) return rc;
+        if (fused && i < last) {
+            // x += fc2(gelu(fc1)) + bias;  h = norm1 of the NEXT block
+            const vitad_deit_layer& Ln = w.layers[i + 1];
+            memset(&f, 0, sizeof(f));
+            f.a = ws.mlp, f.w = L.fc2_w, f.bias = L.fc2_b, f.m = rows, f.k = w.hidden, f.lda = w.hidden, f.ldw = w.hidden;
+            f.x = ws.x, f.gamma = Ln.ln1_w, f.beta = Ln.ln1_b, f.eps = 1e-6f, f.h = ws.h, f.ldh = C;
+            if ((rc = vitad_linear_resid_ln_f16(&f, s))) return rc;
+            continue;
+        }
         memset(&a, 0, sizeof(a));
         a.a = ws.mlp, a.w = L.fc2_w, a.bias = L.fc2_b, a.m = rows, a.n = C, a.k = w.hidden, a.lda = w.hidden,
         a.ldw = w.hidden;

@@ -93,6 +93,38 @@ int make_tmap_f16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
     return VITAD_OK;
 }
 
+int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                  uint32_t box_rows, uint32_t box_cols, bool swizzle128) {
+    // cached like the fp16 maps; d2 / ld2 carry the extra parameters in the key
+    const TmapKey key{base, 0x8000000000000000ull | static_cast<uint64_t>(elem_bytes) << 8 | (swizzle128 ? 1u : 0u), rows, cols, ld,
+                      ~0ull, box_rows, box_cols};
+    TmapSlot& slot = g_tmaps[tmap_hash(key)];
+    if (slot.used && slot.key == key) {
+        *map = slot.map;
+        return VITAD_OK;
+    }
+    auto enc = get_encode();
+    VITAD_REQUIRE(enc != nullptr, VITAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    VITAD_REQUIRE((elem_bytes == 2 || elem_bytes == 4) && aligned16(base) && (ld * elem_bytes) % 16 == 0, VITAD_ERR_ALIGN,
+                  "TMA operand needs a 16-byte aligned base and pitch (base=%p ld=%llu)", base, (unsigned long long)ld);
+    VITAD_REQUIRE(box_rows >= 1 && box_rows <= 256 && box_cols * elem_bytes <= 128 && (box_cols * elem_bytes) % 16 == 0 &&
+                      (!swizzle128 || box_cols * elem_bytes == 128),
+                  VITAD_ERR_SHAPE, "bad TMA box %ux%u", box_rows, box_cols);
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld * elem_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VITAD_REQUIRE(r == CUDA_SUCCESS, VITAD_ERR_CUDA, "cuTensorMapEncodeTiled(2d any) failed: CUresult %d", (int)r);
+    slot.key = key;
+    slot.map = *map;
+    slot.used = true;
+    return VITAD_OK;
+}
+
 int make_tmap_f16_3d(CUtensorMap* map, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint64_t ld2, uint32_t box_rows, uint32_t box_cols) {
     const TmapKey key{base, d2 == 0 ? ~0ull : d2, rows, cols, ld, ld2, box_rows, box_cols};

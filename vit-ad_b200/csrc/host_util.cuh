@@ -38,6 +38,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // 128-byte swizzle (matches the shared-memory matrix descriptors of ptx.cuh).  Out-of-bounds box elements read as zero.
 int make_tmap_f16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols = 64);
+// General 2-D map: element type fp16 (elem_bytes 2) or fp32 (4), box [box_rows, box_cols], 128-byte swizzle or none.
+int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                  uint32_t box_rows, uint32_t box_cols, bool swizzle128);
 // 3-D variant: [d2, rows, cols] with pitches ld (elements, rows) and ld2 (elements, slabs).
 int make_tmap_f16_3d(CUtensorMap* map, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint64_t ld2, uint32_t box_rows, uint32_t box_cols = 64);

@@ -5,6 +5,7 @@
 #include <atomic>
 
 #include "host_util.cuh"
+#include "ln_tree.cuh"
 #include "ptx.cuh"
 
 namespace vitad {
@@ -263,6 +264,63 @@ __global__ void prefix_tokens_kernel(const float* __restrict__ tok, const float*
 }  // namespace vitad
 
 using namespace vitad;
+
+// LayerNorm over C = 768 with the fused residual-GEMM kernel's arithmetic (ln_tree.cuh), one warp per row: lane c holds
+// column 32 u + c of unit u, so a unit's butterfly sum is the warp's xor-shuffle reduction.  Bit-identical to what
+// gemm_ln_kernel writes for the same row, which lets the encoder choose between the two by row count without changing a bit.
+__global__ void __launch_bounds__(256) layernorm768_tree_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ b, __half* __restrict__ out_h,
+                                                                int rows, int ldx, int ldh, float eps) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + static_cast<size_t>(row) * ldx + lane;
+    float v[kTreeUnits];
+#pragma unroll
+    for (int u = 0; u < kTreeUnits; ++u) v[u] = xr[32 * u];
+    float pm[4], pq[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+#pragma unroll
+        for (int i = 0; i < kTreePartUnits; ++i) {
+            float mu, q;
+            tree_unit_stats_warp(v[p * kTreePartUnits + i], mu, q);
+            if (i == 0) {
+                pm[p] = mu;
+                pq[p] = q;
+            } else {
+                tree_merge(pm[p], pq[p], 32.0f * i, mu, q, 32.0f);
+            }
+        }
+    }
+    constexpr float kPart = 32.0f * kTreePartUnits;
+    tree_merge(pm[0], pq[0], kPart, pm[1], pq[1], kPart);
+    tree_merge(pm[2], pq[2], kPart, pm[3], pq[3], kPart);
+    tree_merge(pm[0], pq[0], 2 * kPart, pm[2], pq[2], 2 * kPart);
+    const float mean = pm[0], rstd = tree_rstd(pq[0], eps);
+    __half* hr = out_h + static_cast<size_t>(row) * ldh + lane;
+#pragma unroll
+    for (int u = 0; u < kTreeUnits; ++u)
+        hr[32 * u] = to_h(tree_normalize(v[u], mean, rstd, __ldg(w + 32 * u + lane), __ldg(b + 32 * u + lane)));
+}
+
+// x fp32 [rows, ldx] -> out fp16 [rows, ldh], C = 768, the arithmetic of vitad_linear_resid_ln_f16's LayerNorm half
+extern "C" int vitad_layernorm768_tree(const float* x, const float* weight, const float* bias, void* out_f16, int rows,
+                                       int ldx, int ldh, float eps, void* stream) {
+    int rc = check_device_arch();
+    if (rc) return rc;
+    VITAD_REQUIRE(x && weight && bias && out_f16 && rows > 0 && ldx >= kTreeC && ldh >= kTreeC, VITAD_ERR_ARG,
+                  "layernorm768_tree arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ProfScope prof("layernorm_tree", s);
+    VITAD_CUDA_OK(launch_pdl(layernorm768_tree_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, weight, bias,
+                             static_cast<__half*>(out_f16), rows, ldx, ldh, eps));
+    VITAD_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return VITAD_OK;
+}
 
 extern "C" int vitad_layernorm(const float* x, const float* weight, const float* bias, void* out_f16, float* out_f32,
                                int rows, int c, int ldx, int ld_f16, int ld_f32, int in_tokens, int out_tokens,

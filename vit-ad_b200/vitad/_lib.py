@@ -104,6 +104,23 @@ lib.vitad_linear_f16.argtypes = [C.POINTER(LinearArgs), C.c_void_p]
 lib.vitad_linear_f16.restype = C.c_int
 
 
+class LinearLnArgs(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("m", C.c_int), ("k", C.c_int),
+                ("lda", C.c_int), ("ldw", C.c_int), ("x", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("eps", C.c_float), ("h", C.c_void_p), ("ldh", C.c_int)]
+
+
+lib.vitad_linear_resid_ln_f16.argtypes = [C.POINTER(LinearLnArgs), C.c_void_p]
+lib.vitad_linear_resid_ln_f16.restype = C.c_int
+lib.vitad_set_fused_ln.argtypes = [C.c_int]
+lib.vitad_set_fused_ln.restype = None
+lib.vitad_layernorm768_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                        C.c_void_p]
+lib.vitad_layernorm768_tree.restype = C.c_int
+if os.environ.get("VITAD_FUSED_LN") == "0":  # diagnostics: separate residual GEMM + LayerNorm launches
+    lib.vitad_set_fused_ln(0)
+
+
 def check(rc: int) -> None:
     if rc != 0:
         raise VitadError(f"vitad status {rc}: {lib.vitad_last_error().decode()}")

@@ -27,39 +27,49 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
     current stream; returns after the last metric value has reached the host."""
     dev = v_gmm.device
     t0 = time.perf_counter()
+    main = torch.cuda.current_stream(dev)
+    # Metrics run on their own stream: their host-side reads (sorted-curve sizes, metric values) then wait only for the
+    # gather of THEIR category, not for the scoring kernels of the next one already queued on the main stream — the SMs
+    # never wait for the host.  Everything a metric touches stays referenced until the final synchronize.
+    side = getattr(v_gmm, "_metrics_stream", None)
+    if side is None:
+        side = v_gmm._metrics_stream = torch.cuda.Stream(dev)
     pending, local_metrics, n_images = [], {}, 0
-    keep_alive = []  # gathered buffers stay referenced until their metrics have been read back
+    keep_alive = []
 
     def finish(entry):
-        ci, name, pend = entry
-        if ci % world != rank:  # not the owner: drop the handle (the collective itself was enqueued by every rank)
-            for tag, p in pend.items():
-                keep_alive.append(p.result())
+        ci, name, pend, ev = entry
+        if ci % world != rank:  # not the owner of this category's metrics: only keep the buffers alive
+            keep_alive.append(pend)
             return
-        for tag, p in pend.items():
-            r = p.result()
-            keep_alive.append(r)
-            if not pixel_metrics:
-                r = {k: v for k, v in r.items() if not k.startswith("pixel")}
-                r["pixel_labels"], r["pixel_scores"] = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
-            m = calc_all_metrics_device(r, fp_thres=fp_thres, dataset_name=name, device=dev)
-            local_metrics[f"{name}/{tag}"] = {k: v for k, v in m.items() if isinstance(v, float)}
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            for tag, p in pend.items():
+                r = p.result()  # waits for the collectives on the metrics stream, stitches the global order
+                keep_alive.append(r)
+                if not pixel_metrics:
+                    r = {k: v for k, v in r.items() if not k.startswith("pixel")}
+                    r["pixel_labels"], r["pixel_scores"] = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+                m = calc_all_metrics_device(r, fp_thres=fp_thres, dataset_name=name, device=dev)
+                local_metrics[f"{name}/{tag}"] = {k: v for k, v in m.items() if isinstance(v, float)}
 
     for ci, (name, (images, labels, masks)) in enumerate(data.items()):
         bl = batches(images, labels, masks, batch_size=batch_size)
         v_gmm.gumbel_seed = gmm_seed + ci  # noise field per category, keyed inside by the global batch index
         rg = v_gmm.valid_loop_transformer(bl, keep_origs=False, on_device=True)
         rn = v_nf.valid_loop_transformer_nf(bl, keep_origs=False, on_device=True)
-        entry = (ci, name, {"gmm": gather_results(rg, len(bl), dev, async_op=True),
-                            "nf": gather_results(rn, len(bl), dev, async_op=True)})
+        pend = {"gmm": gather_results(rg, len(bl), dev, async_op=True), "nf": gather_results(rn, len(bl), dev, async_op=True)}
+        keep_alive.append((rg, rn))
+        ev = torch.cuda.Event()
+        ev.record(main)
         n_images += int(images.shape[0])
-        # metrics of the PREVIOUS category now: its gather has had a whole category of scoring to complete, and this
-        # category's kernels are already queued behind it, so the host-side reads of the metric values do not idle the GPU
+        # metrics of the PREVIOUS category now: its gather has had a whole category of scoring to complete
         if pending:
             finish(pending.pop(0))
-        pending.append(entry)
+        pending.append((ci, name, pend, ev))
     while pending:
         finish(pending.pop(0))
+    main.wait_stream(side)
     torch.cuda.synchronize(dev)
     t_local = time.perf_counter() - t0
 
