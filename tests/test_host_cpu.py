@@ -124,6 +124,17 @@ pend = gather_results(rest, num_batches=len(sizes), device=torch.device("cpu"), 
 full_t = pend.result()
 assert torch.is_tensor(full_t["image_scores"]) and full_t["pixel_labels"].dtype == torch.uint8
 assert np.array_equal(full_t["image_scores"].numpy(), full["image_scores"]) and np.array_equal(full_t["pixel_scores"].numpy(), full["pixel_scores"])
+# the layout path: every rank derives the counts from the dealing rule, nothing is exchanged but the payloads; offset 1
+shard1 = _BatchSharding(rank, world, offset=1)
+mine1 = [b for b in range(len(sizes)) if shard1.mine(b)]
+ids1 = np.concatenate([np.arange(starts[b], starts[b + 1]) for b in mine1]) if mine1 else np.zeros(0, np.int64)
+res1 = {"image_scores": torch.from_numpy(ids1.astype(np.float32) * 0.5), "pixel_scores": torch.from_numpy(np.tile(ids1.astype(np.float32)[:, None, None, None], (1, 1, 4, 4))),
+        "image_labels": torch.from_numpy((ids1 % 2).astype(np.int64)), "pixel_labels": torch.zeros((len(ids1), 1, 4, 4), dtype=torch.uint8),
+        "batch_index": np.asarray(mine1, dtype=np.int64), "batch_sizes": np.asarray([sizes[b] for b in mine1], dtype=np.int64)}
+layout = {"batch_sizes": sizes, "owners": [shard1.owner(b) for b in range(len(sizes))], "map_shape": (1, 4, 4), "pixel_label_dtype": torch.uint8}
+full_l = gather_results(res1, num_batches=len(sizes), device=torch.device("cpu"), async_op=True, layout=layout).result()
+assert np.array_equal(full_l["image_scores"].numpy(), full["image_scores"]) and np.array_equal(full_l["pixel_scores"].numpy(), full["pixel_scores"])
+assert np.array_equal(full_l["image_labels"].numpy(), full["image_labels"]) and full_l["pixel_labels"].dtype == torch.uint8
 # fewer batches than ranks: the rank without a batch must take part in the collectives with empty payloads (no hang, no raise)
 one = [b for b in range(1) if _BatchSharding(rank, world).mine(b)]
 r1 = {"image_scores": np.arange(3, dtype=np.float32), "pixel_scores": np.ones((3, 1, 4, 4), np.float32), "image_labels": np.array([0, 1, 0]),

@@ -69,7 +69,7 @@ class PendingGather:
 
 
 def gather_results(result: dict, num_batches: int, device: torch.device | None = None, async_op: bool = False,
-                   as_numpy: bool | None = None):
+                   as_numpy: bool | None = None, layout: dict | None = None):
     """All-gather the per-rank validator dicts (keys image_scores, pixel_scores, image_labels, pixel_labels,
     batch_index, batch_sizes) and restore the original batch order.  Ranks may hold different numbers of images
     (short tail batches) or none at all: payloads are padded to the per-rank maximum for equal-count
@@ -78,7 +78,11 @@ def gather_results(result: dict, num_batches: int, device: torch.device | None =
     Values may be numpy arrays (valid_loop_*) or torch tensors on `device` (valid_loop_*(on_device=True)); tensors that
     already live on the device are gathered in place — no host round trip.  Returns numpy arrays when the input held
     numpy arrays, device tensors otherwise (`as_numpy` overrides).  async_op=True returns a PendingGather after
-    enqueueing the payload collectives, so the caller can score the next category while NVLink moves this one."""
+    enqueueing the payload collectives, so the caller can score the next category while NVLink moves this one.
+
+    `layout` = {"batch_sizes": images of EVERY batch in loader order, "owners": rank of every batch, "map_shape": (1,S,S),
+    "pixel_label_dtype": torch dtype}: when the caller knows how the batches were dealt (it always does: the sharding rule
+    is deterministic), no metadata has to be exchanged and nothing here synchronises the host with the device."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return PendingGather(lambda: result) if async_op else result
     world = dist.get_world_size()
@@ -92,6 +96,8 @@ def gather_results(result: dict, num_batches: int, device: torch.device | None =
     bidx_local = np.asarray(result["batch_index"], dtype=np.int64).reshape(-1)
     n_local, b_local = int(counts_local.sum()), int(counts_local.size)
 
+    if layout is not None:
+        return _gather_with_layout(result, num_batches, device, async_op, as_numpy, layout, n_local)
     # -- metadata: image / batch counts, trailing map shape and label dtype of every rank (empty ranks send zeros)
     ps = result.get("pixel_scores")
     map_shape = tuple(int(v) for v in ps.shape[1:]) if ps is not None and n_local > 0 else (0, 0, 0)
@@ -153,6 +159,52 @@ def gather_results(result: dict, num_batches: int, device: torch.device | None =
             merged[key] = t.cpu().numpy() if as_numpy else t
         merged["batch_index"] = np.asarray(present, dtype=np.int64)
         merged["batch_sizes"] = np.asarray([len(rows[b]) for b in present], dtype=np.int64)
+        return merged
+
+    return PendingGather(finish) if async_op else finish()
+
+
+def _gather_with_layout(result, num_batches, device, async_op, as_numpy, layout, n_local):
+    """gather_results without the metadata exchange: every rank derives all counts from `layout`."""
+    world = dist.get_world_size()
+    sizes = np.asarray(layout["batch_sizes"], dtype=np.int64)
+    owners = np.asarray(layout["owners"], dtype=np.int64)
+    if sizes.size != num_batches or owners.size != num_batches:
+        raise ValueError("gather_results: layout must describe every batch of the loader")
+    per_rank = np.zeros(world, dtype=np.int64)
+    rows = []
+    for b in range(num_batches):  # row of image k of batch b inside the [world * n_max] gather buffer
+        rows.append((int(owners[b]), int(per_rank[owners[b]]), int(sizes[b])))
+        per_rank[owners[b]] += sizes[b]
+    if n_local != int(per_rank[dist.get_rank()]):
+        raise ValueError(f"gather_results: this rank holds {n_local} images, the layout says {int(per_rank[dist.get_rank()])}")
+    n_max = int(per_rank.max())
+    map_shape = tuple(int(v) for v in layout["map_shape"])
+    pl_dtype = layout.get("pixel_label_dtype", torch.float32)
+    trailing = {"image_scores": (), "pixel_scores": map_shape, "image_labels": (), "pixel_labels": map_shape}
+    works, gathered = [], {}
+    for key, dtype in PAYLOAD:
+        dtype = dtype if dtype is not None else pl_dtype
+        t = torch.zeros((n_max,) + trailing[key], device=device, dtype=dtype)
+        local = result.get(key) if n_local > 0 else None
+        if local is not None:
+            src = _as_tensor(local, device, dtype)
+            t[: src.shape[0]] = src.reshape((src.shape[0],) + trailing[key])
+        out = torch.empty((world * n_max,) + trailing[key], device=device, dtype=dtype)
+        works.append(dist.all_gather_into_tensor(out, t, async_op=True))
+        gathered[key] = out
+    order = np.concatenate([np.arange(r * n_max + off, r * n_max + off + n, dtype=np.int64) for r, off, n in rows])
+    order_dev = torch.from_numpy(order).to(device, non_blocking=True)
+
+    def finish():
+        for w in works:
+            w.wait()
+        merged = {}
+        for key, _ in PAYLOAD:
+            t = gathered[key].index_select(0, order_dev)
+            merged[key] = t.cpu().numpy() if as_numpy else t
+        merged["batch_index"] = np.arange(num_batches, dtype=np.int64)
+        merged["batch_sizes"] = sizes.copy()
         return merged
 
     return PendingGather(finish) if async_op else finish()

@@ -53,12 +53,19 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
                 m = calc_all_metrics_device(r, fp_thres=fp_thres, dataset_name=name, device=dev)
                 local_metrics[f"{name}/{tag}"] = {k: v for k, v in m.items() if isinstance(v, float)}
 
+    dealt = 0  # batches dealt so far: the round-robin continues across categories (61 batches over W ranks, not 15 x "rank 0 first")
     for ci, (name, (images, labels, masks)) in enumerate(data.items()):
         bl = batches(images, labels, masks, batch_size=batch_size)
         v_gmm.gumbel_seed = gmm_seed + ci  # noise field per category, keyed inside by the global batch index
+        v_gmm.shard.offset = v_nf.shard.offset = dealt % world
         rg = v_gmm.valid_loop_transformer(bl, keep_origs=False, on_device=True)
         rn = v_nf.valid_loop_transformer_nf(bl, keep_origs=False, on_device=True)
-        pend = {"gmm": gather_results(rg, len(bl), dev, async_op=True), "nf": gather_results(rn, len(bl), dev, async_op=True)}
+        # every rank knows how the batches were dealt: no metadata exchange, no host/device synchronisation in the gather
+        layout = {"batch_sizes": [int(b[0].shape[0]) for b in bl], "owners": [v_gmm.shard.owner(i) for i in range(len(bl))],
+                  "map_shape": (1, int(images.shape[-2]), int(images.shape[-1])), "pixel_label_dtype": torch.uint8}
+        dealt += len(bl)
+        pend = {"gmm": gather_results(rg, len(bl), dev, async_op=True, layout=layout),
+                "nf": gather_results(rn, len(bl), dev, async_op=True, layout=layout)}
         keep_alive.append((rg, rn))
         ev = torch.cuda.Event()
         ev.record(main)

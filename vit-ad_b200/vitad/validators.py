@@ -72,15 +72,20 @@ def _shared_seed() -> int:
 
 
 class _BatchSharding:
-    """Batch-granular round-robin sharding: batch i belongs to rank i % world_size."""
+    """Batch-granular round-robin sharding: batch i belongs to rank (i + offset) % world_size.  `offset` lets a caller that
+    validates many small data sets in a row (the 15-category sweep) continue the round-robin across them instead of
+    handing batch 0 of every set to rank 0."""
 
-    def __init__(self, rank: int = 0, world_size: int = 1):
+    def __init__(self, rank: int = 0, world_size: int = 1, offset: int = 0):
         if not (0 <= rank < world_size):
             raise ValueError(f"rank {rank} outside world of size {world_size}")
-        self.rank, self.world_size = rank, world_size
+        self.rank, self.world_size, self.offset = rank, world_size, offset
+
+    def owner(self, batch_index: int) -> int:
+        return (batch_index + self.offset) % self.world_size
 
     def mine(self, batch_index: int) -> bool:
-        return batch_index % self.world_size == self.rank
+        return self.owner(batch_index) == self.rank
 
 
 class _Pipelined:
