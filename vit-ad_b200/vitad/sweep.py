@@ -21,7 +21,7 @@ from .synthetic import batches
 
 
 def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size: int = 32, pixel_metrics: bool = True,
-              fp_thres: float = 0.3, gmm_seed: int = 1234) -> dict:
+              fp_thres: float = 0.3, gmm_seed: int = 1234, lag: int | None = None) -> dict:
     """`data`: {category: (images [n,3,S,S], image_labels [n], pixel_labels [n,1,S,S])}, host (pinned) or device tensors.
     → {"metrics": {category/head: {...}} (complete on rank 0), "images": n, "timing": {...}}.  Enqueues everything on the
     current stream; returns after the last metric value has reached the host."""
@@ -36,6 +36,8 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
         side = v_gmm._metrics_stream = torch.cuda.Stream(dev)
     pending, local_metrics, n_images = [], {}, 0
     keep_alive = []
+    if lag is None:
+        lag = len(data)  # enqueue every category's scoring and gathers first: ~0.9 GB of gathered rows stay alive per rank
 
     def finish(entry):
         ci, name, pend, ev = entry
@@ -70,10 +72,12 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
         ev = torch.cuda.Event()
         ev.record(main)
         n_images += int(images.shape[0])
-        # metrics of the PREVIOUS category now: its gather has had a whole category of scoring to complete
-        if pending:
-            finish(pending.pop(0))
         pending.append((ci, name, pend, ev))
+        # Metrics trail the scoring by `lag` categories: their host-side reads block this thread until the category's
+        # gather and sort have run, and the main stream must hold enough queued scoring to cover that wait (at 8 GPUs a
+        # category is ~3 ms of scoring per rank, a metric evaluation ~10 ms of latency).
+        if len(pending) > lag:
+            finish(pending.pop(0))
     while pending:
         finish(pending.pop(0))
     main.wait_stream(side)
