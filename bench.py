@@ -29,7 +29,7 @@ PKG = os.path.join(ROOT, "vit-ad_b200")
 METRIC = "images/sec (DeiT enc+GMM score, 224^2, bs32)"
 WORKLOAD = "enc_deit + MDN/GMM head (100 Gaussians) validation scoring, synthetic 224x224 MVTecAD-shaped images, batch 32 per GPU"
 SWEEP_WORKLOAD = ("full 15-category MVTecAD-sized synthetic validation sweep (DeiT + GMM(100) and DeiT + NF(20 steps) heads), "
-                  "batch 32, NCCL gather of scores/maps/labels + AUROC/PR-AUC on the device")
+                  "batch 32, NCCL exchange of scores/maps/labels + AUROC/PR-AUC on the device")
 ENC_GFLOP_PER_IMG = 35.31
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 REFERENCE_ROOT = os.environ.get("VITAD_REFERENCE", "/root/reference")
@@ -583,9 +583,12 @@ def run_sweep_bench(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
         "config": {"workload": SWEEP_WORKLOAD, "categories": len(host), "images": n_images, "heads_per_image": heads,
                    "images_scored_per_step": scored, "batch": args.batch, "gaussians": K,
-                   "timed_region": "scoring of every batch + all_gather of scores/maps/labels per category + image/pixel AUROC, PR-AUC, PRO on the device",
+                   "timed_region": "scoring of every batch + NCCL exchange of scores/maps/labels to the ranks that evaluate them + image/pixel AUROC, PR-AUC, PRO on the device + all_reduce of the metric values",
                    "l2": "1725 distinct images (1.04 GB fp32) per step, far beyond the 126 MB L2",
-                   "parallelism": f"batches dealt round-robin over {world} ranks, weight replica per rank, one all_gather per category and head (async, overlapped with the next category), metrics of category c on rank c % {world}"},
+                   "parallelism": (f"batches dealt round-robin over {world} ranks across the whole sweep, weight replica per rank; one routed "
+                                   f"all_to_all after the scoring sends validation p = (category, head) to rank p % {world}, which computes its "
+                                   "metrics; metric values all-reduced" if world > 1 else
+                                   "one GPU: metrics of category c on a side stream under the scoring of category c+1")},
         "clocks": clocks.summary(),
         "e2e": {"value": scored * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": heads * (img_bytes + mask_bytes), "d2h_bytes_per_step": 8 * n_metric_floats,

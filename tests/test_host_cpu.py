@@ -135,6 +135,27 @@ layout = {"batch_sizes": sizes, "owners": [shard1.owner(b) for b in range(len(si
 full_l = gather_results(res1, num_batches=len(sizes), device=torch.device("cpu"), async_op=True, layout=layout).result()
 assert np.array_equal(full_l["image_scores"].numpy(), full["image_scores"]) and np.array_equal(full_l["pixel_scores"].numpy(), full["pixel_scores"])
 assert np.array_equal(full_l["image_labels"].numpy(), full["image_labels"]) and full_l["pixel_labels"].dtype == torch.uint8
+# the routed exchange of the sweep: three validations with their own layouts, each wanted in full by one owner rank only
+from vitad.parallel import exchange_to_owners
+entries, truth = [], []
+for p, (szs, off) in enumerate((([4, 4, 3], 0), ([2], 1), ([4, 4, 4, 4, 1], 2))):
+    st = np.cumsum([0] + szs)
+    sh = _BatchSharding(rank, world, offset=off)
+    mine_p = [b for b in range(len(szs)) if sh.mine(b)]
+    ids_p = (np.concatenate([np.arange(st[b], st[b + 1]) for b in mine_p]) if mine_p else np.zeros(0, np.int64)) + 1000 * p
+    resp = {"image_scores": torch.from_numpy(ids_p.astype(np.float32)), "pixel_scores": torch.from_numpy(np.tile(ids_p.astype(np.float32)[:, None, None, None], (1, 1, 4, 4))),
+            "image_labels": torch.from_numpy((ids_p % 2).astype(np.int64)), "pixel_labels": torch.from_numpy((ids_p % 3 == 0).astype(np.uint8)[:, None, None, None].repeat(4, 2).repeat(4, 3))}
+    if not mine_p:
+        resp = {}
+    entries.append({"result": resp, "layout": {"batch_sizes": szs, "owners": [sh.owner(b) for b in range(len(szs))], "map_shape": (1, 4, 4), "pixel_label_dtype": torch.uint8}})
+    truth.append(np.arange(sum(szs)) + 1000 * p)
+pair_owner = [p % world for p in range(3)]
+got = exchange_to_owners(entries, pair_owner, torch.device("cpu"))
+assert sorted(got) == [p for p in range(3) if pair_owner[p] == rank], (rank, sorted(got))
+for p, r in got.items():
+    assert np.array_equal(r["image_scores"].numpy(), truth[p].astype(np.float32)), (p, r["image_scores"])
+    assert np.array_equal(r["pixel_scores"][:, 0, 0, 0].numpy(), truth[p].astype(np.float32)) and r["pixel_scores"].shape[1:] == (1, 4, 4)
+    assert np.array_equal(r["image_labels"].numpy(), truth[p] % 2) and np.array_equal(r["pixel_labels"][:, 0, 0, 0].numpy(), (truth[p] % 3 == 0).astype(np.uint8))
 # fewer batches than ranks: the rank without a batch must take part in the collectives with empty payloads (no hang, no raise)
 one = [b for b in range(1) if _BatchSharding(rank, world).mine(b)]
 r1 = {"image_scores": np.arange(3, dtype=np.float32), "pixel_scores": np.ones((3, 1, 4, 4), np.float32), "image_labels": np.array([0, 1, 0]),

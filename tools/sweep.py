@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Config 5 of BASELINE.json from the command line: the full 15-category MVTecAD-sized synthetic validation sweep (DeiT +
 GMM head and DeiT + NF head), batch 32, batches dealt round-robin over the ranks, NCCL all-gather of scores/maps/labels,
-AUROC / PR-AUC on the device (vitad.sweep.run_sweep; `bench.py --workload sweep` times the same function).
+AUROC / PR-AUC on the device of the rank that owns each validation (vitad.sweep.run_sweep; `bench.py --workload sweep` times the same function).
 
     python tools/sweep.py                                        # 1 GPU
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/sweep.py

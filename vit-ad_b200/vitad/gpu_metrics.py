@@ -51,10 +51,12 @@ def _roc_auc(fps: torch.Tensor, tps: torch.Tensor) -> float:
     n_pos, n_neg = int(tps[-1]), int(fps[-1])
     if n_pos == 0 or n_neg == 0:
         raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
-    zero = torch.zeros(1, dtype=fps.dtype, device=fps.device)
-    fpr = torch.cat((zero, fps)).to(torch.float64) / float(n_neg)
-    tpr = torch.cat((zero, tps)).to(torch.float64) / float(n_pos)
-    return _trapz(fpr, tpr)
+    # the trapezoid area in exact integer arithmetic: 2 * area * P * N = sum (fps_i - fps_{i-1}) * (tps_i + tps_{i-1}) with
+    # (fps_0, tps_0) = (0, 0); the sum is < 2 * P * N <= 2^63 for any tensor that fits a GPU, and one division yields what
+    # sklearn's float64 trapezoid sums to within an ulp — in two passes over the curve instead of six float64 ones
+    df = torch.diff(fps, prepend=fps.new_zeros(1))
+    st = tps + torch.cat((tps.new_zeros(1), tps[:-1]))
+    return float(int((df * st).sum())) / (2.0 * n_pos * n_neg)
 
 
 def roc_auc_score(scores: torch.Tensor, labels: torch.Tensor, curve: Curve | None = None) -> float:

@@ -208,3 +208,72 @@ def _gather_with_layout(result, num_batches, device, async_op, as_numpy, layout,
         return merged
 
     return PendingGather(finish) if async_op else finish()
+
+
+def exchange_to_owners(entries: list, pair_owner: list, device: torch.device | None = None) -> dict:
+    """One routed exchange for many validation results at once: entry p = {"result": this rank's rows of validation p
+    (valid_loop_*(on_device=True); may be empty), "layout": as for gather_results} is needed in full only by rank
+    pair_owner[p] (the rank that evaluates its metrics).  Every rank sends each owner exactly the rows it scored — four
+    all_to_all_single calls (scores, maps, image labels, pixel labels) for the whole list, with split sizes every rank
+    derives from the layouts (no metadata exchange, no host/device synchronisation) — and the owners stitch the global
+    batch order back.  → {p: merged result dict (device tensors)} for the entries this rank owns.
+
+    Why not an all_gather per validation as it completes: a collective kernel waits on the device for its peers, and while
+    it sits on an SM the persistent 1-CTA-per-SM GEMM kernels of the scoring path cannot be fully resident — every early
+    gather turned into a barrier across ranks.  One exchange after the scoring has no such coupling and moves 1/W of
+    the bytes."""
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    me = dist.get_rank() if world > 1 else 0
+    if device is None:
+        device = _default_device() if world > 1 else torch.device("cpu")
+    P = len(entries)
+    n_loc = np.zeros((P, world), dtype=np.int64)  # rows of validation p scored by rank r
+    for p, e in enumerate(entries):
+        sizes = np.asarray(e["layout"]["batch_sizes"], dtype=np.int64)
+        owners = np.asarray(e["layout"]["owners"], dtype=np.int64)
+        np.add.at(n_loc[p], owners, sizes)
+    map_shape = tuple(int(v) for v in entries[0]["layout"]["map_shape"])
+    pl_dtype = entries[0]["layout"].get("pixel_label_dtype", torch.float32)
+    trailing = {"image_scores": (), "pixel_scores": map_shape, "image_labels": (), "pixel_labels": map_shape}
+    owned_by = [[p for p in range(P) if pair_owner[p] == d] for d in range(world)]
+    in_split = [int(sum(n_loc[p][me] for p in owned_by[d])) for d in range(world)]
+    out_split = [int(sum(n_loc[p][s] for p in owned_by[me])) for s in range(world)]
+    received = {}
+    for key, dtype in PAYLOAD:
+        dtype = dtype if dtype is not None else pl_dtype
+        parts = []
+        for d in range(world):
+            for p in owned_by[d]:
+                if n_loc[p][me] > 0:
+                    src = _as_tensor(entries[p]["result"][key], device, dtype)
+                    parts.append(src.reshape((src.shape[0],) + trailing[key]))
+        inp = torch.cat(parts) if parts else torch.empty((0,) + trailing[key], device=device, dtype=dtype)
+        if inp.shape[0] != sum(in_split):
+            raise ValueError(f"exchange_to_owners: {key}: this rank holds {inp.shape[0]} rows, the layouts say {sum(in_split)}")
+        out = torch.empty((sum(out_split),) + trailing[key], device=device, dtype=dtype)
+        if world > 1:
+            dist.all_to_all_single(out, inp.contiguous(), out_split, in_split)
+        else:
+            out = inp
+        received[key] = out
+    # stitch: inside the chunk of source s, my validations follow each other in list order, each with s's batches ascending
+    src_base = np.concatenate(([0], np.cumsum(out_split)))[:-1]
+    merged = {}
+    consumed = np.zeros(world, dtype=np.int64)
+    for p in owned_by[me]:
+        sizes = np.asarray(entries[p]["layout"]["batch_sizes"], dtype=np.int64)
+        owners = np.asarray(entries[p]["layout"]["owners"], dtype=np.int64)
+        within = np.zeros(world, dtype=np.int64)
+        idx = []
+        for b in range(sizes.size):
+            s = int(owners[b])
+            start = src_base[s] + consumed[s] + within[s]
+            idx.append(np.arange(start, start + sizes[b], dtype=np.int64))
+            within[s] += sizes[b]
+        consumed += n_loc[p]
+        order = torch.from_numpy(np.concatenate(idx) if idx else np.zeros(0, np.int64)).to(device, non_blocking=True)
+        res = {key: received[key].index_select(0, order) for key, _ in PAYLOAD}
+        res["batch_index"] = np.arange(sizes.size, dtype=np.int64)
+        res["batch_sizes"] = sizes.copy()
+        merged[p] = res
+    return merged

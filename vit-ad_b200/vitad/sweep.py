@@ -2,10 +2,10 @@
 1/2/4/8 GPUs — what `validation_loop.py` does category by category (validate_mdn :35-84, validate_nf :160-207), with the
 reference's per-category tail (ValidatorMDN.py:170-183 result rows → ValidationHelper.calc_all_metrics :131-211).
 
-Per category: every rank scores its batches (batch i → rank i % W, validators._BatchSharding) with the result rows left
-on the device, the rows are all-gathered over NCCL (parallel.gather_results, asynchronous: NVLink moves category c while
-the SMs score category c+1), and the rank that owns the category (c % W) computes its metrics on the device
-(gpu_metrics) — so the AUROC work is spread over the ranks as well.  The only device→host traffic is the metric values.
+Every rank scores its batches (dealt round-robin over the whole sweep, validators._BatchSharding) with the result rows left
+on the device; one routed NCCL exchange (parallel.exchange_to_owners) then sends each (category, head) validation to the
+rank that evaluates its metrics on the device (gpu_metrics) — so the AUROC sorts are spread over the ranks as well.  The
+only device→host traffic is the metric values.
 """
 from __future__ import annotations
 
@@ -16,88 +16,103 @@ import torch
 import torch.distributed as dist
 
 from .gpu_metrics import calc_all_metrics_device
-from .parallel import gather_results
+from .parallel import exchange_to_owners
 from .synthetic import batches
 
 
+METRIC_KEYS = ("image_auroc_score", "image_prauc_score", "pixel_auroc_score", "pro_score")
+
+
 def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size: int = 32, pixel_metrics: bool = True,
-              fp_thres: float = 0.3, gmm_seed: int = 1234, lag: int | None = None) -> dict:
+              fp_thres: float = 0.3, gmm_seed: int = 1234) -> dict:
     """`data`: {category: (images [n,3,S,S], image_labels [n], pixel_labels [n,1,S,S])}, host (pinned) or device tensors.
-    → {"metrics": {category/head: {...}} (complete on rank 0), "images": n, "timing": {...}}.  Enqueues everything on the
-    current stream; returns after the last metric value has reached the host."""
+    → {"metrics": {category/head: {...}} (complete on every rank), "images": n}.  Returns after the last metric value has
+    reached the host.
+
+    One GPU: the metrics of category c run on a side stream while the main stream scores the following categories (their
+    host-side reads wait only for their own inputs).  Several GPUs: every rank scores its batches of the whole sweep (the
+    round-robin continues across categories: 61 batches over W ranks), then ONE routed exchange sends each validation's
+    rows to the rank that evaluates it (parallel.exchange_to_owners; validation p = (category, head) → rank p % W, so the
+    sorts are spread over the ranks too), then the metric values are summed into place on every rank."""
     dev = v_gmm.device
-    t0 = time.perf_counter()
     main = torch.cuda.current_stream(dev)
-    # Metrics run on their own stream: their host-side reads (sorted-curve sizes, metric values) then wait only for the
-    # gather of THEIR category, not for the scoring kernels of the next one already queued on the main stream — the SMs
-    # never wait for the host.  Everything a metric touches stays referenced until the final synchronize.
-    side = getattr(v_gmm, "_metrics_stream", None)
-    if side is None:
-        side = v_gmm._metrics_stream = torch.cuda.Stream(dev)
-    pending, local_metrics, n_images = [], {}, 0
-    keep_alive = []
-    if lag is None:
-        lag = len(data)  # enqueue every category's scoring and gathers first: ~0.9 GB of gathered rows stay alive per rank
+    heads = ("gmm", "nf")
+    names = list(data)
 
-    def finish(entry):
-        ci, name, pend, ev = entry
-        if ci % world != rank:  # not the owner of this category's metrics: only keep the buffers alive
-            keep_alive.append(pend)
-            return
-        with torch.cuda.stream(side):
-            side.wait_event(ev)
-            for tag, p in pend.items():
-                r = p.result()  # waits for the collectives on the metrics stream, stitches the global order
-                keep_alive.append(r)
-                if not pixel_metrics:
-                    r = {k: v for k, v in r.items() if not k.startswith("pixel")}
-                    r["pixel_labels"], r["pixel_scores"] = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
-                m = calc_all_metrics_device(r, fp_thres=fp_thres, dataset_name=name, device=dev)
-                local_metrics[f"{name}/{tag}"] = {k: v for k, v in m.items() if isinstance(v, float)}
+    def evaluate(r, name):
+        if not pixel_metrics:
+            r = {k: v for k, v in r.items() if not k.startswith("pixel")}
+            r["pixel_labels"], r["pixel_scores"] = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+        m = calc_all_metrics_device(r, fp_thres=fp_thres, dataset_name=name, device=dev)
+        return {k: v for k, v in m.items() if isinstance(v, float) and k != "fp_thres"}
 
-    dealt = 0  # batches dealt so far: the round-robin continues across categories (61 batches over W ranks, not 15 x "rank 0 first")
-    for ci, (name, (images, labels, masks)) in enumerate(data.items()):
+    def score(ci, name, dealt):
+        images, labels, masks = data[name]
         bl = batches(images, labels, masks, batch_size=batch_size)
         v_gmm.gumbel_seed = gmm_seed + ci  # noise field per category, keyed inside by the global batch index
         v_gmm.shard.offset = v_nf.shard.offset = dealt % world
         rg = v_gmm.valid_loop_transformer(bl, keep_origs=False, on_device=True)
         rn = v_nf.valid_loop_transformer_nf(bl, keep_origs=False, on_device=True)
-        # every rank knows how the batches were dealt: no metadata exchange, no host/device synchronisation in the gather
         layout = {"batch_sizes": [int(b[0].shape[0]) for b in bl], "owners": [v_gmm.shard.owner(i) for i in range(len(bl))],
                   "map_shape": (1, int(images.shape[-2]), int(images.shape[-1])), "pixel_label_dtype": torch.uint8}
-        dealt += len(bl)
-        pend = {"gmm": gather_results(rg, len(bl), dev, async_op=True, layout=layout),
-                "nf": gather_results(rn, len(bl), dev, async_op=True, layout=layout)}
-        keep_alive.append((rg, rn))
-        ev = torch.cuda.Event()
-        ev.record(main)
-        n_images += int(images.shape[0])
-        pending.append((ci, name, pend, ev))
-        # Metrics trail the scoring by `lag` categories: their host-side reads block this thread until the category's
-        # gather and sort have run, and the main stream must hold enough queued scoring to cover that wait (at 8 GPUs a
-        # category is ~3 ms of scoring per rank, a metric evaluation ~10 ms of latency).
-        if len(pending) > lag:
-            finish(pending.pop(0))
-    while pending:
-        finish(pending.pop(0))
-    main.wait_stream(side)
-    torch.cuda.synchronize(dev)
-    t_local = time.perf_counter() - t0
+        return rg, rn, layout, len(bl)
 
-    metrics = local_metrics
-    if world > 1:  # metric values (a few floats per category) to rank 0
-        parts = [None] * world
-        dist.all_gather_object(parts, local_metrics)
-        metrics = {}
-        for p in parts:
-            metrics.update(p)
-    ordered = {}
-    for name in data:
-        for tag in ("gmm", "nf"):
-            if f"{name}/{tag}" in metrics:
-                ordered[f"{name}/{tag}"] = metrics[f"{name}/{tag}"]
-    keep_alive.clear()
-    return {"metrics": ordered, "images": n_images, "heads_per_image": 2, "host_s": t_local}
+    metrics, n_images, dealt = {}, 0, 0
+    if world == 1:
+        side = getattr(v_gmm, "_metrics_stream", None)
+        if side is None:
+            side = v_gmm._metrics_stream = torch.cuda.Stream(dev)
+        pending, keep_alive = [], []  # everything a metric touches stays referenced until the final synchronize
+
+        def finish(entry):
+            name, rg, rn, ev = entry
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                for tag, r in zip(heads, (rg, rn)):
+                    metrics[f"{name}/{tag}"] = evaluate(r, name)
+
+        for ci, name in enumerate(names):
+            rg, rn, _layout, nb = score(ci, name, dealt)
+            dealt += nb
+            n_images += int(data[name][0].shape[0])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            keep_alive.append((rg, rn))
+            if pending:  # metrics of the PREVIOUS category: this category's kernels are already queued behind its inputs
+                finish(pending.pop(0))
+            pending.append((name, rg, rn, ev))
+        while pending:
+            finish(pending.pop(0))
+        main.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        keep_alive.clear()
+    else:
+        entries = []
+        for ci, name in enumerate(names):
+            rg, rn, layout, nb = score(ci, name, dealt)
+            dealt += nb
+            n_images += int(data[name][0].shape[0])
+            entries += [{"result": rg, "layout": layout}, {"result": rn, "layout": layout}]
+        pair_owner = [p % world for p in range(len(entries))]
+        mine = exchange_to_owners(entries, pair_owner, dev)
+        # metric values: one [pairs, keys] table, every rank fills the rows it owns, a sum puts them everywhere
+        table = torch.full((len(entries), len(METRIC_KEYS)), float("nan"), dtype=torch.float64)
+        for p, r in mine.items():
+            m = evaluate(r, names[p // 2])
+            for j, key in enumerate(METRIC_KEYS):
+                hit = [v for k, v in m.items() if k.startswith(key)]
+                if hit:
+                    table[p, j] = hit[0]
+        present = (~torch.isnan(table)).to(torch.float64)
+        packed = torch.stack((torch.nan_to_num(table, nan=0.0), present)).to(dev)
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+        packed = packed.cpu()
+        pro_key = f"pro_score_{fp_thres}fp"
+        for p in range(len(entries)):
+            name, tag = names[p // 2], heads[p % 2]
+            metrics[f"{name}/{tag}"] = {(pro_key if key == "pro_score" else key): float(packed[0, p, j])
+                                        for j, key in enumerate(METRIC_KEYS) if packed[1, p, j] > 0}
+    return {"metrics": metrics, "images": n_images, "heads_per_image": 2}
 
 
 def build_sweep_models(rank: int, world: int, device, gaussians: int = 100):
