@@ -76,3 +76,32 @@ def test_device_metrics_equal_sklearn_on_validator_output():
         if isinstance(v, float):
             assert round(got[k], 4) == round(v, 4), (k, got[k], v)
     assert set(got) == set(ref)
+
+
+def test_sweep_metrics_equal_the_per_validator_sklearn_path():
+    """vitad.sweep.run_sweep (device-resident rows, metrics on a side stream, one sort per validation) against the
+    reference-shaped path: valid_loop_* → numpy result dictionary → sklearn (vitad.metrics = ValidationHelper.py:131-211),
+    category by category, on host-resident and on device-resident data."""
+    from vitad.metrics import calc_all_metrics
+    from vitad.sweep import build_sweep_models, run_sweep
+    from vitad.synthetic import batches, make_category
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    v_gmm, v_nf = build_sweep_models(0, 1, dev)
+    data = {"alpha": make_category("alpha", 37, seed=901), "beta": make_category("beta", 70, seed=902)}
+    data = {k: (t[0].pin_memory(), t[1], (t[2] != 0).to(torch.uint8)) for k, t in data.items()}
+    out = run_sweep(v_gmm, v_nf, data, batch_size=32)
+    resident = {k: (t[0].to(dev), t[1], t[2].to(dev)) for k, t in data.items()}
+    out_dev = run_sweep(v_gmm, v_nf, resident, batch_size=32)
+    assert out["images"] == 107 and out["metrics"] == out_dev["metrics"]
+    for ci, (name, (images, labels, masks)) in enumerate(data.items()):
+        bl = batches(images, labels, masks.float(), batch_size=32)
+        v_gmm.gumbel_seed = 1234 + ci
+        v_gmm.shard.offset = v_nf.shard.offset = 0
+        for tag, res in (("gmm", v_gmm.valid_loop_transformer(bl, keep_origs=False)),
+                         ("nf", v_nf.valid_loop_transformer_nf(bl, keep_origs=False))):
+            ref = calc_all_metrics(res, fp_thres=0.3, dataset_name=name)
+            got = out["metrics"][f"{name}/{tag}"]
+            for k, v in ref.items():
+                if isinstance(v, float) and k != "fp_thres":
+                    assert abs(got[k] - v) < 1e-6, (name, tag, k, got[k], v)

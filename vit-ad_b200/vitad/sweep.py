@@ -46,9 +46,40 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
         m = calc_all_metrics_device(r, fp_thres=fp_thres, dataset_name=name, device=dev)
         return {k: v for k, v in m.items() if isinstance(v, float) and k != "fp_thres"}
 
-    def score(ci, name, dealt):
-        images, labels, masks = data[name]
+    # Host-resident data: both heads read the same images, so this rank's batches of a category cross PCIe ONCE, on a copy
+    # stream, one category ahead of the scoring (the validators then see device tensors and copy nothing).
+    copy_stream = getattr(v_gmm, "_sweep_copy_stream", None)
+    if copy_stream is None:
+        copy_stream = v_gmm._sweep_copy_stream = torch.cuda.Stream(dev)
+    staged, uploads = {}, []  # uploads: keeps the staged tensors referenced until the final synchronize
+    deal, acc = [], 0  # first global batch number of every category (the round-robin continues across categories)
+    for name in names:
+        deal.append(acc)
+        acc += -(-int(data[name][0].shape[0]) // batch_size)
+
+    def stage(ci):
+        if ci >= len(names) or ci in staged:
+            return
+        images, labels, masks = data[names[ci]]
         bl = batches(images, labels, masks, batch_size=batch_size)
+        ev = None
+        if not (torch.is_tensor(images) and images.device == dev):
+            off = deal[ci] % world
+            with torch.cuda.stream(copy_stream):
+                bl = [((b[0].to(dev, non_blocking=True), torch.as_tensor(b[1]).to(dev, non_blocking=True), b[2])
+                       if (i + off) % world == rank else b) for i, b in enumerate(bl)]
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            uploads.append(bl)
+        staged[ci] = (bl, ev)
+
+    def score(ci, name, dealt):
+        images = data[name][0]
+        stage(ci)
+        bl, ev = staged.pop(ci)
+        stage(ci + 1)  # the next category's upload runs under this category's kernels
+        if ev is not None:
+            main.wait_event(ev)
         v_gmm.gumbel_seed = gmm_seed + ci  # noise field per category, keyed inside by the global batch index
         v_gmm.shard.offset = v_nf.shard.offset = dealt % world
         rg = v_gmm.valid_loop_transformer(bl, keep_origs=False, on_device=True)
@@ -107,6 +138,7 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
         packed = torch.stack((torch.nan_to_num(table, nan=0.0), present)).to(dev)
         dist.all_reduce(packed, op=dist.ReduceOp.SUM)
         packed = packed.cpu()
+        torch.cuda.synchronize(dev)
         pro_key = f"pro_score_{fp_thres}fp"
         for p in range(len(entries)):
             name, tag = names[p // 2], heads[p % 2]
