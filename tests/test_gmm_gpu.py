@@ -274,3 +274,23 @@ def test_log_pi_tensor_core_path_matches_fp32_kernel(K, M):
     print(f"log2-probability max error vs float64: tensor-core split-fp16 {err_tc:.2e}, fp32 CUDA-core kernel {err_f32:.2e}")
     # log2-probabilities reach -20: 1e-4 absolute is a few fp32 ulps of summation-order noise in the 768-term logits
     assert err_f32 <= 5e-5 and err_tc <= 3e-4, (err_tc, err_f32)
+
+
+def test_nan_is_not_swallowed_by_the_score_reductions():
+    """torch.max / torch.amax propagate NaN in the reference (MixtureDensityNetwork.py:90-92, ValidatorNF.py:137-142,
+    ValidatorRecon.py:116): a numerical failure upstream must surface as a NaN score (and make the metrics raise), not as
+    a plausible number."""
+    from vitad import ops
+
+    L = torch.randn(3, 196, device="cuda") - 900.0
+    L[1, 17] = float("nan")
+    prob, scores = torch.ops.vitad.gmm_finish(L)
+    assert torch.isnan(scores).all() and torch.isnan(prob).all()  # the batch-global max couples every image
+    x = torch.rand(4, 14, 14, device="cuda")
+    x[2, 3, 3] = float("nan")
+    _, mx = ops.bilinear_up(x, 224, align_corners=False, want_max=True)
+    assert torch.isnan(mx[2]) and torch.isfinite(mx[[0, 1, 3]]).all()
+    recon, img = torch.rand(2, 3, 224, 224, device="cuda"), torch.rand(2, 3, 224, 224, device="cuda")
+    recon[0, 1, 100, 7] = float("nan")
+    _, sc = ops.l2_map_score(recon, img)
+    assert torch.isnan(sc[0]) and torch.isfinite(sc[1])

@@ -514,7 +514,14 @@ __global__ void __launch_bounds__(1024) gmm_finish_kernel(const float* __restric
     __shared__ float gmax;
     const int M = B * P;
     float mx = -INFINITY;
-    for (int i = threadIdx.x; i < M; i += blockDim.x) mx = fmaxf(mx, L[i]);
+    // a NaN log-likelihood poisons the batch maximum, hence every probability and score, as torch.max does in the
+    // reference (:90-92); fmaxf / fminf alone would drop it
+    bool saw_nan = false;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        mx = fmaxf(mx, L[i]);
+        saw_nan |= L[i] != L[i];
+    }
+    saw_nan = __syncthreads_or(saw_nan);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -523,7 +530,7 @@ __global__ void __launch_bounds__(1024) gmm_finish_kernel(const float* __restric
         float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (threadIdx.x == 0) gmax = v;
+        if (threadIdx.x == 0) gmax = saw_nan ? __int_as_float(0x7FC00000) : v;
     }
     __syncthreads();
     const float g = gmax;
@@ -535,7 +542,7 @@ __global__ void __launch_bounds__(1024) gmm_finish_kernel(const float* __restric
         for (int p = lane; p < P; p += 32) mn = fminf(mn, expf(L[b * P + p] - g));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        if (lane == 0) scores[b] = 1.0f - mn;
+        if (lane == 0) scores[b] = saw_nan ? g : 1.0f - mn;
     }
 }
 

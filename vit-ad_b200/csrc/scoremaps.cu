@@ -6,7 +6,10 @@
 //   * reconstruction L2 map: mean_c (recon - x)^2 and its per-image max
 //       CnnAutoEncoder.py:49,68-74 + ValidatorRecon.py:109-116
 // 128-bit stores, one thread per 4 output pixels; per-image max via warp shuffle + atomicMax on the
-// (non-negative) float bit pattern, which is order independent and therefore deterministic.
+// (non-negative) float bit pattern, which is order independent and therefore deterministic.  A NaN anywhere in an image's
+// map makes its score NaN, as torch.amax does in the reference (fmaxf alone would swallow it and an overflow upstream
+// would turn into a plausible-looking AUROC): the quiet-NaN bit pattern is larger than every finite one, so the same
+// atomicMax carries it.
 #include <atomic>
 
 #include "host_util.cuh"
@@ -14,6 +17,8 @@
 
 namespace vitad {
 extern std::atomic<uint64_t> g_launches;
+
+constexpr unsigned int kNanBits = 0x7FC00000u;  // quiet NaN: above every finite (and infinite) non-negative bit pattern
 
 __device__ __forceinline__ void src_index(int o, int in_size, float scale, bool align, int& i0, int& i1, float& lam) {
     // PyTorch area_pixel_compute_source_index + guard (UpSample.h)
@@ -33,6 +38,7 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const float* __restrict__
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = blockIdx.y;
     float local_max = 0.f;
+    bool saw_nan = false;
     if (idx < per_img) {
         const int oy = (idx * 4) / S, ox0 = (idx * 4) - oy * S;
         const float scale = align ? (S > 1 ? static_cast<float>(g - 1) / (S - 1) : 0.f) : static_cast<float>(g) / S;
@@ -52,13 +58,15 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const float* __restrict__
             if (post_one_minus) v = 1.f - v;
             r[j] = v;
             local_max = fmaxf(local_max, v);
+            saw_nan |= v != v;
         }
         *reinterpret_cast<float4*>(out + (static_cast<size_t>(n) * S + oy) * S + ox0) = make_float4(r[0], r[1], r[2], r[3]);
     }
     if (img_max) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
-        if ((threadIdx.x & 31) == 0) atomicMax(img_max + n, __float_as_uint(fmaxf(local_max, 0.f)));
+        saw_nan = __any_sync(0xffffffffu, saw_nan);
+        if ((threadIdx.x & 31) == 0) atomicMax(img_max + n, saw_nan ? kNanBits : __float_as_uint(fmaxf(local_max, 0.f)));
     }
 }
 
@@ -69,6 +77,7 @@ __global__ void __launch_bounds__(256) l2_map_kernel(const float* __restrict__ r
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index within the image plane
     const int n = blockIdx.y;
     float local_max = 0.f;
+    bool saw_nan = false;
     if (idx < HW / 4) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int c = 0; c < C; ++c) {
@@ -81,10 +90,12 @@ __global__ void __launch_bounds__(256) l2_map_kernel(const float* __restrict__ r
         acc.x /= C, acc.y /= C, acc.z /= C, acc.w /= C;
         reinterpret_cast<float4*>(map + static_cast<size_t>(n) * HW)[idx] = acc;
         local_max = fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w));
+        saw_nan = acc.x != acc.x || acc.y != acc.y || acc.z != acc.z || acc.w != acc.w;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(img_max + n, __float_as_uint(local_max));
+    saw_nan = __any_sync(0xffffffffu, saw_nan);
+    if ((threadIdx.x & 31) == 0) atomicMax(img_max + n, saw_nan ? kNanBits : __float_as_uint(local_max));
 }
 
 }  // namespace vitad
