@@ -132,6 +132,9 @@ typedef struct vitad_linear_args {
      * split_out = 1 (BIAS_F16, BIAS_RELU_F16, CONVT_RELU_F16, RES16_RELU_F16): the epilogue writes [hi (N) | lo (N)]
      * rows (ldo >= 2N; per pixel for CONVT), and RES16 reads its residual in the same form (ldr >= 2N). */
     int split_c, a_taps, split_out;
+    /* QKV: 1 = `vt` receives V in its natural layout [B*windows, H, win_tokens, head_dim] (like k) instead of the
+     * transposed, padded form; pairs with vitad_attention_args.v. */
+    int v_natural;
 } vitad_linear_args;
 
 int vitad_linear_f16(const vitad_linear_args* args, void* stream);
@@ -202,6 +205,10 @@ typedef struct vitad_attention_args {
     const float* bias;
     const signed char* region;
     const int* win2tok;
+    /* Alternative to vt (exactly one of the two): V in its natural layout fp16 [batch_windows, heads, tokens, 64], the
+     * layout of k (head_dim 64, no bias / region).  It enters P.V as an MN-major tensor-core operand, so the QKV
+     * projection (vitad_linear_args.v_natural) stores V like K and no padded transposed buffer exists. */
+    const void* v;
 } vitad_attention_args;
 int vitad_attention_f16(const vitad_attention_args* args, void* stream);
 
@@ -318,7 +325,7 @@ int vitad_gmm_log_pi(const float* x, int ldx, const float* pi_w, const float* pi
 /* The same with the Gumbel noise generated inside the kernel instead of read from memory.  The reference draws it from
  * torch's global generator in every call (F.gumbel_softmax, MixtureDensityNetwork.py:62), so its scores depend on the
  * call order; here element (token t, mixture k) of global batch `batch_index` gets
- *   g = -log(-log(u)),  u = ((w >> 8) + 0.5) * 2^-24,
+ *   g = -log(-log(u)),  u = ((w >> 9) + 0.5) * 2^-23  (exact in fp32, never 0 or 1),
  *   w = word (k/32)%4 of Philox4x32-10(key = seed, counter = (t, k%32, k/128, batch_index)),
  * a pure function of its arguments: a batch scores the same on whichever rank and in whichever order it runs
  * (ValidatorMdn, rank/world_size).  vitad_gumbel_noise writes that noise as fp32 [tokens, num_gaussians]. */

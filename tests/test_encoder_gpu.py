@@ -93,6 +93,10 @@ def test_attention_matches_torch(B, T):
     ref = (attn @ v.float()).transpose(1, 2).reshape(B * T, H * 64)
     err = (out.float() - ref).abs().max().item()
     assert err <= 4e-3, err
+    # V in its natural layout (MN-major tensor-core operand): the same products in the same order -> the same bits
+    out_nat = ops.attention(q, k, None, T, v=v.contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(out_nat, out), (out_nat.float() - out.float()).abs().max().item()
 
 
 def _run_deit(sd, images, block_index=0):

@@ -85,6 +85,12 @@ def test_linear_qkv_layout():
     assert (k.float() - ref[1]).abs().max().item() <= tol
     assert (vt[..., :T].float() - ref[2].transpose(-1, -2)).abs().max().item() <= tol
     assert vt[..., T:].abs().max().item() == 0
+    # v_natural: V is stored like K (the attention kernel reads it as an MN-major operand): same values, other layout
+    q2, k2, vn = torch.zeros_like(q), torch.zeros_like(q), torch.zeros_like(q)
+    ops.linear_qkv(a, w, b, B, T, H, Tpad, q2, k2, vn, 0.125, v_natural=True)
+    torch.cuda.synchronize()
+    assert torch.equal(q2, q) and torch.equal(k2, k)
+    assert torch.equal(vn, vt[..., :T].transpose(-1, -2).contiguous())
 
 
 def test_linear_patch_embed():

@@ -64,7 +64,10 @@ constexpr int kAttnThreads = 256;
 // 32 rows are all beyond T (the second tile of 198 tokens has 70 valid rows, a 49-token window 49) skip the softmax.
 // kBias / kMask specialise the relative-position bias and shifted-window mask away for DeiT: predicated-off
 // instructions still issue, and the generic loop spent 20 instructions per score where 5 are needed.
-template <int TKP, bool kBias, bool kMask>
+// kVNat: V arrives in its natural layout [BW, H, T, hd] (hd = 64: rows of 128 bytes, the same tile K uses) and enters
+// O = P.V as an MN-major B operand (instruction-descriptor bit 16; one 16-key slice = 16 rows = 2048 bytes), so the QKV
+// projection writes V exactly like K — no transposed 2-byte scatter in its epilogue, no zero-padded vT buffer to clear.
+template <int TKP, bool kBias, bool kMask, bool kVNat = false>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                  const __grid_constant__ CUtensorMap tma_vt, const AttnParams p) {
@@ -110,9 +113,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
             mbar_arrive_expect_tx(&bars[0], S::kQBytes + S::kKBytes);
             tma_load_3d(sQ, &tma_q, &bars[0], 0, m0, bh);  // rows >= T and columns >= hd: zero-filled
             tma_load_3d(sK, &tma_k, &bars[0], 0, 0, bh);
-            mbar_arrive_expect_tx(&bars[1], S::kVtBytes);
-            for (int kb = 0; kb < S::kKeyBlocks; ++kb)
-                tma_load_2d(sVt + kb * S::kVtBlockBytes, &tma_vt, &bars[1], kb * 64, bh * p.hd);
+            if constexpr (kVNat) {
+                mbar_arrive_expect_tx(&bars[1], S::kKBytes);
+                tma_load_3d(sVt, &tma_vt, &bars[1], 0, 0, bh);  // [TKP keys][64]: keys >= T zero-filled
+            } else {
+                mbar_arrive_expect_tx(&bars[1], S::kVtBytes);
+                for (int kb = 0; kb < S::kKeyBlocks; ++kb)
+                    tma_load_2d(sVt + kb * S::kVtBlockBytes, &tma_vt, &bars[1], kb * 64, bh * p.hd);
+            }
         }
         __syncwarp();
         tmem_alloc(tmem_slot, kTmemCols);
@@ -305,7 +313,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         tc_fence_after();
         mbar_wait(&bars[1], 0);
         tc_fence_after();
-        constexpr uint32_t idesc_o = make_idesc_f16(128, 64);
+        constexpr uint32_t idesc_o = make_idesc_f16(128, 64) | (kVNat ? (1u << 16) : 0u);  // bit 16: B is MN-major
         const uint32_t v_lo = smem_desc_lo(smem_u32(sVt));
         // fully unrolled inside one elected region: every operand is (uniform base + constant), so the
         // vector->uniform moves are hoisted and pipelined instead of serialising each MMA of a rolled loop
@@ -316,7 +324,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
             for (int kk = 0; kk < TKP / 16; ++kk) {
                 if (kk < nch_u) {
                     const uint32_t a_tmem = kk < h0 ? tmem + kk * 8 : p1_base + kk * 8;  // A = P from TMEM
-                    const uint32_t b_lo = v_lo + (kk >> 2) * (S::kVtBlockBytes >> 4) + 2 * (kk & 3);
+                    const uint32_t b_lo = kVNat ? v_lo + kk * (2048 >> 4)  // 16 key rows of 128 bytes
+                                                : v_lo + (kk >> 2) * (S::kVtBlockBytes >> 4) + 2 * (kk & 3);
                     // two accumulators (even / odd key chunks): consecutive MMAs do not depend on each other
                     umma_f16_ts(tmem + kOCol + (kk & 1) * 64, a_tmem, smem_desc_join(b_lo), idesc_o, kk >= 2);
                 }
@@ -410,10 +419,12 @@ extern "C" int vitad_attention_f16(const vitad_attention_args* args, void* strea
     if (rc) return rc;
     VITAD_REQUIRE(args, VITAD_ERR_ARG, "null args");
     const vitad_attention_args& a = *args;
-    VITAD_REQUIRE(a.q && a.k && a.vt && a.out, VITAD_ERR_ARG, "null pointer");
+    VITAD_REQUIRE(a.q && a.k && (a.vt || a.v) && !(a.vt && a.v) && a.out, VITAD_ERR_ARG, "null pointer (exactly one of vt / v)");
+    VITAD_REQUIRE(!a.v || (a.head_dim == 64 && !a.bias && !a.region), VITAD_ERR_SHAPE,
+                  "natural-layout V: head_dim 64 without bias / region mask");
     VITAD_REQUIRE(a.head_dim == 64 || a.head_dim == 32, VITAD_ERR_SHAPE, "head_dim %d unsupported (32, 64)", a.head_dim);
     VITAD_REQUIRE(a.tokens > 0 && a.tokens <= 208, VITAD_ERR_SHAPE, "tokens=%d unsupported (1..208)", a.tokens);
-    VITAD_REQUIRE(a.tokens_pad >= 256 && a.tokens_pad % 8 == 0, VITAD_ERR_SHAPE,
+    VITAD_REQUIRE(a.v || (a.tokens_pad >= 256 && a.tokens_pad % 8 == 0), VITAD_ERR_SHAPE,
                   "tokens_pad=%d must be >= 256 and a multiple of 8", a.tokens_pad);
     const int nW = a.windows > 0 ? a.windows : 1;
     VITAD_REQUIRE(a.batch_windows > 0 && a.batch_windows % nW == 0 && a.heads > 0, VITAD_ERR_SHAPE, "batch/windows");
@@ -428,16 +439,21 @@ extern "C" int vitad_attention_f16(const vitad_attention_args* args, void* strea
     if (rc) return rc;
     rc = make_tmap_f16_3d(&tk, a.k, BH, a.tokens, hd, hd, static_cast<uint64_t>(a.tokens) * hd, TKP);
     if (rc) return rc;
-    rc = make_tmap_f16_2d(&tv, a.vt, static_cast<uint64_t>(BH) * hd, a.tokens_pad, a.tokens_pad, 64);
+    if (a.v)
+        rc = make_tmap_f16_3d(&tv, a.v, BH, a.tokens, hd, hd, static_cast<uint64_t>(a.tokens) * hd, TKP);
+    else
+        rc = make_tmap_f16_2d(&tv, a.vt, static_cast<uint64_t>(BH) * hd, a.tokens_pad, a.tokens_pad, 64);
     if (rc) return rc;
     VITAD_REQUIRE(!a.region || a.bias, VITAD_ERR_ARG, "a region mask is only supported together with a bias");
     auto kern = a.region ? attention_kernel<TKP, true, true>
-                         : (a.bias ? attention_kernel<TKP, true, false> : attention_kernel<TKP, false, false>);
+                         : (a.bias ? attention_kernel<TKP, true, false>
+                                   : (a.v ? attention_kernel<TKP, false, false, true> : attention_kernel<TKP, false, false>));
     static bool attr_set = false;
     if (!attr_set) {
         VITAD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<TKP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         VITAD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<TKP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         VITAD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<TKP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        VITAD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<TKP, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         attr_set = true;
     }
     const int nch = (a.tokens + 15) / 16;

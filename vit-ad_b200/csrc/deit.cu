@@ -11,6 +11,7 @@
 
 namespace vitad {
 extern std::atomic<int> g_fused_ln;  // gemm_ln.cu: residual GEMM + LayerNorm in one kernel (default on)
+extern std::atomic<int> g_use_pair;  // host_util.cu: CTA-pair GEMM kernels (default on)
 }
 
 extern "C" int vitad_layernorm(const float*, const float*, const float*, void*, float*, int, int, int, int, int, int,
@@ -105,8 +106,11 @@ static int deit_forward_impl(const vitad_deit_weights* wp, const void* images, b
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int rows = batch * T, C = w.dim;
 
+    // V in its natural layout (stored like K, consumed as an MN-major operand by the attention kernel) whenever the QKV
+    // projection runs on the CTA-pair kernel; the transposed, zero-padded form otherwise
+    const bool v_nat = vitad::g_use_pair.load() != 0 && rows > 128 && C / w.heads == 64;
     // patch embedding: gather patches -> GEMM with (+bias +pos_embed) epilogue into x[:, prefix:, :]
-    VITAD_CUDA_OK(cudaMemsetAsync(ws.vt, 0, ws.vt_bytes, s));
+    if (!v_nat) VITAD_CUDA_OK(cudaMemsetAsync(ws.vt, 0, ws.vt_bytes, s));
     if (images_u8)
         rc = vitad_patchify_u8(static_cast<const uint8_t*>(images), ws.patches, batch, 3, w.img, w.patch, s);
     else
@@ -138,11 +142,12 @@ static int deit_forward_impl(const vitad_deit_weights* wp, const void* images, b
         memset(&a, 0, sizeof(a));
         a.a = ws.h, a.w = L.qkv_w, a.bias = L.qkv_b, a.m = rows, a.n = 3 * C, a.k = C, a.lda = C, a.ldw = C;
         a.epilogue = VITAD_EPI_QKV, a.q = ws.q, a.kmat = ws.k, a.vt = ws.vt;
-        a.tokens = T, a.tokens_pad = kTokPad, a.heads = w.heads, a.q_scale = 0.125f;
+        a.tokens = T, a.tokens_pad = kTokPad, a.heads = w.heads, a.q_scale = 0.125f, a.v_natural = v_nat;
         if ((rc = vitad_linear_f16(&a, s))) return rc;
         vitad_attention_args at;
         memset(&at, 0, sizeof(at));
-        at.q = ws.q, at.k = ws.k, at.vt = ws.vt, at.out = ws.h;
+        at.q = ws.q, at.k = ws.k, at.out = ws.h;
+        if (v_nat) at.v = ws.vt; else at.vt = ws.vt;
         at.batch_windows = batch, at.heads = w.heads, at.tokens = T, at.tokens_pad = kTokPad;
         at.head_dim = C / w.heads, at.windows = 1;
         if ((rc = vitad_attention_f16(&at, s))) return rc;

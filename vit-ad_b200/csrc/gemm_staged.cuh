@@ -481,6 +481,7 @@ struct SEpiQkv {
     const int* tok2win;
     int M, L, T, Tpad, H, hd, nW;
     float scale;
+    int v_nat;  // 1: V is stored like K ([bw][h][pos][e], into `vt`) for the MN-major P.V operand of the attention kernel
     // ctx.a = bw*H*T + pos  (q/k row index before the head offset);  ctx.b = bw (-1: row out of range)
     __device__ __forceinline__ RowCtx row_ctx(int row) const {
         if (row >= M) return RowCtx{0, -1};
@@ -495,7 +496,7 @@ struct SEpiQkv {
         const int bw = b * nW + widx;
         return RowCtx{bw * H * T + pos, bw};
     }
-    __device__ __forceinline__ bool direct(int col0) const { return col0 >= 2 * H * hd; }
+    __device__ __forceinline__ bool direct(int col0) const { return !v_nat && col0 >= 2 * H * hd; }
     __device__ __forceinline__ void direct_unit(int, RowCtx ctx, int col0, const uint32_t (&acc)[32]) const {
         const int C = H * hd;
         if (ctx.b < 0 || col0 >= 3 * C) return;
@@ -516,26 +517,26 @@ struct SEpiQkv {
     __device__ __forceinline__ ColC col_const(int col) const {
         ColC c;
         const int C = H * hd;
-        if (col >= 2 * C) {
+        if (col >= 2 * C && (!v_nat || col >= 3 * C)) {
             c.bias = make_float4(0.f, 0.f, 0.f, 0.f);
-            c.which = 2;
+            c.which = 3;  // not stored from the row-contiguous layout
             c.off = 0;
             return c;
         }
         c.bias = __ldg(reinterpret_cast<const float4*>(bias + col));
-        c.which = col >= C ? 1 : 0;
+        c.which = col >= 2 * C ? 2 : (col >= C ? 1 : 0);
         const int cc = col - c.which * C;
         const int h = cc / hd;
         c.off = h * T * hd + (cc - h * hd);
         return c;
     }
     __device__ __forceinline__ void store(int, RowCtx ctx, int, float4 a, Pre, ColC c) const {
-        if (ctx.b < 0 || c.which == 2) return;
+        if (ctx.b < 0 || c.which == 3) return;
         const float s = c.which == 0 ? scale : 1.0f;
         uint2 u;
         u.x = pack_h2((a.x + c.bias.x) * s, (a.y + c.bias.y) * s);
         u.y = pack_h2((a.z + c.bias.z) * s, (a.w + c.bias.w) * s);
-        __half* base = c.which == 0 ? q : k;
+        __half* base = c.which == 0 ? q : (c.which == 1 ? k : vt);
         // (ctx.a - pos) * hd + h*T*hd + pos*hd + e  ==  (bw*H*T)*hd + ... : ctx.a already holds bw*H*T + pos
         *reinterpret_cast<uint2*>(base + static_cast<size_t>(ctx.a) * hd + c.off) = u;
     }

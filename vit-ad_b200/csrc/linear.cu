@@ -120,7 +120,7 @@ static int dispatch_staged(const vitad_linear_args& a, cudaStream_t stream) {
             const int nw = a.windows > 0 ? a.windows : 1;
             const int wt = a.win_tokens > 0 ? a.win_tokens : a.tokens;
             SEpiQkv e{a.bias, static_cast<__half*>(a.q), static_cast<__half*>(a.kmat), static_cast<__half*>(a.vt),
-                      a.tok2win, a.m, a.tokens, wt, a.tokens_pad, a.heads, hd, nw, a.q_scale};
+                      a.tok2win, a.m, a.tokens, wt, a.tokens_pad, a.heads, hd, nw, a.q_scale, a.v_natural};
             return launch_gemm_staged<BLOCK_N>(a, e, stream);
         }
         case VITAD_EPI_PATCH_EMBED:
@@ -328,7 +328,9 @@ extern "C" int vitad_linear_f16(const vitad_linear_args* args, void* stream) {
                               a.n == 3 * a.heads * (a.head_dim > 0 ? a.head_dim : 64) && a.tokens > 0 &&
                               a.m % a.tokens == 0,
                           VITAD_ERR_SHAPE, "QKV epilogue needs N = 3*H*hd (hd 32 or 64) and M = B*tokens");
-            VITAD_REQUIRE(a.tokens_pad >= (a.win_tokens > 0 ? a.win_tokens : a.tokens) &&
+            VITAD_REQUIRE(!a.v_natural || (g_use_pair.load() && a.m > kBlockM), VITAD_ERR_SHAPE,
+                          "v_natural needs the CTA-pair kernel (M > 128)");
+            VITAD_REQUIRE((a.v_natural || a.tokens_pad >= (a.win_tokens > 0 ? a.win_tokens : a.tokens)) &&
                               (a.windows <= 1 || (a.tok2win && a.windows * a.win_tokens == a.tokens)),
                           VITAD_ERR_SHAPE, "QKV epilogue window layout (windows*win_tokens == tokens, map given)");
             break;

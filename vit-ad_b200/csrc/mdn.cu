@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(256) gmm_operand_kernel(const float* __restric
 // The reference draws fresh Gumbel noise in every log_likelihood call (gumbel_softmax, MixtureDensityNetwork.py:62) from
 // torch's global generator, so a score depends on how many draws preceded it.  Here the noise of element (t, k) of
 // global batch `batch_index` is a pure function of (seed, batch_index, t, k): Philox4x32-10 with key = seed and counter =
-// (t, k % 32, (k / 32) / 4, batch_index), word (k / 32) % 4, mapped to g = -log(-log(u)), u = (word >> 8 + 0.5) * 2^-24 in
-// (0, 1).  A sharded run (rank r scores batches r, r + W, ...) therefore reproduces the unsharded scores bit for bit.
+// (t, k % 32, (k / 32) / 4, batch_index), word (k / 32) % 4, mapped to g = -log(-log(u)), u = ((word >> 9) + 0.5) * 2^-23 in
+// (0, 1) — 23 bits, so that the + 0.5 is exact in fp32 and u never rounds to 1 (24 bits did, once in 2^24 draws: g = inf).  A sharded run (rank r scores batches r, r + W, ...) therefore reproduces the unsharded scores bit for bit.
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 key) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -205,7 +205,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 key) {
     return c;
 }
 __device__ __forceinline__ float gumbel_from_word(uint32_t w) {
-    const float u = (static_cast<float>(w >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24: exact, never 0 or 1
+    const float u = (static_cast<float>(w >> 9) + 0.5f) * 1.1920928955078125e-07f;  // 2^-23: exact, in [2^-24, 1 - 2^-24]
     return -logf(-logf(u));
 }
 struct GumbelKey {

@@ -97,6 +97,7 @@ class LinearArgs(C.Structure):
         ("split_c", C.c_int),
         ("a_taps", C.c_int),
         ("split_out", C.c_int),
+        ("v_natural", C.c_int),
     ]
 
 
@@ -143,7 +144,7 @@ lib.vitad_prefix_tokens.restype = _i
 class AttentionArgs(C.Structure):
     _fields_ = [("q", _vp), ("k", _vp), ("vt", _vp), ("out", _vp), ("batch_windows", _i), ("heads", _i),
                 ("tokens", _i), ("tokens_pad", _i), ("head_dim", _i), ("windows", _i), ("bias", _vp),
-                ("region", _vp), ("win2tok", _vp)]
+                ("region", _vp), ("win2tok", _vp), ("v", _vp)]
 
 
 lib.vitad_attention_f16.argtypes = [C.POINTER(AttentionArgs), _vp]

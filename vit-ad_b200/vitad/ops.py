@@ -130,7 +130,7 @@ def prepare_images(images: torch.Tensor, size: int) -> torch.Tensor:
 def linear_qkv(
     a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, batch: int, tokens: int, heads: int, tokens_pad: int,
     q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, q_scale: float, block_n: int = 0, head_dim: int = 0,
-    windows: int = 0, win_tokens: int = 0, tok2win: torch.Tensor | None = None,
+    windows: int = 0, win_tokens: int = 0, tok2win: torch.Tensor | None = None, v_natural: bool = False,
 ) -> None:
     """Fused qkv projection writing q/k as [BW,H,T,hd] and v transposed as [BW,H,hd,Tpad] (fp16); with
     `windows`/`tok2win` the rows are scattered into (shifted) attention windows."""
@@ -145,6 +145,7 @@ def linear_qkv(
     args.q, args.kmat, args.vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
     args.tokens, args.tokens_pad, args.heads, args.q_scale = tokens, tokens_pad, heads, q_scale
     args.head_dim, args.windows, args.win_tokens, args.tok2win = head_dim, windows, win_tokens, _ptr(tok2win)
+    args.v_natural = int(v_natural)  # vt then receives V as [BW,H,T,hd] (the layout of k)
     check(lib.vitad_linear_f16(C.byref(args), _stream()))
 
 
@@ -187,15 +188,17 @@ def patchify(images, patch):
     return out
 
 
-def attention(q, k, vt, tokens, windows=1, bias=None, region=None, win2tok=None):
+def attention(q, k, vt, tokens, windows=1, bias=None, region=None, win2tok=None, v=None):
     """q,k fp16 [BW,H,T,hd] (q pre-scaled); vt fp16 [BW,H,hd,Tpad] zero-padded -> fp16 [BW*T, H*hd] in original
-    token order.  Swin: bias fp32 [H,T_key,T_query] (key-major), region int8 [windows,T], win2tok int32 [windows*T]."""
-    _need_cuda(q, k, vt, bias, region, win2tok)
+    token order.  Swin: bias fp32 [H,T_key,T_query] (key-major), region int8 [windows,T], win2tok int32 [windows*T].
+    Instead of vt: v fp16 [BW,H,T,64] in its natural layout (the MN-major operand path of the kernel)."""
+    _need_cuda(q, k, vt, bias, region, win2tok, v)
     bw, h, t, hd = q.shape
     out = torch.empty((bw * t, h * hd), device=q.device, dtype=torch.float16)
     a = _lib.AttentionArgs()
-    a.q, a.k, a.vt, a.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
-    a.batch_windows, a.heads, a.tokens, a.tokens_pad, a.head_dim, a.windows = bw, h, tokens, vt.shape[-1], hd, windows
+    a.q, a.k, a.vt, a.out, a.v = q.data_ptr(), k.data_ptr(), _ptr(vt), out.data_ptr(), _ptr(v)
+    a.batch_windows, a.heads, a.tokens, a.head_dim, a.windows = bw, h, tokens, hd, windows
+    a.tokens_pad = vt.shape[-1] if vt is not None else 0
     a.bias, a.region, a.win2tok = _ptr(bias), _ptr(region), _ptr(win2tok)
     check(lib.vitad_attention_f16(C.byref(a), _stream()))
     return out
