@@ -92,7 +92,7 @@ def test_seeded_gumbel_noise_is_the_noise_the_kernel_adds(K):
     big = gumbel_noise(99, 3, (32, 196, K)).double().flatten()
     assert torch.isfinite(big).all()
     if K == 100:  # 2^26 draws: a 24-bit uniform rounded to 1.0 once in 2^24 draws (g = +inf, found by the NaN-propagating score tail)
-        many = torch.cat([gumbel_noise(7, bi, (64, 196, 130)).flatten() for bi in range(41)])
+        many = torch.cat([gumbel_noise(7, bi, (64, 196, 130)).flatten() for bi in range(42)])
         assert many.numel() > 2 ** 26 and torch.isfinite(many).all() and many.max().item() < 20.0 and many.min().item() > -4.0
     assert abs(big.mean().item() - 0.5772157) < 5e-3 and abs(big.var().item() - np.pi ** 2 / 6) < 2e-2
     assert abs(torch.corrcoef(torch.stack([big[:-1], big[1:]]))[0, 1].item()) < 5e-3
