@@ -163,6 +163,8 @@ int vitad_linear_resid_ln_f16(const vitad_linear_ln_args* args, void* stream);
  * to fill the 4-CTA clusters (default 1; 0 = always the separate vitad_linear_f16(RESIDUAL_F32) +
  * vitad_layernorm768_tree launches — the results are bit-identical either way). */
 void vitad_set_fused_ln(int enable);
+/* Encoder forward: V in its natural layout, consumed as an MN-major operand (default 1; 0 = transposed padded vT). */
+void vitad_set_v_natural(int enable);
 /* LayerNorm over C = 768 (x fp32 [rows, ldx] -> out fp16 [rows, ldh]) with exactly the arithmetic of the LayerNorm half of
  * vitad_linear_resid_ln_f16 (csrc/ln_tree.cuh): bit-identical rows, so the encoder can pick the fused kernel or the
  * separate launches by row count without changing a result. */

@@ -12,7 +12,10 @@
 namespace vitad {
 extern std::atomic<int> g_fused_ln;  // gemm_ln.cu: residual GEMM + LayerNorm in one kernel (default on)
 extern std::atomic<int> g_use_pair;  // host_util.cu: CTA-pair GEMM kernels (default on)
+std::atomic<int> g_v_natural{1};     // V stored like K for the attention kernel's MN-major operand path (default on)
 }
+
+extern "C" void vitad_set_v_natural(int enable) { vitad::g_v_natural.store(enable ? 1 : 0); }
 
 extern "C" int vitad_layernorm(const float*, const float*, const float*, void*, float*, int, int, int, int, int, int,
                                int, int, float, int, void*);
@@ -108,7 +111,7 @@ static int deit_forward_impl(const vitad_deit_weights* wp, const void* images, b
 
     // V in its natural layout (stored like K, consumed as an MN-major operand by the attention kernel) whenever the QKV
     // projection runs on the CTA-pair kernel; the transposed, zero-padded form otherwise
-    const bool v_nat = vitad::g_use_pair.load() != 0 && rows > 128 && C / w.heads == 64;
+    const bool v_nat = vitad::g_v_natural.load() != 0 && vitad::g_use_pair.load() != 0 && rows > 128 && C / w.heads == 64;
     // patch embedding: gather patches -> GEMM with (+bias +pos_embed) epilogue into x[:, prefix:, :]
     if (!v_nat) VITAD_CUDA_OK(cudaMemsetAsync(ws.vt, 0, ws.vt_bytes, s));
     if (images_u8)

@@ -118,6 +118,10 @@ lib.vitad_set_fused_ln.restype = None
 lib.vitad_layernorm768_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
                                         C.c_void_p]
 lib.vitad_layernorm768_tree.restype = C.c_int
+lib.vitad_set_v_natural.argtypes = [C.c_int]
+lib.vitad_set_v_natural.restype = None
+if os.environ.get("VITAD_VNAT") == "0":  # diagnostics: transposed, zero-padded V for the attention kernel
+    lib.vitad_set_v_natural(0)
 if os.environ.get("VITAD_FUSED_LN") == "0":  # diagnostics: separate residual GEMM + LayerNorm launches
     lib.vitad_set_fused_ln(0)
 
