@@ -140,14 +140,8 @@ static int deit_forward_impl(const vitad_deit_weights* wp, const void* images, b
     vitad_linear_ln_args f;
     for (int i = 0; i <= last; ++i) {
         const vitad_deit_layer& L = w.layers[i];
-        // block 0's norm1 has no producer GEMM in either form: the general kernel (11 us vs 16 us for the tree form at
-        // batch 32), the same at every batch size
-        if (i == 0) {
-            if ((rc = vitad_layernorm(ws.x, L.ln1_w, L.ln1_b, ws.h, nullptr, rows, C, C, C, 0, rows, rows, 0, 1e-6f, 0, s)))
-                return rc;
-        } else if (!fused) {
+        if (!fused || i == 0)
             if ((rc = block_norm(L.ln1_w, L.ln1_b))) return rc;
-        }
         memset(&a, 0, sizeof(a));
         a.a = ws.h, a.w = L.qkv_w, a.bias = L.qkv_b, a.m = rows, a.n = 3 * C, a.k = C, a.lda = C, a.ldw = C;
         a.epilogue = VITAD_EPI_QKV, a.q = ws.q, a.kmat = ws.k, a.vt = ws.vt;
