@@ -583,12 +583,16 @@ def run_sweep_bench(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
         "config": {"workload": SWEEP_WORKLOAD, "categories": len(host), "images": n_images, "heads_per_image": heads,
                    "images_scored_per_step": scored, "batch": args.batch, "gaussians": K,
-                   "timed_region": "scoring of every batch + NCCL exchange of scores/maps/labels to the ranks that evaluate them + image/pixel AUROC, PR-AUC, PRO on the device + all_reduce of the metric values",
+                   "timed_region": "scoring of every batch + delivery of scores/maps/labels to the ranks that evaluate them + image/pixel AUROC, PR-AUC, PRO on the device + all_reduce of the metric values",
                    "l2": "1725 distinct images (1.04 GB fp32) per step, far beyond the 126 MB L2",
-                   "parallelism": (f"batches dealt round-robin over {world} ranks across the whole sweep, weight replica per rank; one routed "
-                                   f"all_to_all after the scoring sends validation p = (category, head) to rank p % {world}, which computes its "
-                                   "metrics; metric values all-reduced" if world > 1 else
-                                   "one GPU: metrics of category c on a side stream under the scoring of category c+1")},
+                   "transport": last["transport"],
+                   "parallelism": ("one GPU: metrics of category c on a side stream under the scoring of category c+1" if world == 1 else
+                                   f"batches dealt round-robin over {world} ranks across the whole sweep, weight replica per rank; validation "
+                                   f"p = (category, head) is evaluated by rank p % {world}: " +
+                                   ("its rows are written into that rank's symmetric-memory buffer over NVLink as they are scored (copy kernels "
+                                    "+ stream-ordered signals, no collective), metrics on a side stream under the scoring"
+                                    if last["transport"] == "peer" else "one routed all_to_all after the scoring") +
+                                   "; metric values all-reduced")},
         "clocks": clocks.summary(),
         "e2e": {"value": scored * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": heads * (img_bytes + mask_bytes), "d2h_bytes_per_step": 8 * n_metric_floats,

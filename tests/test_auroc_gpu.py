@@ -105,3 +105,72 @@ def test_sweep_metrics_equal_the_per_validator_sklearn_path():
             for k, v in ref.items():
                 if isinstance(v, float) and k != "fp_thres":
                     assert abs(got[k] - v) < 1e-6, (name, tag, k, got[k], v)
+
+
+_PEER_SWEEP_SCRIPT = r"""
+import os, sys, json
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+torch.cuda.set_device(0)
+dev = torch.device("cuda", 0)
+dist.init_process_group("nccl", init_method="file://" + sys.argv[2], rank=0, world_size=1, device_id=dev)
+from vitad.parallel import PeerMailbox
+from vitad.sweep import build_sweep_models, run_sweep
+from vitad.synthetic import make_category
+
+# the mailbox alone: rows written in two pieces, one signal, the wait on a side stream
+box = PeerMailbox(40, (1, 8, 8), dev)
+g = torch.Generator().manual_seed(3)
+res = {"image_scores": torch.rand(24, generator=g).to(dev), "pixel_scores": torch.rand(24, 1, 8, 8, generator=g).to(dev),
+       "image_labels": torch.randint(0, 2, (24,), generator=g).to(dev), "pixel_labels": torch.randint(0, 2, (24, 1, 8, 8), generator=g).to(torch.uint8).to(dev)}
+box.put(0, 5, res, 0, 10)
+box.put(0, 15, res, 10, 24)
+box.signal(0, 7)
+side = torch.cuda.Stream()
+with torch.cuda.stream(side):
+    box.wait_all(7)
+    got = {k: v.clone() for k, v in box.rows(5, 24).items()}
+side.synchronize()
+mailbox_ok = all(torch.equal(got[k], res[k]) for k in res)
+try:
+    box.put(0, 30, res, 0, 24)
+    bounds_ok = False
+except ValueError:
+    bounds_ok = True
+
+# the sweep through each delivery path of the multi-rank code (one rank) against the one-GPU path
+v_gmm, v_nf = build_sweep_models(0, 1, dev)
+data = {n: make_category(n, k, seed=910 + i) for i, (n, k) in enumerate((("alpha", 37), ("beta", 70), ("gamma", 33)))}
+data = {k: (t[0].to(dev), t[1], (t[2] != 0).to(torch.uint8).to(dev)) for k, t in data.items()}
+one = run_sweep(v_gmm, v_nf, data, batch_size=32)
+peer = run_sweep(v_gmm, v_nf, data, batch_size=32, transport="peer")
+peer2 = run_sweep(v_gmm, v_nf, data, batch_size=32, transport="peer")  # buffers and signals are reused
+exch = run_sweep(v_gmm, v_nf, data, batch_size=32, transport="exchange")
+print(json.dumps({"mailbox_ok": mailbox_ok, "bounds_ok": bounds_ok, "transports": [one["transport"], peer["transport"], exch["transport"]],
+                  "peer_equal": peer["metrics"] == one["metrics"], "peer_again_equal": peer2["metrics"] == one["metrics"],
+                  "exchange_equal": exch["metrics"] == one["metrics"], "n": len(one["metrics"])}))
+dist.destroy_process_group()
+"""
+
+
+def test_sweep_peer_memory_delivery_reproduces_the_one_gpu_metrics(tmp_path):
+    """config 5's multi-rank code path on the one GPU of the test box (a single-rank NCCL group in a child process): result
+    rows delivered through symmetric memory (parallel.PeerMailbox: copy kernels + stream-ordered signals) and through the
+    routed NCCL exchange give exactly the metrics of the one-GPU path; the mailbox returns the rows it was sent."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "peer_sweep.py"
+    script.write_text(_PEER_SWEEP_SCRIPT)
+    env = dict(os.environ, VITAD_SWEEP_TRANSPORT="")
+    env.pop("VITAD_SWEEP_TRANSPORT")
+    r = subprocess.run([sys.executable, str(script), os.path.join(root, "vit-ad_b200"), str(tmp_path / "store")],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["mailbox_ok"] and out["bounds_ok"], out
+    assert out["transports"] == ["one GPU", "peer", "exchange"], out
+    assert out["peer_equal"] and out["peer_again_equal"] and out["exchange_equal"] and out["n"] == 6, out

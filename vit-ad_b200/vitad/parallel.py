@@ -277,3 +277,68 @@ def exchange_to_owners(entries: list, pair_owner: list, device: torch.device | N
         res["batch_sizes"] = sizes.copy()
         merged[p] = res
     return merged
+
+
+class PeerMailbox:
+    """Receive buffers for validation results in symmetric memory (torch.distributed._symmetric_memory, CUDA backend:
+    cuMem allocations of every rank of the node mapped into each other's address space over NVLink).
+
+    A rank that has scored rows of a validation writes them straight into the buffer of the rank that evaluates it — plain
+    copy kernels on its own stream, 700 GB/s per direction through NVSwitch — and then raises a stream-ordered signal for
+    that validation; the owner waits for one signal per rank on a side stream.  There is no collective and no rendezvous
+    with the receiver: a collective kernel waits on the device for its peers and, while it sits on an SM, the persistent
+    one-CTA-per-SM kernels of the scoring path cannot be resident (exchange_to_owners pays that once, after the scoring;
+    here the rows arrive while both sides keep scoring, so the owner's metrics can run under the scoring again).
+
+    Every rank allocates the same capacity (rows of the busiest owner).  put / signal / wait_all are stream-ordered and do
+    not block the host; a signal raised twice without a wait in between, or a wait without its signals, ends in the
+    device-side time-out of the signal kernels (60 s) instead of a hang."""
+
+    SIGNAL_TIMEOUT_MS = 60000
+
+    def __init__(self, rows: int, map_shape: tuple, device: torch.device, pixel_label_dtype=torch.uint8, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.rows_cap, self.map_shape, self.device = int(rows), tuple(int(v) for v in map_shape), device
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        group = dist.group.WORLD if group is None else group
+        per_map = int(np.prod(self.map_shape))
+        self._spec = {"image_scores": ((), torch.float32), "pixel_scores": (self.map_shape, torch.float32),
+                      "image_labels": ((), torch.int64), "pixel_labels": (self.map_shape, pixel_label_dtype)}
+        self._local, self._hdl, self._peer = {}, {}, {}
+        for key, (trail, dtype) in self._spec.items():
+            n = self.rows_cap * (per_map if trail else 1)
+            t = symm.empty(max(n, 1), dtype=dtype, device=device)
+            self._local[key] = t
+            self._hdl[key] = symm.rendezvous(t, group)  # collective, once
+            self._peer[key] = [self._hdl[key].get_buffer(r, (self.rows_cap,) + trail, dtype, 0) if n else None
+                               for r in range(self.world)]
+        self._sig = self._hdl["image_scores"]  # one signal pad serves all four payloads
+        self.channels = self._sig.signal_pad_size // 4 // self.world
+
+    def put(self, owner: int, row0: int, result: dict, lo: int, hi: int) -> None:
+        """rows [lo, hi) of this rank's result → rows [row0, row0 + hi - lo) of `owner`'s buffers (current stream)."""
+        if hi <= lo:
+            return
+        if row0 < 0 or row0 + (hi - lo) > self.rows_cap:
+            raise ValueError(f"PeerMailbox.put: rows [{row0}, {row0 + hi - lo}) outside the capacity {self.rows_cap}")
+        for key, (trail, dtype) in self._spec.items():
+            src = result[key][lo:hi]
+            self._peer[key][owner].narrow(0, row0, hi - lo).copy_(src.reshape((hi - lo,) + trail), non_blocking=True)
+
+    def signal(self, owner: int, channel: int) -> None:
+        """After everything this stream has written so far: tell `owner` that this rank is done with `channel`."""
+        self._sig.put_signal(owner, channel, self.SIGNAL_TIMEOUT_MS)
+
+    def wait_all(self, channel: int) -> None:
+        """Current stream waits until every rank (this one included) has signalled `channel`; the signals are consumed."""
+        for src in range(self.world):
+            self._sig.wait_signal(src, channel, self.SIGNAL_TIMEOUT_MS)
+
+    def rows(self, row0: int, n: int) -> dict:
+        """This rank's received rows [row0, row0 + n) as a result dictionary (views of the buffers)."""
+        out = {}
+        for key, (trail, _dtype) in self._spec.items():
+            out[key] = self._local[key][: self.rows_cap * (int(np.prod(trail)) if trail else 1)].view(
+                (self.rows_cap,) + trail).narrow(0, row0, n)
+        return out

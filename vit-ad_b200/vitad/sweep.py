@@ -24,7 +24,7 @@ METRIC_KEYS = ("image_auroc_score", "image_prauc_score", "pixel_auroc_score", "p
 
 
 def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size: int = 32, pixel_metrics: bool = True,
-              fp_thres: float = 0.3, gmm_seed: int = 1234) -> dict:
+              fp_thres: float = 0.3, gmm_seed: int = 1234, transport: str | None = None) -> dict:
     """`data`: {category: (images [n,3,S,S], image_labels [n], pixel_labels [n,1,S,S])}, host (pinned) or device tensors.
     → {"metrics": {category/head: {...}} (complete on every rank), "images": n}.  Returns after the last metric value has
     reached the host.
@@ -33,7 +33,20 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
     host-side reads wait only for their own inputs).  Several GPUs: every rank scores its batches of the whole sweep (the
     round-robin continues across categories: 61 batches over W ranks), then ONE routed exchange sends each validation's
     rows to the rank that evaluates it (parallel.exchange_to_owners; validation p = (category, head) → rank p % W, so the
-    sorts are spread over the ranks too), then the metric values are summed into place on every rank."""
+    sorts are spread over the ranks too), then the metric values are summed into place on every rank.
+    `transport` (default: env VITAD_SWEEP_TRANSPORT, else "peer"): "peer" delivers the rows through symmetric memory as they
+    are scored (parallel.PeerMailbox: NVLink writes + signals, no collective; the owners' metrics run under the scoring),
+    "exchange" is the single routed NCCL exchange after the scoring; "peer" falls back to it where symmetric memory cannot
+    be set up (every rank takes the same decision).  A transport named explicitly is also honoured by a single-rank
+    process group: the multi-rank code path with one rank, which is how the one-GPU test box checks it against the path
+    above."""
+    import os
+
+    explicit = transport or os.environ.get("VITAD_SWEEP_TRANSPORT")
+    if explicit not in (None, "peer", "exchange"):
+        raise ValueError(f"run_sweep: transport {explicit!r} (peer, exchange)")
+    transport = explicit or "peer"
+    one_gpu = world == 1 and not (explicit and dist.is_available() and dist.is_initialized())
     dev = v_gmm.device
     main = torch.cuda.current_stream(dev)
     heads = ("gmm", "nf")
@@ -89,7 +102,7 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
         return rg, rn, layout, len(bl)
 
     metrics, n_images, dealt = {}, 0, 0
-    if world == 1:
+    if one_gpu:
         side = getattr(v_gmm, "_metrics_stream", None)
         if side is None:
             side = v_gmm._metrics_stream = torch.cuda.Stream(dev)
@@ -118,33 +131,116 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
         torch.cuda.synchronize(dev)
         keep_alive.clear()
     else:
-        entries = []
-        for ci, name in enumerate(names):
-            rg, rn, layout, nb = score(ci, name, dealt)
-            dealt += nb
-            n_images += int(data[name][0].shape[0])
-            entries += [{"result": rg, "layout": layout}, {"result": rn, "layout": layout}]
-        pair_owner = [p % world for p in range(len(entries))]
-        mine = exchange_to_owners(entries, pair_owner, dev)
-        # metric values: one [pairs, keys] table, every rank fills the rows it owns, a sum puts them everywhere
-        table = torch.full((len(entries), len(METRIC_KEYS)), float("nan"), dtype=torch.float64)
-        for p, r in mine.items():
+        n_pairs = 2 * len(names)
+        table = torch.full((n_pairs, len(METRIC_KEYS)), float("nan"), dtype=torch.float64)
+
+        def fill(p, r):
             m = evaluate(r, names[p // 2])
             for j, key in enumerate(METRIC_KEYS):
                 hit = [v for k, v in m.items() if k.startswith(key)]
                 if hit:
                     table[p, j] = hit[0]
+
+        pair_owner = [p % world for p in range(n_pairs)]  # validation p = (category, head) → rank p mod W
+        box = _mailbox(v_gmm, data, names, pair_owner, world, dev) if transport != "exchange" else None
+        if box is not None:
+            # Peer-memory delivery: rows go straight into the owner's buffer as soon as they are scored (NVLink writes, no
+            # collective), the owner evaluates a validation `lag` categories later on a side stream — by then its rows
+            # have arrived and the main stream has the categories in between queued — so only the last ones are exposed.
+            side = getattr(v_gmm, "_metrics_stream", None)
+            if side is None:
+                side = v_gmm._metrics_stream = torch.cuda.Stream(dev)
+            sizes = [int(data[n][0].shape[0]) for n in names]
+            base, used = [0] * n_pairs, [0] * world
+            for p in range(n_pairs):
+                base[p] = used[pair_owner[p]]
+                used[pair_owner[p]] += sizes[p // 2]
+            lag = max(1, min(3, world // 2))
+            keep_alive = []
+
+            def deliver(p, res, layout):
+                starts = np.concatenate(([0], np.cumsum(layout["batch_sizes"])))
+                lo = 0
+                for b, o in enumerate(layout["owners"]):
+                    if o == rank:
+                        n = int(layout["batch_sizes"][b])
+                        box.put(pair_owner[p], base[p] + int(starts[b]), res, lo, lo + n)
+                        lo += n
+                box.signal(pair_owner[p], p)  # every rank signals every validation, rows or not
+
+            def finish_category(ci):
+                for p in (2 * ci, 2 * ci + 1):
+                    if pair_owner[p] == rank:
+                        with torch.cuda.stream(side):
+                            box.wait_all(p)
+                            fill(p, box.rows(base[p], sizes[ci]))
+
+            for ci, name in enumerate(names):
+                rg, rn, layout, nb = score(ci, name, dealt)
+                dealt += nb
+                n_images += sizes[ci]
+                deliver(2 * ci, rg, layout)
+                deliver(2 * ci + 1, rn, layout)
+                keep_alive.append((rg, rn))
+                if ci >= lag:
+                    finish_category(ci - lag)
+            for ci in range(max(0, len(names) - lag), len(names)):
+                finish_category(ci)
+            main.wait_stream(side)
+        else:
+            entries = []
+            for ci, name in enumerate(names):
+                rg, rn, layout, nb = score(ci, name, dealt)
+                dealt += nb
+                n_images += int(data[name][0].shape[0])
+                entries += [{"result": rg, "layout": layout}, {"result": rn, "layout": layout}]
+            mine = exchange_to_owners(entries, pair_owner, dev)
+            for p, r in mine.items():
+                fill(p, r)
+        # metric values: one [pairs, keys] table, every rank fills the rows it owns, a sum puts them everywhere (and no
+        # rank starts the next sweep — whose rows land in the same buffers — before every owner is done with this one)
         present = (~torch.isnan(table)).to(torch.float64)
         packed = torch.stack((torch.nan_to_num(table, nan=0.0), present)).to(dev)
         dist.all_reduce(packed, op=dist.ReduceOp.SUM)
         packed = packed.cpu()
         torch.cuda.synchronize(dev)
         pro_key = f"pro_score_{fp_thres}fp"
-        for p in range(len(entries)):
+        for p in range(n_pairs):
             name, tag = names[p // 2], heads[p % 2]
             metrics[f"{name}/{tag}"] = {(pro_key if key == "pro_score" else key): float(packed[0, p, j])
                                         for j, key in enumerate(METRIC_KEYS) if packed[1, p, j] > 0}
-    return {"metrics": metrics, "images": n_images, "heads_per_image": 2}
+    used = "one GPU" if one_gpu else ("peer" if box is not None else "exchange")
+    return {"metrics": metrics, "images": n_images, "heads_per_image": 2, "transport": used}
+
+
+def _mailbox(holder, data: dict, names: list, pair_owner: list, world: int, dev):
+    """The sweep's PeerMailbox, sized for the busiest owner and kept on the validator between sweeps; None (on every rank)
+    when symmetric memory is not available."""
+    from .parallel import PeerMailbox
+
+    rows = [0] * world
+    for p, o in enumerate(pair_owner):
+        rows[o] += int(data[names[p // 2]][0].shape[0])
+    images = data[names[0]][0]
+    key = (max(rows), int(images.shape[-2]), int(images.shape[-1]), world)
+    cached = getattr(holder, "_sweep_mailbox", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    ok = torch.ones(1, device=dev)
+    box = None
+    try:
+        box = PeerMailbox(key[0], (1, key[1], key[2]), dev)
+        if box.channels < len(pair_owner):
+            raise RuntimeError(f"signal pad holds {box.channels} channels, the sweep needs {len(pair_owner)}")
+    except Exception as exc:  # noqa: BLE001 — any set-up failure means: use the NCCL exchange, on every rank
+        print(f"vitad.sweep: symmetric memory unavailable ({type(exc).__name__}: {exc}); using the NCCL exchange", flush=True)
+        ok.zero_()
+        box = None
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok.item()) < 1.0:
+        box = None
+    holder._sweep_mailbox = (key, box)
+    return box
 
 
 def build_sweep_models(rank: int, world: int, device, gaussians: int = 100):
