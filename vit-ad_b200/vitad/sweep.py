@@ -155,7 +155,9 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
             for p in range(n_pairs):
                 base[p] = used[pair_owner[p]]
                 used[pair_owner[p]] += sizes[p // 2]
-            lag = max(1, min(3, world // 2))
+            # how far the metrics trail the scoring: the host blocks on a validation's metric values, so it needs queued
+            # kernels ahead of them; 2 * lag validations (at most one per rank) are left for after the last category
+            lag = int(os.environ.get("VITAD_SWEEP_LAG", 0)) or max(1, world // 2)
             keep_alive = []
 
             def deliver(p, res, layout):
