@@ -279,3 +279,31 @@ def test_esvit_checkpoint_position_encoding_interpolation():
     sd = enc.esvit.state_dict()
     assert sd["layers.0.blocks.0.attn.relative_position_bias_table"].shape == (729, 3)
     assert sd["layers.0.blocks.0.attn.relative_position_index"].dtype == torch.int64
+
+
+def test_delivery_plan_tiles_the_owner_buffer_in_global_batch_order():
+    """vitad.sweep.delivery_plan (peer-memory transport of config 5): the pieces all ranks write cover the validation's rows
+    exactly once, in global batch order, whatever the dealing offset, ragged last batches and ranks without a batch."""
+    from vitad.sweep import delivery_plan
+    from vitad.validators import _BatchSharding
+
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        for trial in range(20):
+            nb = int(rng.integers(1, 12))
+            sizes = [32] * (nb - 1) + [int(rng.integers(1, 33))]
+            offset = int(rng.integers(0, world))
+            owners = [_BatchSharding(0, world, offset).owner(b) for b in range(nb)]
+            base = int(rng.integers(0, 100))
+            total = sum(sizes)
+            buf = np.full(base + total + 5, -1, dtype=np.int64)
+            starts = np.concatenate(([0], np.cumsum(sizes)))
+            for rank in range(world):
+                local = np.concatenate([np.arange(starts[b], starts[b + 1]) for b in range(nb) if owners[b] == rank] or [np.zeros(0, np.int64)])
+                covered = 0
+                for row0, lo, hi in delivery_plan(sizes, owners, rank, base):
+                    assert (buf[row0:row0 + hi - lo] == -1).all()  # nobody else wrote here
+                    buf[row0:row0 + hi - lo] = local[lo:hi]
+                    covered += hi - lo
+                assert covered == local.size
+            assert (buf[base:base + total] == np.arange(total)).all() and (buf[:base] == -1).all() and (buf[base + total:] == -1).all()

@@ -161,13 +161,8 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
             keep_alive = []
 
             def deliver(p, res, layout):
-                starts = np.concatenate(([0], np.cumsum(layout["batch_sizes"])))
-                lo = 0
-                for b, o in enumerate(layout["owners"]):
-                    if o == rank:
-                        n = int(layout["batch_sizes"][b])
-                        box.put(pair_owner[p], base[p] + int(starts[b]), res, lo, lo + n)
-                        lo += n
+                for row0, lo, hi in delivery_plan(layout["batch_sizes"], layout["owners"], rank, base[p]):
+                    box.put(pair_owner[p], row0, res, lo, hi)
                 box.signal(pair_owner[p], p)  # every rank signals every validation, rows or not
 
             def finish_category(ci):
@@ -213,6 +208,21 @@ def run_sweep(v_gmm, v_nf, data: dict, rank: int = 0, world: int = 1, batch_size
                                         for j, key in enumerate(METRIC_KEYS) if packed[1, p, j] > 0}
     used = "one GPU" if one_gpu else ("peer" if box is not None else "exchange")
     return {"metrics": metrics, "images": n_images, "heads_per_image": 2, "transport": used}
+
+
+def delivery_plan(batch_sizes, owners, rank: int, base: int = 0) -> list:
+    """Where the rows a rank scored go in the evaluating rank's buffer.  A validation's rows are stored in global batch
+    order from row `base`; `rank` holds the rows of its own batches (owners[b] == rank) back to back in ascending batch
+    order.  → [(destination row, first local row, end local row)] per batch of `rank`: both sides derive it from the
+    dealing rule, nothing is negotiated."""
+    plan, lo, start = [], 0, int(base)
+    for size, owner in zip(batch_sizes, owners):
+        size = int(size)
+        if int(owner) == rank and size > 0:
+            plan.append((start, lo, lo + size))
+            lo += size
+        start += size
+    return plan
 
 
 def _mailbox(holder, data: dict, names: list, pair_owner: list, world: int, dev):
